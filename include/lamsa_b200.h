@@ -1,0 +1,193 @@
+/*
+ * lamsa_b200.h -- C ABI of liblamsa_b200.so, the B200 (sm_100a) replacement for
+ * the banded-DP hot path of LAMSA.
+ *
+ * Two layers are exported:
+ *
+ *  1. DROP-IN entry points.  Same names, argument meaning, ownership rules and
+ *     error behaviour as the reference prototypes, so that the reference's
+ *     callers (frag_check.c, split_mapping.c, bwt_aln.c) link against this
+ *     library instead of their own ksw.o without source changes.  Each
+ *     prototype cites the reference declaration it replaces (paths relative to
+ *     the reference tree).  Every DP cell is evaluated by the CUDA kernels in
+ *     lamsa_b200/csrc; there is NO CPU implementation behind these symbols and
+ *     they abort with a message on stderr when no sm_100 device is usable.
+ *
+ *  2. BATCH interface (lb2_*).  The producer side of "thousands of independent
+ *     DP tasks per launch": the caller describes tasks with plain pointers and
+ *     sizes, the library packs them, runs them on one GPU and hands back
+ *     scores, end points and CIGARs.  The drop-in symbols are thin wrappers
+ *     that submit a batch of one.
+ *
+ * Only plain C types cross this boundary (no torch / C++ types).
+ */
+#ifndef LAMSA_B200_H
+#define LAMSA_B200_H
+
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ types -- */
+
+#ifndef cigar32_t
+#define cigar32_t int32_t          /* src/lamsa_aln.h:210  (len<<4 | op)        */
+#endif
+
+/* BAM-style CIGAR operators: src/lamsa_aln.h:183-204 */
+enum { LB2_CMATCH = 0, LB2_CINS = 1, LB2_CDEL = 2, LB2_CREF_SKIP = 3,
+       LB2_CSOFT_CLIP = 4, LB2_CHARD_CLIP = 5 };
+
+/* Layout-identical restatement of `lamsa_aln_para` (src/lamsa_aln.h:384-432;
+ * 224 bytes on x86-64, offsets in SURVEY.md appendix B).  The layout is checked
+ * against the reference header by tests/test_abi.py through oracle/ref_shim.c.
+ * When the reference's own headers are in scope (a real drop-in link, where
+ * __LAMSA_ALN_H__-style guards already defined the type) define
+ * LAMSA_B200_NO_PARA_TYPE before including this header. */
+#ifndef LAMSA_B200_NO_PARA_TYPE
+typedef struct {
+    int n_thread;
+    int seed_len, seed_step, seed_inv;
+    int per_aln_m;
+    int first_loci_thd;
+    int SV_len_thd;
+    int ske_max;
+    float ovlp_rat;
+    int bwt_seed_len, bwt_max_len, bwt_min_len;
+    int fastest;
+    int split_len;
+    int split_pen;
+    int res_mul_max;
+    int hash_len, hash_key_len, hash_step, hash_size;
+    uint8_t supp_soft, comm;
+    FILE *outp;
+    int match_dis, mismatch_thd;
+    int del_thd; int ins_thd;
+    int *frag_score_table;
+    int ins_gapo, ins_gape, del_gapo, del_gape;      /* penalties of the global fill   */
+    int ins_ext_o, ins_ext_e, del_ext_o, del_ext_e;  /* penalties of the extension     */
+    int match, mis;
+    int8_t sc_mat[25];
+    int band_w, end_bonus, zdrop;
+    float ed_rate, mis_rate, id_rate, mat_rate;
+    int read_type;
+    uint8_t aln_mode;
+} lamsa_aln_para;
+#endif
+
+/* ------------------------------------------------- 1. drop-in entry points -- */
+
+/* replaces src/ksw.h:83 / src/ksw.c:543.  *cigar is malloc'd, caller frees.
+ * qlen<0 || tlen<0 -> message on stderr and exit(-1) (src/ksw.c:547-548). */
+int ksw_global2(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                int m, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
+                int w, int *n_cigar, cigar32_t **cigar);
+/* replaces src/ksw.h:82 / src/ksw.c:655 */
+int ksw_global(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+               int m, const int8_t *mat, int gapo, int gape,
+               int w, int *n_cigar, cigar32_t **cigar);
+/* replaces src/ksw.h:107 / src/ksw.c:387 (score-only extension) */
+int ksw_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                int m, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
+                int w, int end_bonus, int zdrop, int h0,
+                int *qle, int *tle, int *gtle, int *gscore, int *max_off);
+/* replaces src/ksw.h:106 / src/ksw.c:492 */
+int ksw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+               int m, const int8_t *mat, int gapo, int gape,
+               int w, int end_bonus, int zdrop, int h0,
+               int *qle, int *tle, int *gtle, int *gscore, int *max_off);
+/* replaces src/ksw.h:110 / src/ksw.c:667.  Reads ins_ext_o/e, del_ext_o/e,
+ * end_bonus, zdrop from AP.  Outputs are written only when n_cigar_ && cigar_
+ * (src/ksw.c:781); *cigar_ stays NULL with *n_cigar_==0 when nothing aligned. */
+int ksw_extend_core(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                    int m, const int8_t *mat, int w, int h0, lamsa_aln_para *AP,
+                    int *_qle, int *_tle, cigar32_t **cigar_, int *n_cigar_, int *m_cigar_);
+/* replaces src/ksw.h:114 / src/ksw.c:809: 0 query end reached, 1 target end, 2 neither */
+int ksw_extend_c(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                 int m, const int8_t *mat, int w, int h0, lamsa_aln_para *AP,
+                 int *_qle, int *_tle, cigar32_t **cigar_, int *n_cigar_, int *m_cigar_);
+/* replaces src/ksw.h:117 / src/ksw.c:820 (extension of the reversed pair) */
+int ksw_extend_r(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                 int m, const int8_t *mat, int w, int h0, lamsa_aln_para *AP,
+                 int *_qre, int *_tre, cigar32_t **cigar_, int *n_cigar_, int *m_cigar_);
+/* replaces src/ksw.h:123 / src/ksw.c:862 */
+int ksw_bi_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
+                  int m, const int8_t *mat, int lh0, int rh0, lamsa_aln_para *AP,
+                  cigar32_t **cigar_, int *n_cigar_, int *m_cigar_);
+/* replaces src/ksw.c:841 (extern-declared by src/frag_check.c:526) */
+void sw_mid_fix(cigar32_t **cigar, int *cigar_n, int *cigar_m,
+                cigar32_t *lcigar, int ln_cigar, cigar32_t *rcigar, int rn_cigar,
+                const uint8_t *query, int qlen, int lqe, int rqe,
+                const uint8_t *target, int tlen, int lte, int rte,
+                lamsa_aln_para *AP, int m, const int8_t *mat);
+
+/* ------------------------------------------------------ 2. batch interface -- */
+
+typedef struct lb2_ctx lb2_ctx;        /* one per (process, GPU) */
+typedef struct lb2_batch lb2_batch;    /* packed, device-resident task set */
+
+enum { LB2_KIND_GLOBAL = 0, LB2_KIND_EXTEND = 1 };
+enum { LB2_FLAG_CIGAR = 1 };           /* produce the traceback / CIGAR */
+
+/* One DP task.  `w` is the band as the CALLER would pass it to the reference;
+ * the adjustments of src/ksw.c:549 and :696-704 are applied by the library. */
+typedef struct {
+    int32_t kind;                 /* LB2_KIND_*                                  */
+    int32_t flags;                /* LB2_FLAG_*                                  */
+    int32_t qlen, tlen;
+    const uint8_t *query;         /* qlen codes 0..m-1, host memory              */
+    const uint8_t *target;        /* tlen codes 0..m-1, host memory              */
+    int32_t w;
+    int32_t h0;                   /* extension only, must be > 0                 */
+    int32_t o_del, e_del, o_ins, e_ins;
+    int32_t end_bonus, zdrop;     /* extension only                              */
+    int32_t m;                    /* alphabet size, 1..8                         */
+    const int8_t *mat;            /* m*m scores, host memory                     */
+} lb2_task;
+
+typedef struct {
+    int32_t score;                /* global: H(tlen-1,qlen-1); extend: best      */
+    int32_t qle, tle;             /* extend: end point chosen by src/ksw.c:785-791
+                                     (with LB2_FLAG_CIGAR) or max_j+1,max_i+1    */
+    int32_t gtle, gscore, max_off;/* extend: src/ksw.c:484-488                   */
+    int32_t n_cigar;              /* number of CIGAR words                       */
+    int32_t reserved;
+    int64_t cigar_off;            /* first word inside the batch's CIGAR pool    */
+    int64_t cells;                /* inner-loop bodies evaluated     */
+} lb2_result;
+
+/* All functions return 0 on success, non-zero on error (message via lb2_last_error). */
+int  lb2_ctx_create(int device, lb2_ctx **out);
+void lb2_ctx_destroy(lb2_ctx *ctx);
+const char *lb2_last_error(void);
+/* cap on device scratch used for direction bits per launch wave (bytes) */
+int  lb2_ctx_set_scratch_limit(lb2_ctx *ctx, uint64_t bytes);
+
+/* One-shot: host tasks in, host results out (pack + H2D + kernels + D2H).
+ * `*cigar_pool` is malloc'd (caller frees with lb2_free); result i owns words
+ * [cigar_off, cigar_off+n_cigar). */
+int  lb2_dp_run(lb2_ctx *ctx, int64_t n, const lb2_task *tasks, lb2_result *results,
+                cigar32_t **cigar_pool, int64_t *cigar_pool_n);
+
+/* Staged form used by the benchmark and by pipelined producers. */
+int  lb2_batch_create(lb2_ctx *ctx, int64_t n, const lb2_task *tasks, lb2_batch **out); /* pack to pinned host */
+int  lb2_batch_upload(lb2_batch *b);                       /* H2D, async on the ctx stream */
+int  lb2_batch_compute(lb2_batch *b, float *kernel_ms);    /* fill + traceback kernels; CUDA-event ms or NULL */
+int  lb2_batch_download(lb2_batch *b, lb2_result *results,
+                        cigar32_t **cigar_pool, int64_t *cigar_pool_n);
+int  lb2_batch_stats(const lb2_batch *b, int64_t *h2d_bytes, int64_t *d2h_bytes,
+                     int64_t *launches, float *fill_ms, float *trace_ms);
+void lb2_batch_destroy(lb2_batch *b);
+void lb2_free(void *p);
+
+/* Integer-pipe issue-rate microbenchmark: returns measured G(int16 lane-ops)/s
+ * for the s16x2 DPX max/add chain the fill kernels are built from. */
+int  lb2_int_peak(lb2_ctx *ctx, double *gops_s16x2, double *gops_s32, int *sm_count, int *clock_khz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAMSA_B200_H */

@@ -1,0 +1,121 @@
+"""ctypes view of include/lamsa_b200.h (structs, constants, library loading)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblamsa_b200.so")
+
+KIND_GLOBAL, KIND_EXTEND = 0, 1
+FLAG_CIGAR = 1
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+# lb2_task / lb2_result as numpy structured dtypes (C layout, x86-64)
+TASK_DTYPE = np.dtype([
+    ("kind", "<i4"), ("flags", "<i4"), ("qlen", "<i4"), ("tlen", "<i4"),
+    ("query", "<u8"), ("target", "<u8"),
+    ("w", "<i4"), ("h0", "<i4"), ("o_del", "<i4"), ("e_del", "<i4"), ("o_ins", "<i4"), ("e_ins", "<i4"),
+    ("end_bonus", "<i4"), ("zdrop", "<i4"), ("m", "<i4"), ("_pad", "<i4"), ("mat", "<u8"),
+], align=True)
+assert TASK_DTYPE.itemsize == 80
+
+RESULT_DTYPE = np.dtype([
+    ("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"), ("gscore", "<i4"),
+    ("max_off", "<i4"), ("n_cigar", "<i4"), ("m_cigar", "<i4"), ("cigar_off", "<i8"), ("cells", "<i8"),
+], align=True)
+assert RESULT_DTYPE.itemsize == 48
+
+
+class AlnPara(C.Structure):
+    """Mirror of `lamsa_aln_para` (reference src/lamsa_aln.h:384-432), same field order."""
+    _fields_ = [
+        ("n_thread", C.c_int),
+        ("seed_len", C.c_int), ("seed_step", C.c_int), ("seed_inv", C.c_int),
+        ("per_aln_m", C.c_int), ("first_loci_thd", C.c_int),
+        ("SV_len_thd", C.c_int), ("ske_max", C.c_int), ("ovlp_rat", C.c_float),
+        ("bwt_seed_len", C.c_int), ("bwt_max_len", C.c_int), ("bwt_min_len", C.c_int),
+        ("fastest", C.c_int),
+        ("split_len", C.c_int), ("split_pen", C.c_int), ("res_mul_max", C.c_int),
+        ("hash_len", C.c_int), ("hash_key_len", C.c_int), ("hash_step", C.c_int), ("hash_size", C.c_int),
+        ("supp_soft", C.c_uint8), ("comm", C.c_uint8),
+        ("outp", C.c_void_p),
+        ("match_dis", C.c_int), ("mismatch_thd", C.c_int),
+        ("del_thd", C.c_int), ("ins_thd", C.c_int),
+        ("frag_score_table", C.c_void_p),
+        ("ins_gapo", C.c_int), ("ins_gape", C.c_int), ("del_gapo", C.c_int), ("del_gape", C.c_int),
+        ("ins_ext_o", C.c_int), ("ins_ext_e", C.c_int), ("del_ext_o", C.c_int), ("del_ext_e", C.c_int),
+        ("match", C.c_int), ("mis", C.c_int),
+        ("sc_mat", C.c_int8 * 25),
+        ("band_w", C.c_int), ("end_bonus", C.c_int), ("zdrop", C.c_int),
+        ("ed_rate", C.c_float), ("mis_rate", C.c_float), ("id_rate", C.c_float), ("mat_rate", C.c_float),
+        ("read_type", C.c_int),
+        ("aln_mode", C.c_uint8),
+    ]
+
+
+# order of oracle/ref_shim.c:ref_para_offsets
+PARA_FIELDS = [
+    "n_thread", "seed_len", "seed_step", "seed_inv", "per_aln_m", "first_loci_thd", "SV_len_thd", "ske_max",
+    "ovlp_rat", "split_len", "split_pen", "res_mul_max", "match_dis", "mismatch_thd", "frag_score_table",
+    "ins_gapo", "ins_gape", "del_gapo", "del_gape", "ins_ext_o", "ins_ext_e", "del_ext_o", "del_ext_e",
+    "match", "mis", "sc_mat", "band_w", "end_bonus", "zdrop", "ed_rate", "mis_rate", "id_rate", "mat_rate",
+    "read_type", "aln_mode",
+]
+
+# every symbol include/lamsa_b200.h declares
+EXPORTS = [
+    "ksw_global2", "ksw_global", "ksw_extend2", "ksw_extend", "ksw_extend_core", "ksw_extend_c",
+    "ksw_extend_r", "ksw_bi_extend", "sw_mid_fix",
+    "lb2_ctx_create", "lb2_ctx_destroy", "lb2_last_error", "lb2_ctx_set_scratch_limit", "lb2_dp_run",
+    "lb2_batch_create", "lb2_batch_upload", "lb2_batch_compute", "lb2_batch_download", "lb2_batch_stats",
+    "lb2_batch_destroy", "lb2_free", "lb2_int_peak",
+]
+
+_lib = None
+
+
+def load_library():
+    """Load liblamsa_b200.so; raises LibraryMissing (never falls back to a CPU path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU implementation to fall back to)")
+    lib = C.CDLL(LIB_PATH)
+    P, I, I64 = C.c_void_p, C.c_int, C.c_int64
+    lib.lb2_last_error.restype = C.c_char_p
+    lib.lb2_ctx_create.argtypes = [I, C.POINTER(P)]
+    lib.lb2_ctx_destroy.argtypes = [P]
+    lib.lb2_ctx_destroy.restype = None
+    lib.lb2_ctx_set_scratch_limit.argtypes = [P, C.c_uint64]
+    lib.lb2_dp_run.argtypes = [P, I64, P, P, C.POINTER(P), C.POINTER(I64)]
+    lib.lb2_batch_create.argtypes = [P, I64, P, C.POINTER(P)]
+    lib.lb2_batch_upload.argtypes = [P]
+    lib.lb2_batch_compute.argtypes = [P, C.POINTER(C.c_float)]
+    lib.lb2_batch_download.argtypes = [P, P, C.POINTER(P), C.POINTER(I64)]
+    lib.lb2_batch_stats.argtypes = [P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64),
+                                    C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.lb2_batch_destroy.argtypes = [P]
+    lib.lb2_batch_destroy.restype = None
+    lib.lb2_free.argtypes = [P]
+    lib.lb2_free.restype = None
+    lib.lb2_int_peak.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(I), C.POINTER(I)]
+    u8p, i8p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_int8), C.POINTER(I)
+    cpp = C.POINTER(C.POINTER(C.c_int32))
+    app = C.POINTER(AlnPara)
+    lib.ksw_global2.argtypes = [I, u8p, I, u8p, I, i8p, I, I, I, I, I, ip, cpp]
+    lib.ksw_global.argtypes = [I, u8p, I, u8p, I, i8p, I, I, I, ip, cpp]
+    lib.ksw_extend2.argtypes = [I, u8p, I, u8p, I, i8p, I, I, I, I, I, I, I, I, ip, ip, ip, ip, ip]
+    lib.ksw_extend.argtypes = [I, u8p, I, u8p, I, i8p, I, I, I, I, I, I, ip, ip, ip, ip, ip]
+    for name in ("ksw_extend_core", "ksw_extend_c", "ksw_extend_r"):
+        getattr(lib, name).argtypes = [I, u8p, I, u8p, I, i8p, I, I, app, ip, ip, cpp, ip, ip]
+    lib.ksw_bi_extend.argtypes = [I, u8p, I, u8p, I, i8p, I, I, app, cpp, ip, ip]
+    _lib = lib
+    return lib

@@ -1,0 +1,537 @@
+// dp_batch.cu -- host side of the batch interface declared in include/lamsa_b200.h:
+// packs DP tasks, sizes the direction scratch, launches the fill / traceback
+// kernels class by class, and unpacks results.  No DP arithmetic happens here.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/lamsa_b200.h"
+#include "dp_fill.cuh"
+#include "dp_trace.cuh"
+#include "int_peak.cuh"
+
+using namespace lb2;
+
+// ------------------------------------------------------------------ errors --
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
+    return fail("%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); } while (0)
+
+extern "C" const char* lb2_last_error(void) { return g_err.c_str(); }
+extern "C" void lb2_free(void* p) { free(p); }
+
+// ----------------------------------------------------------------- context --
+constexpr int kNumCS = 6;                    // columns per lane: 1,2,4,8,16,32
+constexpr int kNumClass = 2 * kNumCS;        // x {global, extend}
+
+struct lb2_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t scratch_limit = 0;
+    uint8_t* d_z = nullptr;    size_t z_cap = 0;        // direction nibbles (+ row bands)
+    int32_t* d_ctmp = nullptr; size_t ctmp_cap = 0;     // per-task reversed CIGAR scratch (words)
+    int occ[kNumClass] = {0};
+};
+
+typedef void (*fill_fn)(const DTask*, const int32_t*, int, const uint8_t*, uint8_t*, DResult*,
+                        const uint2*, unsigned int*);
+static fill_fn fill_table(int cls) {
+    switch (cls) {
+        case 0: return fill_kernel<1, kKindGlobal>;   case 1: return fill_kernel<2, kKindGlobal>;
+        case 2: return fill_kernel<4, kKindGlobal>;   case 3: return fill_kernel<8, kKindGlobal>;
+        case 4: return fill_kernel<16, kKindGlobal>;  case 5: return fill_kernel<32, kKindGlobal>;
+        case 6: return fill_kernel<1, kKindExtend>;   case 7: return fill_kernel<2, kKindExtend>;
+        case 8: return fill_kernel<4, kKindExtend>;   case 9: return fill_kernel<8, kKindExtend>;
+        case 10: return fill_kernel<16, kKindExtend>; default: return fill_kernel<32, kKindExtend>;
+    }
+}
+
+extern "C" int lb2_ctx_create(int device, lb2_ctx** out) {
+    if (!out) return fail("lb2_ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("lb2_ctx_create: no CUDA device (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return fail("lb2_ctx_create: device %d of %d", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("lb2_ctx_create: device %d is sm_%d%d, need sm_100", device, prop.major, prop.minor);
+    lb2_ctx* c = new lb2_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    size_t fr = 0, tot = 0;
+    CU(cudaMemGetInfo(&fr, &tot));
+    c->scratch_limit = (uint64_t)(fr * 0.40);
+    for (int k = 0; k < kNumClass; ++k) {
+        int nb = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fill_table(k), 128, 0));
+        c->occ[k] = nb > 0 ? nb : 1;
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" void lb2_ctx_destroy(lb2_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->d_z) cudaFree(c->d_z);
+    if (c->d_ctmp) cudaFree(c->d_ctmp);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int lb2_ctx_set_scratch_limit(lb2_ctx* c, uint64_t bytes) {
+    if (!c) return fail("ctx is NULL");
+    c->scratch_limit = bytes < (1u << 20) ? (1u << 20) : bytes;
+    return 0;
+}
+
+// ------------------------------------------------------------------- batch --
+struct Wave {
+    int cls_off[kNumClass + 1];      // ranges inside `order`, by class
+    int first, count;                // range inside `order`
+    uint64_t z_bytes, ctmp_words;
+};
+
+struct lb2_batch {
+    lb2_ctx* ctx = nullptr;
+    int64_t n = 0;
+    // pinned host staging
+    uint8_t* h_pool = nullptr;  size_t pool_bytes = 0;
+    DTask* h_tasks = nullptr;
+    int32_t* h_order = nullptr;
+    uint2* h_mats = nullptr;
+    DResult* h_results = nullptr;
+    // device
+    uint8_t* d_pool = nullptr;
+    DTask* d_tasks = nullptr;
+    int32_t* d_order = nullptr;
+    uint2* d_mats = nullptr;
+    DResult* d_results = nullptr;
+    int32_t* d_cdense = nullptr;  uint64_t dense_cap = 0;
+    unsigned long long* d_cursor = nullptr;
+    unsigned int* d_counters = nullptr;  int n_counters = 0;
+    int* d_err = nullptr;
+    std::vector<Wave> waves;
+    std::vector<uint8_t> flags;      // per task: LB2_FLAG_*
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t h2d_bytes = 0, d2h_bytes = 0, launches = 0;
+    float fill_ms = 0, trace_ms = 0;
+    bool uploaded = false, computed = false;
+};
+
+// src/ksw.c:696-704 -- double division, truncation toward zero
+static int extend_band(int w, int qlen, int m, const int8_t* mat, int end_bonus,
+                       int o_del, int e_del, int o_ins, int e_ins) {
+    int best = 0;
+    for (int a = 0; a < m * m; ++a) best = best > mat[a] ? best : mat[a];
+    int lim = (int)((double)(qlen * best + end_bonus - o_ins) / e_ins + 1.);
+    lim = lim > 1 ? lim : 1;
+    w = w < lim ? w : lim;
+    lim = (int)((double)(qlen * best + end_bonus - o_del) / e_del + 1.);
+    lim = lim > 1 ? lim : 1;
+    w = w < lim ? w : lim;
+    return w;
+}
+
+static int pick_cshift(int qlen, int w) {
+    for (int cs = 0; cs < kNumCS; ++cs) {
+        const long C = 1L << cs;
+        if ((long)qlen + 1 <= 32 * C || 31 * C >= 2L * w + 1) return cs;
+    }
+    return -1;
+}
+
+extern "C" void lb2_batch_destroy(lb2_batch* b) {
+    if (!b) return;
+    if (b->ctx) cudaSetDevice(b->ctx->device);
+    cudaFreeHost(b->h_pool); cudaFreeHost(b->h_tasks); cudaFreeHost(b->h_order);
+    cudaFreeHost(b->h_mats); cudaFreeHost(b->h_results);
+    cudaFree(b->d_pool); cudaFree(b->d_tasks); cudaFree(b->d_order); cudaFree(b->d_mats);
+    cudaFree(b->d_results); cudaFree(b->d_cdense); cudaFree(b->d_cursor);
+    cudaFree(b->d_counters); cudaFree(b->d_err);
+    for (auto& e : b->ev) if (e) cudaEventDestroy(e);
+    delete b;
+}
+
+static unsigned hw_threads() {
+    unsigned t = std::thread::hardware_concurrency();
+    const char* env = getenv("LB2_HOST_THREADS");
+    if (env && atoi(env) > 0) t = (unsigned)atoi(env);
+    if (t == 0) t = 1;
+    return t > 32 ? 32 : t;
+}
+
+template <class F>
+static void parallel_for(int64_t n, F f) {
+    unsigned nt = hw_threads();
+    if (n < 4096 || nt == 1) { f(0, n); return; }
+    std::vector<std::thread> th;
+    const int64_t step = (n + nt - 1) / nt;
+    for (unsigned k = 0; k < nt; ++k) {
+        const int64_t a = k * step, e = std::min<int64_t>(n, a + step);
+        if (a >= e) break;
+        th.emplace_back([=] { f(a, e); });
+    }
+    for (auto& t : th) t.join();
+}
+
+extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_batch** out) {
+    if (!ctx || !out || (n > 0 && !tasks)) return fail("lb2_batch_create: NULL argument");
+    if (n < 0 || n > (int64_t)1 << 30) return fail("lb2_batch_create: n=%lld out of range", (long long)n);
+    CU(cudaSetDevice(ctx->device));
+    lb2_batch* b = new lb2_batch();
+    b->ctx = ctx; b->n = n;
+    struct Guard { lb2_batch* b; bool ok = false; ~Guard() { if (!ok) lb2_batch_destroy(b); } } guard{b};
+
+    // ---- pass 1: validate, classify, lay out pool / scratch
+    std::vector<uint64_t> qoff(n), toff(n), zsz(n);
+    std::vector<int32_t> wfin(n), ctmpw(n);
+    std::vector<int8_t> cshift(n), matid(n);
+    std::vector<std::vector<int8_t>> mats;           // distinct matrices, each 64 entries (8x8, zero padded)
+    b->flags.resize(n);
+    uint64_t pool = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const lb2_task& t = tasks[i];
+        if (t.qlen < 0 || t.tlen < 0) return fail("task %lld: qlen %d tlen %d", (long long)i, t.qlen, t.tlen);
+        if (t.kind != LB2_KIND_GLOBAL && t.kind != LB2_KIND_EXTEND) return fail("task %lld: kind %d", (long long)i, t.kind);
+        if (t.m < 1 || t.m > 8 || !t.mat) return fail("task %lld: alphabet size %d unsupported (1..8)", (long long)i, t.m);
+        if ((t.qlen && !t.query) || (t.tlen && !t.target)) return fail("task %lld: NULL sequence", (long long)i);
+        if (t.e_del <= 0 || t.e_ins <= 0) return fail("task %lld: gap extension penalties must be > 0", (long long)i);
+        int w = t.w;
+        if (t.kind == LB2_KIND_GLOBAL) {
+            const int dl = std::abs(t.qlen - t.tlen);
+            w = dl + 3 < w ? w : dl + 3;                                  // src/ksw.c:549
+        } else {
+            if (t.h0 <= 0) return fail("task %lld: h0 must be > 0 (src/ksw.c:682)", (long long)i);
+            w = extend_band(w, t.qlen, t.m, t.mat, t.end_bonus, t.o_del, t.e_del, t.o_ins, t.e_ins);
+        }
+        if (w < 0) return fail("task %lld: negative band", (long long)i);
+        wfin[i] = w;
+        const int cs = pick_cshift(t.qlen, w);
+        if (cs < 0) return fail("task %lld: qlen %d with band %d exceeds the single-warp kernels", (long long)i, t.qlen, w);
+        cshift[i] = (int8_t)cs;
+        // matrix table
+        int8_t m8[64]; memset(m8, 0, sizeof m8);
+        for (int a = 0; a < t.m; ++a) for (int c = 0; c < t.m; ++c) m8[a * 8 + c] = t.mat[a * t.m + c];
+        int id = -1;
+        for (size_t k = 0; k < mats.size(); ++k) if (!memcmp(mats[k].data(), m8, 64)) { id = (int)k; break; }
+        if (id < 0) {
+            if ((int)mats.size() == kMaxMats) return fail("more than %d distinct scoring matrices in one batch", kMaxMats);
+            mats.emplace_back(m8, m8 + 64); id = (int)mats.size() - 1;
+        }
+        matid[i] = (int8_t)id;
+        b->flags[i] = (uint8_t)t.flags;
+        qoff[i] = pool; pool += ((uint64_t)t.qlen + 1 + 31) & ~uint64_t(31);
+        toff[i] = pool; pool += ((uint64_t)t.tlen + 31) & ~uint64_t(31);
+        if (t.flags & LB2_FLAG_CIGAR) {
+            const int C = 1 << cs;
+            const long ncol = std::min<long>(t.qlen, 2L * w + 1);
+            const int rw = row_chunks_for((int)ncol, C);
+            uint64_t z = (uint64_t)t.tlen * rw * dir_chunk_bytes(C);
+            if (t.kind == LB2_KIND_EXTEND) z += ext_meta_bytes(t.tlen);
+            zsz[i] = (z + 15) & ~uint64_t(15);
+            ctmpw[i] = t.qlen + t.tlen + 2;
+        } else { zsz[i] = 0; ctmpw[i] = 0; }
+    }
+    if (pool >> 37) return fail("sequence pool of %llu bytes is too large for one batch", (unsigned long long)pool);
+
+    // ---- waves: consecutive tasks whose scratch fits the limit, then class/cost order inside a wave
+    b->pool_bytes = pool + 64;
+    CU(cudaMallocHost(&b->h_pool, b->pool_bytes));
+    CU(cudaMallocHost(&b->h_tasks, sizeof(DTask) * std::max<int64_t>(n, 1)));
+    CU(cudaMallocHost(&b->h_order, sizeof(int32_t) * std::max<int64_t>(n, 1)));
+    CU(cudaMallocHost(&b->h_mats, sizeof(uint2) * kMaxMats * 8));
+    CU(cudaMallocHost(&b->h_results, sizeof(DResult) * std::max<int64_t>(n, 1)));
+    memset(b->h_mats, 0, sizeof(uint2) * kMaxMats * 8);
+    for (size_t k = 0; k < mats.size(); ++k)
+        for (int r = 0; r < 8; ++r) memcpy(&b->h_mats[k * 8 + r], mats[k].data() + r * 8, 8);
+
+    const uint64_t zlimit = ctx->scratch_limit;
+    uint64_t dense = 0;
+    {
+        int64_t i = 0;
+        while (i < n) {
+            Wave wv; wv.first = (int)i; wv.z_bytes = 0; wv.ctmp_words = 0;
+            int64_t j = i;
+            while (j < n) {
+                const uint64_t nz = wv.z_bytes + zsz[j], nc = wv.ctmp_words + (uint64_t)ctmpw[j];
+                if (j > i && nz + nc * 4 > zlimit) break;
+                wv.z_bytes = nz; wv.ctmp_words = nc; ++j;
+            }
+            if (wv.z_bytes + wv.ctmp_words * 4 > zlimit && zlimit < (uint64_t)1 << 36)
+                ; // a single task larger than the limit still runs alone
+            wv.count = (int)(j - i);
+            dense += wv.ctmp_words;
+            b->waves.push_back(wv);
+            i = j;
+        }
+    }
+    // order + per-wave offsets
+    for (auto& wv : b->waves) {
+        std::vector<int32_t> idx(wv.count);
+        for (int k = 0; k < wv.count; ++k) idx[k] = wv.first + k;
+        auto cls = [&](int32_t a) { return (int)tasks[a].kind * kNumCS + cshift[a]; };
+        auto cost = [&](int32_t a) {
+            return (int64_t)tasks[a].tlen * std::min<int64_t>(tasks[a].qlen, 2L * wfin[a] + 1);
+        };
+        std::sort(idx.begin(), idx.end(), [&](int32_t a, int32_t c) {
+            const int ca = cls(a), cc = cls(c);
+            if (ca != cc) return ca < cc;
+            const int64_t xa = cost(a), xc = cost(c);
+            if (xa != xc) return xa > xc;
+            return a < c;
+        });
+        int pos = 0;
+        for (int c = 0; c < kNumClass; ++c) {
+            wv.cls_off[c] = pos;
+            while (pos < wv.count && cls(idx[pos]) == c) ++pos;
+        }
+        wv.cls_off[kNumClass] = pos;
+        memcpy(b->h_order + wv.first, idx.data(), sizeof(int32_t) * wv.count);
+        uint64_t z = 0, cw = 0;
+        for (int k = 0; k < wv.count; ++k) {          // scratch offsets follow the original order
+            const int64_t a = wv.first + k;
+            DTask& d = b->h_tasks[a];
+            d.z_off = z; z += zsz[a];
+            cw += (uint64_t)ctmpw[a]; d.ctmp_end = cw; d.ctmp_cap = ctmpw[a];
+        }
+    }
+    // ---- pass 2: fill descriptors and copy sequences (parallel)
+    uint8_t* hp = b->h_pool;
+    DTask* ht = b->h_tasks;
+    parallel_for(n, [&, hp, ht](int64_t a, int64_t e) {
+        for (int64_t i = a; i < e; ++i) {
+            const lb2_task& t = tasks[i];
+            DTask& d = ht[i];
+            d.q_off32 = (uint32_t)(qoff[i] >> 5); d.t_off32 = (uint32_t)(toff[i] >> 5);
+            d.qlen = t.qlen; d.tlen = t.tlen; d.w = wfin[i]; d.h0 = t.h0;
+            d.o_del = t.o_del; d.e_del = t.e_del; d.o_ins = t.o_ins; d.e_ins = t.e_ins;
+            d.end_bonus = t.end_bonus; d.zdrop = t.zdrop;
+            d.kind = (uint8_t)t.kind; d.want_dir = (t.flags & LB2_FLAG_CIGAR) ? 1 : 0;
+            d.mat_id = (uint8_t)matid[i]; d.cshift = (uint8_t)cshift[i];
+            const long ncol = std::min<long>(t.qlen, 2L * wfin[i] + 1);
+            d.row_chunks = row_chunks_for((int)ncol, 1 << cshift[i]);
+            d.pad = 0;
+            uint8_t* q = hp + qoff[i];
+            const uint64_t qp = ((uint64_t)t.qlen + 1 + 31) & ~uint64_t(31);
+            if (t.qlen) memcpy(q, t.query, t.qlen);
+            memset(q + t.qlen, 0, qp - t.qlen);
+            uint8_t* tt = hp + toff[i];
+            const uint64_t tp = ((uint64_t)t.tlen + 31) & ~uint64_t(31);
+            if (t.tlen) memcpy(tt, t.target, t.tlen);
+            memset(tt + t.tlen, 0, tp - t.tlen);
+        }
+    });
+
+    // ---- device allocations
+    const int64_t n1 = std::max<int64_t>(n, 1);
+    CU(cudaMalloc(&b->d_pool, b->pool_bytes));
+    CU(cudaMalloc(&b->d_tasks, sizeof(DTask) * n1));
+    CU(cudaMalloc(&b->d_order, sizeof(int32_t) * n1));
+    CU(cudaMalloc(&b->d_mats, sizeof(uint2) * kMaxMats * 8));
+    CU(cudaMalloc(&b->d_results, sizeof(DResult) * n1));
+    b->dense_cap = dense + 16;
+    CU(cudaMalloc(&b->d_cdense, sizeof(int32_t) * b->dense_cap));
+    CU(cudaMalloc(&b->d_cursor, sizeof(unsigned long long)));
+    b->n_counters = (int)b->waves.size() * kNumClass + 1;
+    CU(cudaMalloc(&b->d_counters, sizeof(unsigned int) * b->n_counters));
+    CU(cudaMalloc(&b->d_err, sizeof(int)));
+    for (auto& e : b->ev) CU(cudaEventCreate(&e));
+    // grow the context's scratch
+    uint64_t zmax = 16, cmax = 16;
+    for (auto& wv : b->waves) { zmax = std::max(zmax, wv.z_bytes); cmax = std::max(cmax, wv.ctmp_words); }
+    if (ctx->z_cap < zmax) {
+        if (ctx->d_z) CU(cudaFree(ctx->d_z));
+        ctx->d_z = nullptr; ctx->z_cap = 0;
+        CU(cudaMalloc(&ctx->d_z, zmax + 64)); ctx->z_cap = zmax;
+    }
+    if (ctx->ctmp_cap < cmax) {
+        if (ctx->d_ctmp) CU(cudaFree(ctx->d_ctmp));
+        ctx->d_ctmp = nullptr; ctx->ctmp_cap = 0;
+        CU(cudaMalloc(&ctx->d_ctmp, (cmax + 16) * 4)); ctx->ctmp_cap = cmax;
+    }
+    guard.ok = true;
+    *out = b;
+    return 0;
+}
+
+extern "C" int lb2_batch_upload(lb2_batch* b) {
+    if (!b) return fail("batch is NULL");
+    lb2_ctx* c = b->ctx;
+    CU(cudaSetDevice(c->device));
+    const int64_t n1 = std::max<int64_t>(b->n, 1);
+    CU(cudaMemcpyAsync(b->d_pool, b->h_pool, b->pool_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(b->d_tasks, b->h_tasks, sizeof(DTask) * n1, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(b->d_order, b->h_order, sizeof(int32_t) * n1, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(b->d_mats, b->h_mats, sizeof(uint2) * kMaxMats * 8, cudaMemcpyHostToDevice, c->stream));
+    b->h2d_bytes = (int64_t)b->pool_bytes + (int64_t)(sizeof(DTask) + 4) * n1 + (int64_t)sizeof(uint2) * kMaxMats * 8;
+    b->uploaded = true;
+    return 0;
+}
+
+extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
+    if (!b) return fail("batch is NULL");
+    if (!b->uploaded) return fail("lb2_batch_compute before lb2_batch_upload");
+    lb2_ctx* c = b->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    CU(cudaMemsetAsync(b->d_cursor, 0, sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned int) * b->n_counters, s));
+    CU(cudaMemsetAsync(b->d_err, 0, sizeof(int), s));
+    b->launches = 0; b->fill_ms = 0; b->trace_ms = 0;
+    CU(cudaEventRecord(b->ev[0], s));
+    float fill_acc = 0, trace_acc = 0;
+    const bool one_wave = b->waves.size() == 1;
+    for (size_t wi = 0; wi < b->waves.size(); ++wi) {
+        const Wave& wv = b->waves[wi];
+        if (!one_wave) CU(cudaEventRecord(b->ev[1], s));
+        for (int k = 0; k < kNumClass; ++k) {
+            const int cnt = wv.cls_off[k + 1] - wv.cls_off[k];
+            if (!cnt) continue;
+            int grid = (cnt + 3) / 4;
+            const int cap = c->sm_count * c->occ[k];
+            if (grid > cap) grid = cap;
+            fill_table(k)<<<grid, 128, 0, s>>>(b->d_tasks, b->d_order + wv.first + wv.cls_off[k], cnt,
+                                               b->d_pool, c->d_z, b->d_results, b->d_mats,
+                                               b->d_counters + wi * kNumClass + k);
+            CU(cudaGetLastError());
+            ++b->launches;
+        }
+        CU(cudaEventRecord(b->ev[2], s));
+        if (wv.ctmp_words) {
+            trace_kernel<<<(wv.count + 127) / 128, 128, 0, s>>>(b->d_tasks, b->d_order + wv.first, wv.count,
+                                                                c->d_z, b->d_results, c->d_ctmp, b->d_cdense,
+                                                                b->d_cursor, b->dense_cap, b->d_err);
+            CU(cudaGetLastError());
+            ++b->launches;
+        }
+        CU(cudaEventRecord(b->ev[3], s));
+        if (!one_wave) {      // per-wave split needs a sync; only taken when scratch forces several waves
+            CU(cudaEventSynchronize(b->ev[3]));
+            float a = 0, t = 0;
+            CU(cudaEventElapsedTime(&a, b->ev[1], b->ev[2]));
+            CU(cudaEventElapsedTime(&t, b->ev[2], b->ev[3]));
+            fill_acc += a; trace_acc += t;
+        }
+    }
+    CU(cudaEventSynchronize(b->ev[3]));
+    float total = 0;
+    CU(cudaEventElapsedTime(&total, b->ev[0], b->ev[3]));
+    if (one_wave) {
+        CU(cudaEventElapsedTime(&fill_acc, b->ev[0], b->ev[2]));
+        CU(cudaEventElapsedTime(&trace_acc, b->ev[2], b->ev[3]));
+    }
+    b->fill_ms = fill_acc; b->trace_ms = trace_acc;
+    if (kernel_ms) *kernel_ms = total;
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, b->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (err) return fail("traceback kernel reported CIGAR scratch overflow (code %d)", err);
+    b->computed = true;
+    return 0;
+}
+
+static int cigar_capacity(int n) {      // capacity after the doubling pushes of src/ksw.c:506-516
+    if (n == 0) return 0;
+    int m = 4; while (m < n) m <<= 1; return m;
+}
+
+extern "C" int lb2_batch_download(lb2_batch* b, lb2_result* results, cigar32_t** cigar_pool, int64_t* cigar_pool_n) {
+    if (!b || (b->n && !results)) return fail("lb2_batch_download: NULL argument");
+    if (!b->computed) return fail("lb2_batch_download before lb2_batch_compute");
+    lb2_ctx* c = b->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    unsigned long long used = 0;
+    CU(cudaMemcpyAsync(&used, b->d_cursor, sizeof used, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(b->h_results, b->d_results, sizeof(DResult) * std::max<int64_t>(b->n, 1), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    cigar32_t* pool = nullptr;
+    if (cigar_pool) {
+        pool = (cigar32_t*)malloc(sizeof(cigar32_t) * (used ? used : 1));
+        if (!pool) return fail("out of host memory for %llu CIGAR words", used);
+        if (used) {
+            CU(cudaMemcpyAsync(pool, b->d_cdense, sizeof(cigar32_t) * used, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+        }
+        *cigar_pool = pool;
+    }
+    if (cigar_pool_n) *cigar_pool_n = (int64_t)used;
+    b->d2h_bytes = (int64_t)sizeof(DResult) * b->n + (cigar_pool ? (int64_t)used * 4 : 0) + 8;
+    const DResult* hr = b->h_results;
+    const DTask* ht = b->h_tasks;
+    const uint8_t* fl = b->flags.data();
+    parallel_for(b->n, [=](int64_t a, int64_t e) {
+        for (int64_t i = a; i < e; ++i) {
+            const DResult& r = hr[i];
+            lb2_result& o = results[i];
+            o.score = r.score;
+            if (ht[i].kind == kKindExtend) {
+                if (fl[i] & LB2_FLAG_CIGAR) { o.qle = r.tk + 1; o.tle = r.ti + 1; }
+                else { o.qle = r.max_j + 1; o.tle = r.max_i + 1; }
+                o.gtle = r.max_ie + 1; o.gscore = r.gscore; o.max_off = r.max_off;
+            } else {
+                o.qle = ht[i].qlen; o.tle = ht[i].tlen; o.gtle = 0; o.gscore = 0; o.max_off = 0;
+            }
+            o.n_cigar = r.n_cigar; o.reserved = cigar_capacity(r.n_cigar);
+            o.cigar_off = r.cigar_off; o.cells = r.cells;
+        }
+    });
+    return 0;
+}
+
+extern "C" int lb2_batch_stats(const lb2_batch* b, int64_t* h2d, int64_t* d2h, int64_t* launches,
+                               float* fill_ms, float* trace_ms) {
+    if (!b) return fail("batch is NULL");
+    if (h2d) *h2d = b->h2d_bytes;
+    if (d2h) *d2h = b->d2h_bytes;
+    if (launches) *launches = b->launches;
+    if (fill_ms) *fill_ms = b->fill_ms;
+    if (trace_ms) *trace_ms = b->trace_ms;
+    return 0;
+}
+
+extern "C" int lb2_dp_run(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_result* results,
+                          cigar32_t** cigar_pool, int64_t* cigar_pool_n) {
+    lb2_batch* b = nullptr;
+    if (lb2_batch_create(ctx, n, tasks, &b)) return 1;
+    int rc = lb2_batch_upload(b);
+    if (!rc) rc = lb2_batch_compute(b, nullptr);
+    if (!rc) rc = lb2_batch_download(b, results, cigar_pool, cigar_pool_n);
+    lb2_batch_destroy(b);
+    return rc;
+}
+
+extern "C" int lb2_int_peak(lb2_ctx* ctx, double* gops_s16x2, double* gops_s32, int* sm_count, int* clock_khz) {
+    if (!ctx) return fail("ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+    if (clock_khz) *clock_khz = khz;
+    double a = 0, c = 0;
+    if (int_peak_measure(ctx->stream, prop.multiProcessorCount, &a, &c)) return fail("int_peak: %s", cudaGetErrorString(cudaGetLastError()));
+    if (gops_s16x2) *gops_s16x2 = a;
+    if (gops_s32) *gops_s32 = c;
+    return 0;
+}

@@ -1,0 +1,59 @@
+// dp_device.cuh -- device-side data layout shared by the fill and traceback
+// kernels of the banded affine-gap DP (sm_100a).
+//
+// Reference semantics being reproduced (paths relative to the reference tree):
+//   ksw_global2      src/ksw.c:543-653
+//   ksw_extend_core  src/ksw.c:667-807   (ksw_extend2 :387-490 is the same fill
+//                                          without direction bits)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lb2 {
+
+constexpr int kNegInf = -0x40000000;     // src/ksw.c:504
+constexpr int kMaxMats = 16;             // distinct scoring matrices per batch
+constexpr int kKindGlobal = 0;
+constexpr int kKindExtend = 1;
+constexpr unsigned kFull = 0xffffffffu;
+
+// One DP task as the kernels see it.  Sequences live in one pooled byte array
+// (`pool`), every sequence starting on a 32-byte boundary and padded so that a
+// whole column chunk can always be fetched with one aligned vector load.
+struct __align__(16) DTask {
+    uint32_t q_off32, t_off32;   // offsets into pool, in 32-byte units
+    int32_t qlen, tlen;
+    int32_t w;                   // FINAL band: after src/ksw.c:549 resp. :696-704
+    int32_t h0;
+    int32_t o_del, e_del, o_ins, e_ins;
+    int32_t end_bonus, zdrop;
+    uint8_t kind, want_dir, mat_id, cshift;   // cshift = log2(columns per lane)
+    int32_t row_chunks;          // chunks of direction nibbles stored per row
+    uint64_t z_off;              // byte offset of this task's direction scratch
+    uint64_t ctmp_end;           // word offset one past this task's CIGAR scratch
+    int32_t ctmp_cap;            // words available below ctmp_end
+    int32_t pad;
+};
+static_assert(sizeof(DTask) == 80, "DTask layout");
+
+struct __align__(16) DResult {
+    int32_t score;               // global: eh[qlen].h ; extend: max
+    int32_t max_i, max_j, max_ie, gscore, max_off;   // extend bookkeeping
+    int32_t ti, tk;              // traceback start cell
+    int32_t n_cigar, rows;       // rows = rows entered before the loop ended
+    int64_t cigar_off;
+    int64_t cells;
+};
+static_assert(sizeof(DResult) == 64, "DResult layout");
+
+// direction nibble: bits0-1 source of H (0 diagonal, 1 E, 2 F), bit2 E was an
+// extension, bit3 F was an extension.  The reference byte (src/ksw.c:556) is
+// nib&3 | (nib&4) | (nib&8)<<2.
+__host__ __device__ inline uint64_t ext_meta_bytes(int tlen) {
+    return ((uint64_t)tlen * 8 + 15) & ~uint64_t(15);
+}
+__host__ __device__ inline int row_chunks_for(int ncol, int C) {
+    return ncol > 0 ? (ncol + C - 2) / C + 1 : 1;
+}
+
+}  // namespace lb2

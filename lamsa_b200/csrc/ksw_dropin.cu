@@ -1,0 +1,276 @@
+// ksw_dropin.cu -- the reference's ksw_* entry points (include/lamsa_b200.h,
+// section 1) implemented on top of the batch interface.  Every DP cell is
+// evaluated by the CUDA kernels; this file only holds the host control flow
+// that the reference keeps in its wrappers (src/ksw.c:809-926) and the CIGAR
+// list helpers those wrappers use (src/frag_check.h:139-188).
+//
+// A call made outside a batch scope submits a batch of one task and blocks.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/lamsa_b200.h"
+
+namespace {
+
+std::mutex g_mu;
+lb2_ctx* g_ctx = nullptr;
+
+lb2_ctx* default_ctx() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx) {
+        int dev = 0;
+        if (const char* e = getenv("LB2_DEVICE")) dev = atoi(e);
+        if (lb2_ctx_create(dev, &g_ctx)) {
+            fprintf(stderr, "[lamsa_b200] cannot open GPU %d: %s\n", dev, lb2_last_error());
+            exit(1);                               // same style as the reference's fatal paths
+        }
+    }
+    return g_ctx;
+}
+
+// run one task; returns malloc'd CIGAR (or NULL) through *cig
+void run_one(const lb2_task& t, lb2_result* r, cigar32_t** cig) {
+    lb2_ctx* c = default_ctx();
+    cigar32_t* pool = nullptr; int64_t pn = 0;
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);      // one stream per context
+        rc = lb2_dp_run(c, 1, &t, r, cig ? &pool : nullptr, &pn);
+    }
+    if (rc) { fprintf(stderr, "[lamsa_b200] DP launch failed: %s\n", lb2_last_error()); exit(1); }
+    if (cig) {
+        if (r->n_cigar > 0) {
+            // hand back exactly the capacity the reference would have grown to
+            cigar32_t* out = (cigar32_t*)malloc(sizeof(cigar32_t) * (size_t)r->reserved);
+            memcpy(out, pool + r->cigar_off, sizeof(cigar32_t) * (size_t)r->n_cigar);
+            *cig = out;
+        } else *cig = nullptr;
+        lb2_free(pool);
+    }
+}
+
+// ---- CIGAR list helpers (src/frag_check.h:139-188) -------------------------
+void list_add(cigar32_t** c, int* n, int* cap, cigar32_t op) {            // _push_cigar0
+    if (*n > 0 && (((*c)[*n - 1] ^ op) & 0xf) == 0) { (*c)[*n - 1] += (op >> 4) << 4; return; }
+    if (*n == *cap) {
+        *cap = *cap ? *cap << 1 : 4;
+        *c = (cigar32_t*)realloc(*c, sizeof(cigar32_t) * (size_t)*cap);
+        if (!*c) { fprintf(stderr, "\n[lamsa_b200] out of memory.\n"); exit(1); }
+    }
+    (*c)[(*n)++] = op;
+}
+void list_add_nonempty(cigar32_t** c, int* n, int* cap, cigar32_t op) {   // _push_cigar1
+    if (op >> 4) list_add(c, n, cap, op);
+}
+void list_append(cigar32_t** c, int* n, int* cap, const cigar32_t* src, int cnt) {   // _push_cigar
+    if (cnt == 0) return;
+    int i = *n, j = 0;
+    if (i > 0) {
+        const int a = (*c)[i - 1] & 0xf, b = src[0] & 0xf;
+        if (a == b) { (*c)[i - 1] += (src[0] >> 4) << 4; j = 1; }
+        else if ((a == LB2_CINS && b == LB2_CSOFT_CLIP) || (a == LB2_CSOFT_CLIP && b == LB2_CINS)) {
+            (*c)[i - 1] = ((((*c)[i - 1] >> 4) + (src[0] >> 4)) << 4) | LB2_CSOFT_CLIP; j = 1;
+        }
+    }
+    for (; j < cnt; ++i, ++j) {
+        if (i == *cap) {
+            *cap = *cap ? *cap << 1 : 4;
+            *c = (cigar32_t*)realloc(*c, sizeof(cigar32_t) * (size_t)*cap);
+            if (!*c) { fprintf(stderr, "\n[lamsa_b200] out of memory.\n"); exit(1); }
+        }
+        (*c)[i] = src[j];
+    }
+    *n = i;
+}
+void list_reverse(cigar32_t* c, int n) {                                  // _invert_cigar
+    for (int a = 0, b = n - 1; a < b; ++a, --b) { cigar32_t t = c[a]; c[a] = c[b]; c[b] = t; }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ksw_global2(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                int m, const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins,
+                int w, int* n_cigar, cigar32_t** cigar)
+{
+    if (qlen < 0 || tlen < 0) {
+        fprintf(stderr, "[ksw_global2] Error: qlen: %d tlen: %d\n", qlen, tlen); exit(-1);
+    }
+    if (n_cigar) *n_cigar = 0;
+    const bool want = n_cigar && cigar;
+    lb2_task t; memset(&t, 0, sizeof t);
+    t.kind = LB2_KIND_GLOBAL; t.flags = want ? LB2_FLAG_CIGAR : 0;
+    t.qlen = qlen; t.tlen = tlen; t.query = query; t.target = target;
+    t.w = w; t.h0 = 0; t.o_del = o_del; t.e_del = e_del; t.o_ins = o_ins; t.e_ins = e_ins;
+    t.m = m; t.mat = mat;
+    lb2_result r;
+    cigar32_t* c = nullptr;
+    run_one(t, &r, want ? &c : nullptr);
+    if (want) { *n_cigar = r.n_cigar; *cigar = c; }
+    return r.score;
+}
+
+int ksw_global(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+               int m, const int8_t* mat, int gapo, int gape, int w, int* n_cigar, cigar32_t** cigar)
+{
+    return ksw_global2(qlen, query, tlen, target, m, mat, gapo, gape, gapo, gape, w, n_cigar, cigar);
+}
+
+int ksw_extend2(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                int m, const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins,
+                int w, int end_bonus, int zdrop, int h0,
+                int* qle, int* tle, int* gtle, int* gscore, int* max_off)
+{
+    if (h0 <= 0) { fprintf(stderr, "[ksw_extend2] Assertion `h0 > 0' failed.\n"); abort(); }
+    lb2_task t; memset(&t, 0, sizeof t);
+    t.kind = LB2_KIND_EXTEND; t.flags = 0;
+    t.qlen = qlen; t.tlen = tlen; t.query = query; t.target = target;
+    t.w = w; t.h0 = h0; t.o_del = o_del; t.e_del = e_del; t.o_ins = o_ins; t.e_ins = e_ins;
+    t.end_bonus = end_bonus; t.zdrop = zdrop; t.m = m; t.mat = mat;
+    lb2_result r;
+    run_one(t, &r, nullptr);
+    if (qle) *qle = r.qle;
+    if (tle) *tle = r.tle;
+    if (gtle) *gtle = r.gtle;
+    if (gscore) *gscore = r.gscore;
+    if (max_off) *max_off = r.max_off;
+    return r.score;
+}
+
+int ksw_extend(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+               int m, const int8_t* mat, int gapo, int gape, int w, int end_bonus, int zdrop, int h0,
+               int* qle, int* tle, int* gtle, int* gscore, int* max_off)
+{
+    return ksw_extend2(qlen, query, tlen, target, m, mat, gapo, gape, gapo, gape, w, end_bonus, zdrop, h0,
+                       qle, tle, gtle, gscore, max_off);
+}
+
+int ksw_extend_core(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                    int m, const int8_t* mat, int w, int h0, lamsa_aln_para* AP,
+                    int* _qle, int* _tle, cigar32_t** cigar_, int* n_cigar_, int* m_cigar_)
+{
+    if (qlen < 0 || tlen < 0) {
+        fprintf(stderr, "[ksw_extend_core] Error: qlen: %d tlen: %d\n", qlen, tlen); exit(-1);
+    }
+    if (h0 <= 0) { fprintf(stderr, "[ksw_extend_core] Assertion `h0 > 0' failed.\n"); abort(); }
+    const bool want = n_cigar_ && cigar_;
+    lb2_task t; memset(&t, 0, sizeof t);
+    t.kind = LB2_KIND_EXTEND; t.flags = want ? LB2_FLAG_CIGAR : 0;
+    t.qlen = qlen; t.tlen = tlen; t.query = query; t.target = target;
+    t.w = w; t.h0 = h0;
+    t.o_del = AP->del_ext_o; t.e_del = AP->del_ext_e; t.o_ins = AP->ins_ext_o; t.e_ins = AP->ins_ext_e;
+    t.end_bonus = AP->end_bonus; t.zdrop = AP->zdrop; t.m = m; t.mat = mat;
+    lb2_result r;
+    cigar32_t* c = nullptr;
+    run_one(t, &r, want ? &c : nullptr);
+    if (want) {                                  // src/ksw.c:781-803
+        if (_qle) *_qle = r.qle;
+        if (_tle) *_tle = r.tle;
+        *n_cigar_ = r.n_cigar; *cigar_ = c; *m_cigar_ = r.reserved;
+    }
+    return r.score;
+}
+
+int ksw_extend_c(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                 int m, const int8_t* mat, int w, int h0, lamsa_aln_para* AP,
+                 int* _qle, int* _tle, cigar32_t** cigar_, int* n_cigar_, int* m_cigar_)
+{
+    *n_cigar_ = *m_cigar_ = 0;
+    ksw_extend_core(qlen, query, tlen, target, m, mat, w, h0, AP, _qle, _tle, cigar_, n_cigar_, m_cigar_);
+    return *_qle == qlen ? 0 : *_tle == tlen ? 1 : 2;
+}
+
+int ksw_extend_r(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                 int m, const int8_t* mat, int w, int h0, lamsa_aln_para* AP,
+                 int* _qre, int* _tre, cigar32_t** cigar_, int* n_cigar_, int* m_cigar_)
+{
+    *n_cigar_ = *m_cigar_ = 0;
+    uint8_t* rq = (uint8_t*)malloc(qlen > 0 ? qlen : 1);
+    uint8_t* rt = (uint8_t*)malloc(tlen > 0 ? tlen : 1);
+    for (int a = 0; a < qlen; ++a) rq[a] = query[qlen - 1 - a];
+    for (int a = 0; a < tlen; ++a) rt[a] = target[tlen - 1 - a];
+    ksw_extend_core(qlen, rq, tlen, rt, m, mat, w, h0, AP, _qre, _tre, cigar_, n_cigar_, m_cigar_);
+    free(rq); free(rt);
+    return *_qre == qlen ? 0 : *_tre == tlen ? 1 : 2;
+}
+
+void sw_mid_fix(cigar32_t** cigar, int* cigar_n, int* cigar_m,
+                cigar32_t* lcigar, int ln_cigar, cigar32_t* rcigar, int rn_cigar,
+                const uint8_t* query, int qlen, int lqe, int rqe,
+                const uint8_t* target, int tlen, int lte, int rte,
+                lamsa_aln_para* AP, int m, const int8_t* mat)
+{
+    const int Sn = qlen - lqe - rqe, Hn = tlen - lte - rte, half = AP->split_len / 2;
+    if (abs(Sn) >= half || abs(Hn) >= half || abs(Sn - Hn) >= half || tlen < 0 || qlen < 0) {
+        list_append(cigar, cigar_n, cigar_m, lcigar, ln_cigar);
+        list_add(cigar, cigar_n, cigar_m, (Sn << 4) | LB2_CSOFT_CLIP);
+        list_add(cigar, cigar_n, cigar_m, Hn << 4 | LB2_CHARD_CLIP);
+        list_append(cigar, cigar_n, cigar_m, rcigar, rn_cigar);
+    } else {            // small leftovers: re-align the whole pair globally
+        cigar32_t* g = nullptr; int gn = 0;
+        ksw_global2(qlen, query, tlen, target, m, mat, AP->del_gapo, AP->del_gape,
+                    AP->ins_gapo, AP->ins_gape, AP->band_w, &gn, &g);
+        list_append(cigar, cigar_n, cigar_m, g, gn);
+        free(g);
+    }
+}
+
+int ksw_bi_extend(int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                  int m, const int8_t* mat, int lh0, int rh0, lamsa_aln_para* AP,
+                  cigar32_t** cigar_, int* n_cigar_, int* m_cigar_)
+{
+    if (*n_cigar_) *n_cigar_ = 0;
+    const int dl = abs(qlen - tlen);
+    const int w = dl + 3 > AP->band_w ? dl + 3 : AP->band_w;                  // src/ksw.c:873
+    // the reference compares an int with a float expression (:881, :900);
+    // aln_mode_high_id_err() evaluates to 0 or 2 (src/lamsa_aln.h:438)
+    const bool near = dl < AP->split_len + tlen * AP->id_rate * (AP->aln_mode & 2);
+
+    int lqe = 0, lte = 0, ln = 0, lm = 0; cigar32_t* lc = nullptr;
+    int res = ksw_extend_c(qlen, query, tlen, target, m, mat, w, lh0, AP, &lqe, &lte, &lc, &ln, &lm);
+    if (res < 2) {
+        *cigar_ = lc; *n_cigar_ = ln; *m_cigar_ = lm;
+        list_add_nonempty(cigar_, n_cigar_, m_cigar_,
+                          res == 0 ? (((tlen - lte) << 4) | LB2_CDEL) : (((qlen - lqe) << 4) | LB2_CINS));
+        return 0;
+    }
+    if (near && ((lqe << 1 > qlen) || (lte << 1 > tlen))) {
+        if (lc) free(lc);
+        ksw_global2(qlen, query, tlen, target, m, mat, AP->del_gapo, AP->del_gape,
+                    AP->ins_gapo, AP->ins_gape, AP->band_w, n_cigar_, cigar_);
+        *m_cigar_ = *n_cigar_;
+        return 0;
+    }
+    int rqe = 0, rte = 0, rn = 0, rm = 0; cigar32_t* rc = nullptr;
+    res = ksw_extend_r(qlen, query, tlen, target, m, mat, w, rh0, AP, &rqe, &rte, &rc, &rn, &rm);
+    if (res < 2) {
+        list_add_nonempty(&rc, &rn, &rm,
+                          res == 0 ? (((tlen - rte) << 4) | LB2_CDEL) : (((qlen - rqe) << 4) | LB2_CINS));
+        list_reverse(rc, rn);
+        *cigar_ = rc; *n_cigar_ = rn; *m_cigar_ = rm;
+        free(lc);
+        return 0;
+    }
+    if (near && ((rqe << 1 > qlen) || (rte << 1 > tlen))) {
+        if (lc) free(lc);
+        if (rc) free(rc);
+        ksw_global2(qlen, query, tlen, target, m, mat, AP->del_gapo, AP->del_gape,
+                    AP->ins_gapo, AP->ins_gape, AP->band_w, n_cigar_, cigar_);
+        *m_cigar_ = *n_cigar_;
+        return 0;
+    }
+    list_reverse(rc, rn);
+    cigar32_t* out = (cigar32_t*)malloc(10 * sizeof(cigar32_t));             // :911-912
+    int on = 0, om = 10;
+    const int Sn = qlen - lqe - rqe;
+    sw_mid_fix(&out, &on, &om, lc, ln, rc, rn, query, qlen, lqe, rqe, target, tlen, lte, rte, AP, m, mat);
+    *cigar_ = out; *n_cigar_ = on; *m_cigar_ = om;
+    if (lc) free(lc);
+    if (rc) free(rc);
+    return Sn >= AP->split_len ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,244 @@
+"""Host-side mirror of the reference's ksw interface (reference src/ksw.h:64-127).
+
+Two ways in, both going through the C ABI of ``liblamsa_b200.so``:
+
+* ``ksw_global2`` / ``ksw_extend_core`` / ``ksw_bi_extend`` ... -- same names and
+  argument meaning as the reference prototypes; each call reaches the drop-in
+  symbol of the same name (one blocking GPU task per DP).
+* ``Context`` / ``Batch`` -- the batch producer: thousands of tasks per launch.
+
+There is no CPU implementation here; without the library or a GPU these raise.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import (AlnPara, FLAG_CIGAR, KIND_EXTEND, KIND_GLOBAL, RESULT_DTYPE, TASK_DTYPE,
+                   load_library)
+
+
+def default_matrix(match=1, mis=3):
+    """5x5 matrix of the reference's lamsa_fill_mat (src/lamsa_aln.c:1331-1340)."""
+    m = np.full((5, 5), -mis, dtype=np.int8)
+    for i in range(4):
+        m[i, i] = match
+    m[4, :] = -1
+    m[:, 4] = -1
+    return np.ascontiguousarray(m.reshape(-1))
+
+
+def _err(lib, what):
+    return RuntimeError(f"{what}: {lib.lb2_last_error().decode()}")
+
+
+class Context:
+    """One GPU context (lb2_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        if self.lib.lb2_ctx_create(int(device), C.byref(h)):
+            raise _err(self.lib, "lb2_ctx_create")
+        self.handle = h
+        self.device = device
+
+    def set_scratch_limit(self, nbytes):
+        if self.lib.lb2_ctx_set_scratch_limit(self.handle, int(nbytes)):
+            raise _err(self.lib, "lb2_ctx_set_scratch_limit")
+
+    def int_peak(self):
+        a, b = C.c_double(), C.c_double()
+        sm, khz = C.c_int(), C.c_int()
+        if self.lib.lb2_int_peak(self.handle, C.byref(a), C.byref(b), C.byref(sm), C.byref(khz)):
+            raise _err(self.lib, "lb2_int_peak")
+        return {"gops_s16x2": a.value, "gops_s32": b.value, "sm_count": sm.value, "clock_khz": khz.value}
+
+    def run(self, tasks, keep=()):
+        """One-shot lb2_dp_run: tasks (TASK_DTYPE array) -> (results, cigar_pool)."""
+        b = Batch(self, tasks, keep)
+        try:
+            b.upload()
+            b.compute()
+            return b.download()
+        finally:
+            b.close()
+
+    def close(self):
+        if self.handle:
+            self.lib.lb2_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """Staged batch (lb2_batch): create=pack, upload=H2D, compute=kernels, download=D2H."""
+
+    def __init__(self, ctx, tasks, keep=()):
+        self.ctx, self.lib = ctx, ctx.lib
+        tasks = np.ascontiguousarray(tasks, dtype=TASK_DTYPE)
+        self.n = len(tasks)
+        self._keep = (tasks, keep)
+        h = C.c_void_p()
+        if self.lib.lb2_batch_create(ctx.handle, self.n, tasks.ctypes.data, C.byref(h)):
+            raise _err(self.lib, "lb2_batch_create")
+        self.handle = h
+
+    def upload(self):
+        if self.lib.lb2_batch_upload(self.handle):
+            raise _err(self.lib, "lb2_batch_upload")
+
+    def compute(self):
+        ms = C.c_float()
+        if self.lib.lb2_batch_compute(self.handle, C.byref(ms)):
+            raise _err(self.lib, "lb2_batch_compute")
+        return ms.value
+
+    def download(self, want_cigar=True):
+        res = np.zeros(self.n, dtype=RESULT_DTYPE)
+        pool, pn = C.c_void_p(), C.c_int64()
+        if self.lib.lb2_batch_download(self.handle, res.ctypes.data,
+                                       C.byref(pool) if want_cigar else None, C.byref(pn)):
+            raise _err(self.lib, "lb2_batch_download")
+        cig = np.zeros(0, dtype=np.int32)
+        if want_cigar:
+            if pn.value:
+                cig = np.ctypeslib.as_array(C.cast(pool, C.POINTER(C.c_int32)), shape=(pn.value,)).copy()
+            self.lib.lb2_free(pool)
+        return res, cig
+
+    def stats(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        f, t = C.c_float(), C.c_float()
+        self.lib.lb2_batch_stats(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(f), C.byref(t))
+        return {"h2d_bytes": a.value, "d2h_bytes": b.value, "launches": c.value,
+                "fill_ms": f.value, "trace_ms": t.value}
+
+    def close(self):
+        if self.handle:
+            self.lib.lb2_batch_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_tasks(kind, qseq, qoff, qlen, tseq, toff, tlen, w, mat, *, h0=0, o_del=5, e_del=2, o_ins=5,
+               e_ins=2, end_bonus=0, zdrop=0, cigar=True, m=5):
+    """Vectorised construction of a TASK_DTYPE array over pooled sequences.
+
+    qseq/tseq: uint8 arrays holding all sequences; task i uses qseq[qoff[i]:qoff[i]+qlen[i]].
+    Scalar or per-task arrays are accepted for every parameter.  The caller must
+    keep qseq, tseq and mat alive while the tasks are in use.
+    """
+    n = len(qlen)
+    t = np.zeros(n, dtype=TASK_DTYPE)
+    t["kind"] = kind
+    t["flags"] = np.where(np.broadcast_to(np.asarray(cigar), (n,)), FLAG_CIGAR, 0)
+    t["qlen"], t["tlen"] = qlen, tlen
+    t["query"] = qseq.ctypes.data + np.asarray(qoff, dtype=np.uint64)
+    t["target"] = tseq.ctypes.data + np.asarray(toff, dtype=np.uint64)
+    for name, v in (("w", w), ("h0", h0), ("o_del", o_del), ("e_del", e_del), ("o_ins", o_ins),
+                    ("e_ins", e_ins), ("end_bonus", end_bonus), ("zdrop", zdrop), ("m", m)):
+        t[name] = v
+    t["mat"] = mat.ctypes.data
+    return t
+
+
+# ------------------------------------------------------------ drop-in mirrors --
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _i8(a):
+    a = np.ascontiguousarray(a, dtype=np.int8)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int8))
+
+
+def _take_cigar(lib, ptr, n):
+    out = [int(ptr[i]) for i in range(n)] if n else []
+    if ptr:
+        lib.lb2_free(C.cast(ptr, C.c_void_p))
+    return out
+
+
+def ksw_global2(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, w, want_cigar=True):
+    """reference src/ksw.c:543 -> (score, cigar words or None)"""
+    lib = load_library()
+    q, qp = _u8(query)
+    t, tp = _u8(target)
+    mm, mp = _i8(mat)
+    if not want_cigar:
+        return lib.ksw_global2(qlen, qp, tlen, tp, m, mp, o_del, e_del, o_ins, e_ins, w, None, None), None
+    n, c = C.c_int(), C.POINTER(C.c_int32)()
+    s = lib.ksw_global2(qlen, qp, tlen, tp, m, mp, o_del, e_del, o_ins, e_ins, w, C.byref(n), C.byref(c))
+    return s, _take_cigar(lib, c, n.value)
+
+
+def ksw_global(qlen, query, tlen, target, m, mat, gapo, gape, w, want_cigar=True):
+    """reference src/ksw.c:655"""
+    return ksw_global2(qlen, query, tlen, target, m, mat, gapo, gape, gapo, gape, w, want_cigar)
+
+
+def ksw_extend2(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0):
+    """reference src/ksw.c:387 -> (score, qle, tle, gtle, gscore, max_off)"""
+    lib = load_library()
+    q, qp = _u8(query)
+    t, tp = _u8(target)
+    mm, mp = _i8(mat)
+    o = [C.c_int() for _ in range(5)]
+    s = lib.ksw_extend2(qlen, qp, tlen, tp, m, mp, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0,
+                        *[C.byref(x) for x in o])
+    return (s,) + tuple(x.value for x in o)
+
+
+def ksw_extend(qlen, query, tlen, target, m, mat, gapo, gape, w, end_bonus, zdrop, h0):
+    """reference src/ksw.c:492"""
+    return ksw_extend2(qlen, query, tlen, target, m, mat, gapo, gape, gapo, gape, w, end_bonus, zdrop, h0)
+
+
+def _ext_call(name, qlen, query, tlen, target, m, mat, w, h0, AP):
+    lib = load_library()
+    q, qp = _u8(query)
+    t, tp = _u8(target)
+    mm, mp = _i8(mat)
+    qle, tle, n, cap = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    c = C.POINTER(C.c_int32)()
+    r = getattr(lib, name)(qlen, qp, tlen, tp, m, mp, w, h0, C.byref(AP), C.byref(qle), C.byref(tle),
+                           C.byref(c), C.byref(n), C.byref(cap))
+    return r, qle.value, tle.value, _take_cigar(lib, c, n.value), cap.value
+
+
+def ksw_extend_core(qlen, query, tlen, target, m, mat, w, h0, AP):
+    """reference src/ksw.c:667 -> (max, qle, tle, cigar, m_cigar)"""
+    return _ext_call("ksw_extend_core", qlen, query, tlen, target, m, mat, w, h0, AP)
+
+
+def ksw_extend_c(qlen, query, tlen, target, m, mat, w, h0, AP):
+    """reference src/ksw.c:809 -> (0|1|2, qle, tle, cigar, m_cigar)"""
+    return _ext_call("ksw_extend_c", qlen, query, tlen, target, m, mat, w, h0, AP)
+
+
+def ksw_extend_r(qlen, query, tlen, target, m, mat, w, h0, AP):
+    """reference src/ksw.c:820 -> (0|1|2, qre, tre, cigar, m_cigar)"""
+    return _ext_call("ksw_extend_r", qlen, query, tlen, target, m, mat, w, h0, AP)
+
+
+def ksw_bi_extend(qlen, query, tlen, target, m, mat, lh0, rh0, AP):
+    """reference src/ksw.c:862 -> (0|1, cigar, m_cigar)"""
+    lib = load_library()
+    q, qp = _u8(query)
+    t, tp = _u8(target)
+    mm, mp = _i8(mat)
+    n, cap = C.c_int(), C.c_int()
+    c = C.POINTER(C.c_int32)()
+    r = lib.ksw_bi_extend(qlen, qp, tlen, tp, m, mp, lh0, rh0, C.byref(AP), C.byref(c), C.byref(n), C.byref(cap))
+    return r, _take_cigar(lib, c, n.value), cap.value

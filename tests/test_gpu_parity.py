@@ -1,0 +1,96 @@
+"""GPU suite (B200): the CUDA path, reached through the C ABI, against
+  * the committed golden outputs of the unmodified reference ksw.c,
+  * the oracle on seeded random task streams (bit-exact: scores, end points,
+    every CIGAR word, evaluated-cell counts),
+  * the reference-named drop-in entry points.
+Nothing here reads /root/reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import _oracle
+import lamsa_b200
+from lamsa_b200 import workload
+from test_oracle import SETS, golden_results
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(ctx, tasks, keep):
+    return ctx.run(tasks, keep)
+
+
+@pytest.mark.parametrize("name", list(SETS))
+def test_gpu_matches_reference_golden(ctx, name):
+    tasks, keep = SETS[name]()
+    gres, gcig, sha = golden_results(name)
+    assert _oracle.inputs_digest(tasks) == sha
+    res, cig = run_gpu(ctx, tasks, keep)
+    bad = _oracle.compare(tasks, res, cig, gres, gcig, what=f"gpu-vs-golden[{name}]")
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("seed,n,kw", [
+    (201, 20000, dict()),
+    (202, 30000, dict(qmin=1, qmax=160, wmin=1, wmax=30, max_err=0.3, max_dl=20)),
+    (203, 4000, dict(qmin=600, qmax=1000, wmin=150, wmax=200)),
+    (204, 6000, dict(cigar=False)),
+])
+def test_gpu_matches_oracle_random(ctx, seed, n, kw):
+    tasks, keep = workload.gen_microbench(n, seed=seed, **kw)
+    res, cig = run_gpu(ctx, tasks, keep)
+    ores, ocig, _ = _oracle.oracle_run(tasks)
+    bad = _oracle.compare(tasks, res, cig, ores, ocig, what="gpu-vs-oracle", check_cells=True)
+    assert not bad, "\n".join(bad)
+
+
+def test_gpu_multi_wave_equals_single_wave(ctx):
+    tasks, keep = workload.gen_microbench(3000, seed=205, qmax=500)
+    a = run_gpu(ctx, tasks, keep)
+    small = lamsa_b200.Context(0)
+    small.set_scratch_limit(8 << 20)          # forces many waves through the same scratch
+    b = small.run(tasks, keep)
+    small.close()
+    bad = _oracle.compare(tasks, a[0], a[1], b[0], b[1], what="wave")
+    assert not bad, "\n".join(bad)
+
+
+def test_dropin_entry_points(ctx):
+    rng = np.random.default_rng(5)
+    mat = lamsa_b200.default_matrix(1, 3)
+    AP = lamsa_b200.AlnPara()
+    AP.ins_ext_o = AP.del_ext_o = 5
+    AP.ins_ext_e = AP.del_ext_e = 2
+    AP.ins_gapo = AP.del_gapo = 5
+    AP.ins_gape = AP.del_gape = 2
+    AP.end_bonus, AP.zdrop, AP.band_w, AP.split_len = 5, 100, 10, 100
+    AP.id_rate, AP.aln_mode = 0.04, 0
+    orc = C.CDLL(_oracle.ensure_oracle())
+    for it in range(40):
+        ql = int(rng.integers(0, 300))
+        q = rng.integers(0, 4, size=ql, dtype=np.uint8)
+        t = q.copy()
+        if ql > 10:
+            k = int(rng.integers(1, ql // 2))
+            t = np.concatenate((q[:k], rng.integers(0, 4, size=int(rng.integers(0, 8)), dtype=np.uint8), q[k + int(rng.integers(0, 5)):]))
+        tl = len(t)
+        tasks = np.zeros(2, dtype=lamsa_b200.TASK_DTYPE)
+        qb, tb = np.concatenate((q, np.zeros(8, np.uint8))), np.concatenate((t, np.zeros(8, np.uint8)))
+        for r, kind in zip(tasks, (0, 1)):
+            r["kind"], r["flags"], r["qlen"], r["tlen"] = kind, 1, ql, tl
+            r["query"], r["target"], r["w"], r["h0"] = qb.ctypes.data, tb.ctypes.data, 10, 19
+            r["o_del"], r["e_del"], r["o_ins"], r["e_ins"] = 5, 2, 5, 2
+            r["end_bonus"], r["zdrop"], r["m"], r["mat"] = 5, 100, 5, mat.ctypes.data
+        ores, ocig, _ = _oracle.oracle_run(tasks, 1)
+        s, cg = lamsa_b200.ksw_global2(ql, qb, tl, tb, 5, mat, 5, 2, 5, 2, 10)
+        assert s == ores["score"][0]
+        assert cg == list(ocig[ores["cigar_off"][0]: ores["cigar_off"][0] + ores["n_cigar"][0]])
+        s2, _ = lamsa_b200.ksw_global(ql, qb, tl, tb, 5, mat, 5, 2, 10, want_cigar=False)
+        assert s2 == s
+        mx, qle, tle, cg, cap = lamsa_b200.ksw_extend_core(ql, qb, tl, tb, 5, mat, 10, 19, AP)
+        assert (mx, qle, tle, cap) == (ores["score"][1], ores["qle"][1], ores["tle"][1], ores["m_cigar"][1])
+        assert cg == list(ocig[ores["cigar_off"][1]: ores["cigar_off"][1] + ores["n_cigar"][1]])
+        rc, qle2, tle2, cg2, _ = lamsa_b200.ksw_extend_c(ql, qb, tl, tb, 5, mat, 10, 19, AP)
+        assert (qle2, tle2, cg2) == (qle, tle, cg)
+        assert rc == (0 if qle == ql else 1 if tle == tl else 2)
