@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- banded-DP throughput (GCUPS) of the B200 path, BASELINE.json configs[1]:
+the ksw_global2 / ksw_extend_core microbenchmark (1 M synthetic DP tasks, 50-1000 bp,
+band 10..200, half global / half extension, CIGARs produced).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--tasks T] [--impl reference]
+
+A "step" = one pass of the hot path (fill + traceback kernels) over the whole task
+batch, inputs resident in HBM.  `value` = DP cells the reference would evaluate
+(counted by the kernels, identical to the oracle's count) / device time, summed over
+ranks; `e2e` = the same through lb2_dp_run with HOST task records (pack + H2D +
+kernels + D2H of scores/CIGARs).  N>1: one process per GPU (torchrun), tasks sharded
+by rank (independent batches, no collective on the data path), weak scaling.
+`--impl reference` times the reference's own CPU ksw.c (oracle/_ref, or the oracle
+port when that was not built) on all host cores, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+OPS_EXTEND, OPS_GLOBAL = 22, 16        # algorithmic integer ops per cell
+METRIC = "banded_dp_gcups"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.p = gpu, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # median over the upper half of samples = clocks under load (idle samples sit at the floor)
+        hi = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(tasks, threads):
+    """Time the reference ksw.c (or the oracle port) on host threads -> (gcups, kind, seconds, cells)."""
+    import _oracle
+    ores, _, _ = _oracle.oracle_run(tasks[:1], 1)      # builds/loads the oracle
+    if _oracle.have_ref():
+        kind = "reference"
+        res, cig, secs = _oracle.ref_run(tasks, threads)
+        cells = int(_oracle.oracle_run(tasks, threads)[0]["cells"].sum())   # the reference .so has no cell counter
+    else:
+        kind = "port"
+        res, cig, secs = _oracle.oracle_run(tasks, threads)
+        cells = int(res["cells"].sum())
+    return cells / secs / 1e9, kind, secs, cells
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--tasks", type=int, default=env_int("LB2_BENCH_TASKS", 1_000_000), help="DP tasks per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=200_000)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--seed", type=int, default=20260101)
+    a = ap.parse_args()
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    from lamsa_b200 import workload
+    workload_name = (f"ksw microbenchmark C2: {a.tasks} tasks/GPU, qlen U[50,1000], w U[10,200], "
+                     "half ksw_global2 / half ksw_extend_core, CIGAR on")
+    threads = os.cpu_count() or 1
+
+    # ------------------------------------------------------------ reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        n = min(a.tasks, a.cpu_sample)
+        tasks, keep = workload.gen_microbench(n, seed=a.seed)
+        vals, secs_all = [], []
+        kind = "port"
+        for s in range(a.warmup + a.steps):
+            g, kind, secs, cells = cpu_reference(tasks, threads)
+            if s >= a.warmup:
+                vals.append(g); secs_all.append(secs)
+        v = float(np.mean(vals))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(secs_all)),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+                "data": "synthetic", "config": {"workload": workload_name, "sample_tasks": n},
+                "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": threads, "kind": kind,
+                                 "sample": f"first {n} tasks of the workload, pthread pool over all host cores"},
+                "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import lamsa_b200
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = local if world > 1 else 0
+    torch.cuda.set_device(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    tasks, keep = workload.gen_microbench(a.tasks, seed=a.seed + 1000 * rank)
+    ctx = lamsa_b200.Context(dev)
+    peak = ctx.int_peak()
+    batch = lamsa_b200.Batch(ctx, tasks, keep)
+    batch.upload()
+    for _ in range(max(a.warmup, 3)):
+        batch.compute()
+    sampler = ClockSampler(dev)
+    barrier()
+    sampler.start()
+    t_wall = time.perf_counter()
+    dev_ms, fill_ms, trace_ms, launches = 0.0, 0.0, 0.0, 0
+    for _ in range(a.steps):
+        dev_ms += batch.compute()                    # CUDA events on the library's stream
+        st = batch.stats()
+        fill_ms += st["fill_ms"]; trace_ms += st["trace_ms"]; launches += st["launches"]
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    res, cig = batch.download()
+    cells = int(res["cells"].sum())
+    ext = tasks["kind"] == 1
+    cells_ext = int(res["cells"][ext].sum())
+    ops_per_step = cells_ext * OPS_EXTEND + (cells - cells_ext) * OPS_GLOBAL
+    # algorithmic HBM bytes of one step: sequences in, direction nibbles (+ row bands) out and back in
+    # along the traceback path, CIGAR words out
+    seq_bytes = int(tasks["qlen"].sum() + tasks["tlen"].sum())
+    dir_bytes = cells // 2
+    cigar_bytes = int(res["n_cigar"].sum()) * 4
+    batch.close()
+
+    # ---- end to end through the public one-shot call, host task records in / host results out
+    e2e_secs, h2d, d2h = [], 0, 0
+    for s in range(1 + a.e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        b = lamsa_b200.Batch(ctx, tasks, keep)       # == lb2_dp_run, staged so the byte counters can be read
+        b.upload(); b.compute(); r2, c2 = b.download()
+        st2 = b.stats()
+        b.close()
+        barrier()
+        if s >= 1:
+            e2e_secs.append(time.perf_counter() - t0)
+        h2d, d2h = st2["h2d_bytes"], st2["d2h_bytes"]
+    e2e_s = float(np.mean(e2e_secs))
+
+    # ---- reduce over ranks: max time, summed cells
+    tmax, cells_all, ops_all, e2e_max = dev_ms, cells, ops_per_step, e2e_s
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_s, fill_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tmax, e2e_max, fill_max = t.tolist()
+        c = torch.tensor([cells, ops_per_step], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        cells_all, ops_all = int(c[0].item()), int(c[1].item())
+    else:
+        fill_max = fill_ms
+    ms_step = tmax / a.steps
+    value = cells_all / (ms_step * 1e-3) / 1e9
+
+    cpu = None
+    if rank == 0 and world == 1:
+        n = min(a.tasks, a.cpu_sample)
+        g, kind, secs, ccells = cpu_reference(tasks[:n], threads)
+        cpu = {"value": g, "unit": "GCUPS", "cores": threads, "kind": kind,
+               "sample": f"first {n} tasks of the same workload ({ccells} cells, {secs:.2f} s wall), pthread pool"}
+
+    if rank == 0:
+        peak_tops = peak["gops_s16x2"] / 1e3
+        fill_step_ms = fill_max / a.steps
+        achieved = (ops_all / world) / (fill_step_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload_name, "tasks_per_gpu": a.tasks, "cells_per_gpu": cells,
+                       "l2": "inputs (sequence pool + direction scratch) far larger than the 126 MB L2",
+                       "parallelism": f"task-sharded x{world}, no collective"},
+            "aligned_mbp_per_s": float(tasks["qlen"].sum()) * world / (ms_step * 1e-3) / 1e6,
+            "wall_ms_per_step": 1e3 * t_wall / a.steps,
+            "e2e": {"value": cells_all / e2e_max / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "seconds_per_step": e2e_max},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak_tops, "unit": "Tops/s (int16 lane-ops)",
+                         "frac": achieved / peak_tops,
+                         "peak_source": "measured live: VIADDMNMX.S16x2 issue rate (lb2_int_peak); "
+                                        "MEASURED_PEAKS.json has no integer figure",
+                         "kernel": "fill_kernel<C,KIND> (all launches of a step)", "kernel_ms_per_step": fill_step_ms,
+                         "trace_ms_per_step": trace_ms / a.steps,
+                         "ops_per_cell": {"extend": OPS_EXTEND, "global": OPS_GLOBAL},
+                         "hbm": {"algorithmic_bytes": seq_bytes + 2 * dir_bytes + cigar_bytes,
+                                 "achieved_gbs": (seq_bytes + 2 * dir_bytes + cigar_bytes) / (ms_step * 1e-3) / 1e9},
+                         "traffic": None},
+            "int_peak": peak,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
