@@ -34,8 +34,20 @@ extern "C" const char* lb2_last_error(void) { return g_err.c_str(); }
 extern "C" void lb2_free(void* p) { free(p); }
 
 // ----------------------------------------------------------------- context --
-constexpr int kNumCS = 6;                    // columns per lane: 1,2,4,8,16,32
-constexpr int kNumClass = 2 * kNumCS;        // x {global, extend}
+// A launch class = (kind, G = columns per lane per tile, S = shared-memory window slots).
+constexpr int kMinLogS = 6, kMaxLogS = 14;          // 64 .. 16384 slots (10 bytes each) per warp
+constexpr int kNumLogS = kMaxLogS - kMinLogS + 1;
+constexpr int kNumClass = 2 * 3 * kNumLogS;
+constexpr size_t kMaxDynSmem = 200 * 1024;
+static inline int class_id(int kind, int gs, int logS) { return (kind * 3 + gs) * kNumLogS + (logS - kMinLogS); }
+static inline int class_kind(int c) { return c / (3 * kNumLogS); }
+static inline int class_gs(int c) { return (c / kNumLogS) % 3; }
+static inline int class_logS(int c) { return c % kNumLogS + kMinLogS; }
+static inline int class_warps(int logS) {            // warps per block
+    int wpb = 8;
+    while (wpb > 1 && (size_t)wpb * warp_smem_bytes(1 << logS) > 160 * 1024) wpb >>= 1;
+    return wpb;
+}
 
 struct lb2_ctx {
     int device = 0;
@@ -44,20 +56,14 @@ struct lb2_ctx {
     uint64_t scratch_limit = 0;
     uint8_t* d_z = nullptr;    size_t z_cap = 0;        // direction nibbles (+ row bands)
     int32_t* d_ctmp = nullptr; size_t ctmp_cap = 0;     // per-task reversed CIGAR scratch (words)
-    int occ[kNumClass] = {0};
+    int occ[kNumClass] = {0};                           // resident blocks per SM, filled lazily
 };
 
 typedef void (*fill_fn)(const DTask*, const int32_t*, int, const uint8_t*, uint8_t*, DResult*,
-                        const uint2*, unsigned int*);
-static fill_fn fill_table(int cls) {
-    switch (cls) {
-        case 0: return fill_kernel<1, kKindGlobal>;   case 1: return fill_kernel<2, kKindGlobal>;
-        case 2: return fill_kernel<4, kKindGlobal>;   case 3: return fill_kernel<8, kKindGlobal>;
-        case 4: return fill_kernel<16, kKindGlobal>;  case 5: return fill_kernel<32, kKindGlobal>;
-        case 6: return fill_kernel<1, kKindExtend>;   case 7: return fill_kernel<2, kKindExtend>;
-        case 8: return fill_kernel<4, kKindExtend>;   case 9: return fill_kernel<8, kKindExtend>;
-        case 10: return fill_kernel<16, kKindExtend>; default: return fill_kernel<32, kKindExtend>;
-    }
+                        const uint2*, unsigned int*, int);
+static fill_fn fill_table(int kind, int gs) {
+    if (kind == kKindGlobal) return gs == 0 ? fill_kernel<1, kKindGlobal> : gs == 1 ? fill_kernel<2, kKindGlobal> : fill_kernel<4, kKindGlobal>;
+    return gs == 0 ? fill_kernel<1, kKindExtend> : gs == 1 ? fill_kernel<2, kKindExtend> : fill_kernel<4, kKindExtend>;
 }
 
 extern "C" int lb2_ctx_create(int device, lb2_ctx** out) {
@@ -79,11 +85,9 @@ extern "C" int lb2_ctx_create(int device, lb2_ctx** out) {
     size_t fr = 0, tot = 0;
     CU(cudaMemGetInfo(&fr, &tot));
     c->scratch_limit = (uint64_t)(fr * 0.40);
-    for (int k = 0; k < kNumClass; ++k) {
-        int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fill_table(k), 128, 0));
-        c->occ[k] = nb > 0 ? nb : 1;
-    }
+    for (int kind = 0; kind < 2; ++kind)
+        for (int gs = 0; gs < 3; ++gs)
+            CU(cudaFuncSetAttribute(fill_table(kind, gs), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
     *out = c;
     return 0;
 }
@@ -151,12 +155,15 @@ static int extend_band(int w, int qlen, int m, const int8_t* mat, int end_bonus,
     return w;
 }
 
-static int pick_cshift(int qlen, int w) {
-    for (int cs = 0; cs < kNumCS; ++cs) {
-        const long C = 1L << cs;
-        if ((long)qlen + 1 <= 32 * C || 31 * C >= 2L * w + 1) return cs;
-    }
-    return -1;
+// columns per lane per tile, from the widest band a row can have
+static int pick_gshift(long ncol) { return ncol <= 36 ? 0 : ncol <= 72 ? 1 : 2; }
+// window slots: the whole eh[] array when it is small, else band window + look-ahead
+static int pick_logS(int qlen, int w) {
+    const long qpad = ((long)qlen + 1 + 31) & ~31L;
+    const long need = std::min<long>(qpad, 2L * w + 72);
+    int l = kMinLogS;
+    while ((1L << l) < need && l <= kMaxLogS) ++l;
+    return l <= kMaxLogS ? l : -1;
 }
 
 extern "C" void lb2_batch_destroy(lb2_batch* b) {
@@ -204,7 +211,7 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     // ---- pass 1: validate, classify, lay out pool / scratch
     std::vector<uint64_t> qoff(n), toff(n), zsz(n);
     std::vector<int32_t> wfin(n), ctmpw(n);
-    std::vector<int8_t> cshift(n), matid(n);
+    std::vector<int8_t> cshift(n), matid(n), logS(n);
     std::vector<std::vector<int8_t>> mats;           // distinct matrices, each 64 entries (8x8, zero padded)
     b->flags.resize(n);
     uint64_t pool = 0;
@@ -225,9 +232,11 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
         }
         if (w < 0) return fail("task %lld: negative band", (long long)i);
         wfin[i] = w;
-        const int cs = pick_cshift(t.qlen, w);
-        if (cs < 0) return fail("task %lld: qlen %d with band %d exceeds the single-warp kernels", (long long)i, t.qlen, w);
-        cshift[i] = (int8_t)cs;
+        const long ncol_i = std::min<long>(t.qlen, 2L * w + 1);
+        const int cs = pick_gshift(ncol_i);
+        const int ls = pick_logS(t.qlen, w);
+        if (ls < 0) return fail("task %lld: qlen %d with band %d needs a window beyond %d slots (not supported yet)", (long long)i, t.qlen, w, 1 << kMaxLogS);
+        cshift[i] = (int8_t)cs; logS[i] = (int8_t)ls;
         // matrix table
         int8_t m8[64]; memset(m8, 0, sizeof m8);
         for (int a = 0; a < t.m; ++a) for (int c = 0; c < t.m; ++c) m8[a * 8 + c] = t.mat[a * t.m + c];
@@ -242,10 +251,9 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
         qoff[i] = pool; pool += ((uint64_t)t.qlen + 1 + 31) & ~uint64_t(31);
         toff[i] = pool; pool += ((uint64_t)t.tlen + 31) & ~uint64_t(31);
         if (t.flags & LB2_FLAG_CIGAR) {
-            const int C = 1 << cs;
-            const long ncol = std::min<long>(t.qlen, 2L * w + 1);
-            const int rw = row_chunks_for((int)ncol, C);
-            uint64_t z = (uint64_t)t.tlen * rw * dir_chunk_bytes(C);
+            const int G = 1 << cs;
+            const int rt = row_tiles_for(ncol_i, G);
+            uint64_t z = (uint64_t)t.tlen * rt * 32 * dir_lane_bytes(G);
             if (t.kind == LB2_KIND_EXTEND) z += ext_meta_bytes(t.tlen);
             zsz[i] = (z + 15) & ~uint64_t(15);
             ctmpw[i] = t.qlen + t.tlen + 2;
@@ -288,7 +296,7 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     for (auto& wv : b->waves) {
         std::vector<int32_t> idx(wv.count);
         for (int k = 0; k < wv.count; ++k) idx[k] = wv.first + k;
-        auto cls = [&](int32_t a) { return (int)tasks[a].kind * kNumCS + cshift[a]; };
+        auto cls = [&](int32_t a) { return class_id((int)tasks[a].kind, cshift[a], logS[a]); };
         auto cost = [&](int32_t a) {
             return (int64_t)tasks[a].tlen * std::min<int64_t>(tasks[a].qlen, 2L * wfin[a] + 1);
         };
@@ -328,7 +336,7 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
             d.kind = (uint8_t)t.kind; d.want_dir = (t.flags & LB2_FLAG_CIGAR) ? 1 : 0;
             d.mat_id = (uint8_t)matid[i]; d.cshift = (uint8_t)cshift[i];
             const long ncol = std::min<long>(t.qlen, 2L * wfin[i] + 1);
-            d.row_chunks = row_chunks_for((int)ncol, 1 << cshift[i]);
+            d.row_chunks = row_tiles_for(ncol, 1 << cshift[i]);
             d.pad = 0;
             uint8_t* q = hp + qoff[i];
             const uint64_t qp = ((uint64_t)t.qlen + 1 + 31) & ~uint64_t(31);
@@ -406,12 +414,20 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
         for (int k = 0; k < kNumClass; ++k) {
             const int cnt = wv.cls_off[k + 1] - wv.cls_off[k];
             if (!cnt) continue;
-            int grid = (cnt + 3) / 4;
+            const int kind = class_kind(k), gs = class_gs(k), ls = class_logS(k);
+            const int wpb = class_warps(ls);
+            const size_t smem = (size_t)wpb * warp_smem_bytes(1 << ls);
+            if (!c->occ[k]) {
+                int nb = 0;
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fill_table(kind, gs), wpb * 32, smem));
+                c->occ[k] = nb > 0 ? nb : 1;
+            }
+            int grid = (cnt + wpb - 1) / wpb;
             const int cap = c->sm_count * c->occ[k];
             if (grid > cap) grid = cap;
-            fill_table(k)<<<grid, 128, 0, s>>>(b->d_tasks, b->d_order + wv.first + wv.cls_off[k], cnt,
-                                               b->d_pool, c->d_z, b->d_results, b->d_mats,
-                                               b->d_counters + wi * kNumClass + k);
+            fill_table(kind, gs)<<<grid, wpb * 32, smem, s>>>(b->d_tasks, b->d_order + wv.first + wv.cls_off[k], cnt,
+                                                            b->d_pool, c->d_z, b->d_results, b->d_mats,
+                                                            b->d_counters + wi * kNumClass + k, 1 << ls);
             CU(cudaGetLastError());
             ++b->launches;
         }

@@ -27,8 +27,8 @@ struct __align__(16) DTask {
     int32_t h0;
     int32_t o_del, e_del, o_ins, e_ins;
     int32_t end_bonus, zdrop;
-    uint8_t kind, want_dir, mat_id, cshift;   // cshift = log2(columns per lane)
-    int32_t row_chunks;          // chunks of direction nibbles stored per row
+    uint8_t kind, want_dir, mat_id, cshift;   // cshift = log2(G), G = columns per lane per tile
+    int32_t row_chunks;          // tiles (32*G columns) of direction nibbles stored per row
     uint64_t z_off;              // byte offset of this task's direction scratch
     uint64_t ctmp_end;           // word offset one past this task's CIGAR scratch
     int32_t ctmp_cap;            // words available below ctmp_end
@@ -51,9 +51,6 @@ static_assert(sizeof(DResult) == 64, "DResult layout");
 // nib&3 | (nib&4) | (nib&8)<<2.
 __host__ __device__ inline uint64_t ext_meta_bytes(int tlen) {
     return ((uint64_t)tlen * 8 + 15) & ~uint64_t(15);
-}
-__host__ __device__ inline int row_chunks_for(int ncol, int C) {
-    return ncol > 0 ? (ncol + C - 2) / C + 1 : 1;
 }
 
 }  // namespace lb2

@@ -7,20 +7,27 @@
 //     E(i+1,j) = max(E(i,j) - e_del, M(i,j) - oe_del)          per-column state
 //     F(i,j+1) = max(F(i,j) - e_ins, M(i,j) - oe_ins)          max-plus prefix scan
 //     H(i,j)   = max(M, E, F)
-// F is an exclusive prefix maximum of u_j = t_j + (j+1)*e_ins, which the warp
-// evaluates with one Kogge-Stone pass over the per-lane maxima.  Integer
-// max/add are exact and associative, so every value (including the "-inf"
-// arithmetic of the global fill) is bit-identical to the sequential loop.
+// F(i,j) is the exclusive prefix maximum of u_k = t_k + (k+1)*e_ins (k < j)
+// minus j*e_ins.  Integer max/add are exact and associative, so every value
+// (including the "-inf" arithmetic of the global fill) is bit-identical to
+// the sequential loop.
 //
-// Ownership: lane L holds the reference's eh[] slots of column chunk q
-// (columns q*C .. q*C+C-1) with q % 32 == L, in registers.  The band window
-// [i-w, i+w+1] slides right one column per row; when a lane's chunk has fallen
-// completely left of the window the lane adopts chunk q+32 and initialises the
-// slots to the "row -1" values (src/ksw.c:569-572 / :692-694).  31*C >= 2w+1
-// (or 32*C >= qlen+1) guarantees the adopted chunk is not needed before the
-// old one is dead.  Slots keep whatever they held when a row does not visit
-// them, exactly like the reference array (the adaptive band of the extension
-// can read such slots later: SURVEY.md A.2-8).
+// Data layout.  The reference's eh[] array (src/ksw.c:383-385) lives in SHARED
+// memory, one circular window per warp: hb[j & (S-1)], eb[j & (S-1)] hold slot
+// j, S >= band window + 64.  Slots are initialised to the "row -1" values
+// (src/ksw.c:569-572 / :692-694) one column ahead of the band's right edge and
+// keep whatever they held when a row does not visit them, exactly like the
+// reference array (the adaptive band of the extension reads such slots later:
+// SURVEY.md A.2-8).  qb[] holds, per query column, the PRMT selector that
+// extracts (sign-extended) the score of that query code from the 8-byte
+// scoring-matrix row of the current target base.
+//
+// Work mapping.  A row's live columns [beg,end) are cut into tiles of 32*G
+// columns; in a tile lane L owns G consecutive columns (G in {1,2,4}), so the
+// number of warp iterations per row follows the ACTUAL band (adaptive in the
+// extension), not the static one.  Per tile: vector LDS of h/e/selectors, G
+// cells of straight-line integer code, one Kogge-Stone prefix-max over the
+// lane totals, vector STS of the new h/e, one store of G direction nibbles.
 #pragma once
 #include "dp_device.cuh"
 #include <climits>
@@ -39,47 +46,6 @@ __device__ __forceinline__ uint32_t sel_for_code(uint32_t code) {
     return code + (code | 8u) * 0x1110u;
 }
 
-template <int C> struct QChunk { uint32_t w[(C + 3) / 4]; };
-
-template <int C>
-__device__ __forceinline__ QChunk<C> load_qchunk(const uint8_t* __restrict__ q, int chunk, int qpad) {
-    QChunk<C> r;
-#pragma unroll
-    for (int k = 0; k < (C + 3) / 4; ++k) r.w[k] = 0;
-    const long off = (long)chunk * C;
-    if (off < qpad) {
-        if constexpr (C == 1) r.w[0] = q[off];
-        else if constexpr (C == 2) r.w[0] = *reinterpret_cast<const uint16_t*>(q + off);
-        else if constexpr (C == 4) r.w[0] = *reinterpret_cast<const uint32_t*>(q + off);
-        else if constexpr (C == 8) {
-            uint2 v = *reinterpret_cast<const uint2*>(q + off); r.w[0] = v.x; r.w[1] = v.y;
-        } else if constexpr (C == 16) {
-            uint4 v = *reinterpret_cast<const uint4*>(q + off);
-            r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
-        } else {
-            static_assert(C == 32, "unsupported chunk");
-            uint4 v = *reinterpret_cast<const uint4*>(q + off);
-            uint4 u = *reinterpret_cast<const uint4*>(q + off + 16);
-            r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
-            r.w[4] = u.x; r.w[5] = u.y; r.w[6] = u.z; r.w[7] = u.w;
-        }
-    }
-    return r;
-}
-
-template <int C>
-__device__ __forceinline__ void store_dir(uint8_t* p, const uint32_t (&d)[(C + 7) / 8]) {
-    if constexpr (C == 1) *p = (uint8_t)d[0];          // one nibble per byte (C==1 only)
-    else if constexpr (C == 2) *p = (uint8_t)d[0];
-    else if constexpr (C == 4) *reinterpret_cast<uint16_t*>(p) = (uint16_t)d[0];
-    else if constexpr (C == 8) *reinterpret_cast<uint32_t*>(p) = d[0];
-    else if constexpr (C == 16) *reinterpret_cast<uint2*>(p) = make_uint2(d[0], d[1]);
-    else *reinterpret_cast<uint4*>(p) = make_uint4(d[0], d[1], d[2], d[3]);
-}
-
-// bytes of direction storage per chunk
-__host__ __device__ constexpr int dir_chunk_bytes(int C) { return C >= 2 ? C / 2 : 1; }
-
 // "row -1" value of slot j: src/ksw.c:569-572 (global) / :692-694 (extension)
 template <int KIND>
 __device__ __forceinline__ int init_h(int j, int qlen, int w, int h0, int o_ins, int e_ins) {
@@ -94,45 +60,73 @@ __device__ __forceinline__ int init_h(int j, int qlen, int w, int h0, int o_ins,
     }
 }
 
-template <int C, int KIND>
+template <int G> struct Vec;
+template <> struct Vec<1> {
+    static __device__ __forceinline__ void ld(const int* p, int (&v)[1]) { v[0] = p[0]; }
+    static __device__ __forceinline__ void st(int* p, const int (&v)[1]) { p[0] = v[0]; }
+    static __device__ __forceinline__ void ldq(const uint16_t* p, uint32_t (&v)[1]) { v[0] = p[0]; }
+};
+template <> struct Vec<2> {
+    static __device__ __forceinline__ void ld(const int* p, int (&v)[2]) {
+        int2 t = *reinterpret_cast<const int2*>(p); v[0] = t.x; v[1] = t.y; }
+    static __device__ __forceinline__ void st(int* p, const int (&v)[2]) {
+        *reinterpret_cast<int2*>(p) = make_int2(v[0], v[1]); }
+    static __device__ __forceinline__ void ldq(const uint16_t* p, uint32_t (&v)[2]) {
+        uint32_t t = *reinterpret_cast<const uint32_t*>(p); v[0] = t & 0xffffu; v[1] = t >> 16; }
+};
+template <> struct Vec<4> {
+    static __device__ __forceinline__ void ld(const int* p, int (&v)[4]) {
+        int4 t = *reinterpret_cast<const int4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    static __device__ __forceinline__ void st(int* p, const int (&v)[4]) {
+        *reinterpret_cast<int4*>(p) = make_int4(v[0], v[1], v[2], v[3]); }
+    static __device__ __forceinline__ void ldq(const uint16_t* p, uint32_t (&v)[4]) {
+        uint2 t = *reinterpret_cast<const uint2*>(p);
+        v[0] = t.x & 0xffffu; v[1] = t.x >> 16; v[2] = t.y & 0xffffu; v[3] = t.y >> 16; }
+};
+
+// bytes of direction storage per lane per tile (G nibbles; one byte when G==1)
+__host__ __device__ constexpr int dir_lane_bytes(int G) { return G >= 2 ? G / 2 : 1; }
+// tiles a row can span: columns [beg & ~(G-1), end] with end-beg <= ncol
+__host__ __device__ inline int row_tiles_for(long ncol, int G) { return (int)((ncol + G) / (32 * G)) + 1; }
+// shared-memory bytes one warp needs for a window of S slots
+__host__ __device__ constexpr size_t warp_smem_bytes(int S) { return (size_t)S * 10; }
+
+template <int G, int KIND>
 __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
                           uint8_t* __restrict__ zbase, DResult* __restrict__ res,
-                          const uint2* __restrict__ smat /* [kMaxMats][8] */, const int lane)
+                          const uint2* __restrict__ smat /* [kMaxMats][8] */,
+                          int* __restrict__ hb, int* __restrict__ eb, uint16_t* __restrict__ qb,
+                          const int S, const int lane)
 {
-    constexpr int CS = (C == 1 ? 0 : C == 2 ? 1 : C == 4 ? 2 : C == 8 ? 3 : C == 16 ? 4 : 5);
+    constexpr int GS = (G == 1 ? 0 : G == 2 ? 1 : 2);
     constexpr int EINIT = (KIND == kKindGlobal) ? kNegInf : 0;
-    constexpr int NDW = (C + 7) / 8;
+    constexpr int FINIT = (KIND == kKindGlobal) ? kNegInf : 0;
+    const int SM = S - 1;
     const int qlen = T.qlen, tlen = T.tlen, w = T.w, h0 = T.h0;
     const int o_del = T.o_del, e_del = T.e_del, o_ins = T.o_ins, e_ins = T.e_ins;
     const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
     const uint8_t* __restrict__ qseq = pool + (size_t)T.q_off32 * 32;
     const uint8_t* __restrict__ tseq = pool + (size_t)T.t_off32 * 32;
-    const int qpad = (qlen + 1 + 31) & ~31;
     const bool want = T.want_dir != 0;
-    const int RW = T.row_chunks;
+    const int RT = T.row_chunks;                        // tiles per stored row
     int2* __restrict__ rowmeta = reinterpret_cast<int2*>(zbase + T.z_off);
     uint8_t* __restrict__ zdir = zbase + T.z_off + (KIND == kKindExtend ? ext_meta_bytes(tlen) : 0);
+    const size_t zrow_bytes = (size_t)RT * 32 * dir_lane_bytes(G);
     const uint2* __restrict__ mrows = smat + (int)T.mat_id * 8;
+    const int qpad = (qlen + 1 + 31) & ~31;
 
-    int hs[C], es[C];
-    uint32_t qsel[C];
-    int chunk = lane;
-    QChunk<C> qnext;
-
-    auto adopt = [&](const QChunk<C>& qc) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const int j = chunk * C + c;
-            hs[c] = init_h<KIND>(j, qlen, w, h0, o_ins, e_ins);
-            es[c] = EINIT;
-            qsel[c] = sel_for_code((qc.w[c / 4] >> (8 * (c & 3))) & 0xffu);
-        }
-    };
-    {
-        QChunk<C> q0 = load_qchunk<C>(qseq, chunk, qpad);
-        qnext = load_qchunk<C>(qseq, chunk + 32, qpad);
-        adopt(q0);
+    // ---- window initialisation: slots 0..send_0, selectors for the first columns
+    int slot_hi = (w + 1 < qlen) ? w + 1 : qlen;        // slots [0, slot_hi] are initialised
+    for (int j = lane; j <= slot_hi; j += 32) {
+        hb[j & SM] = init_h<KIND>(j, qlen, w, h0, o_ins, e_ins);
+        eb[j & SM] = EINIT;
     }
+    int q_hi = 0;                                       // selectors of columns [.., q_hi) are in qb
+    while (q_hi < slot_hi + 1 && q_hi < qpad) {
+        qb[(q_hi + lane) & SM] = (uint16_t)sel_for_code(qseq[q_hi + lane]);
+        q_hi += 32;
+    }
+    uint32_t qpre = (q_hi < qpad) ? qseq[q_hi + lane] : 0u;    // next 32 codes, prefetched
 
     int beg = 0, end = qlen;
     int mx = h0, mx_i = -1, mx_j = -1, mx_ie = -1, gscore = -1, max_off = 0;
@@ -140,6 +134,7 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
     const int tpad = (tlen + 31) & ~31;
     uint32_t tcur = (lane < tpad) ? tseq[lane] : 0u;
     uint32_t tnext = (32 + lane < tpad) ? tseq[32 + lane] : 0u;
+    __syncwarp();
     int i = 0;
     for (; i < tlen; ++i) {
         if ((i & 31) == 0 && i) {
@@ -148,21 +143,32 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
         }
         const int tb = __shfl_sync(kFull, (int)tcur, i & 31) & 7;
         const int sbeg = i > w ? i - w : 0;
+        const int send = i + w + 1 < qlen ? i + w + 1 : qlen;
         if (KIND == kKindExtend) {
             if (beg < i - w) beg = i - w;
-            if (end > i + w + 1) end = i + w + 1;
-            if (end > qlen) end = qlen;
+            if (end > send) end = send;
         } else {
             beg = sbeg;
-            end = i + w + 1 < qlen ? i + w + 1 : qlen;
+            end = send;
         }
-        if ((chunk + 1) * C <= sbeg) {          // my chunk is dead: adopt the next one
-            chunk += 32;
-            QChunk<C> qc = qnext;
-            qnext = load_qchunk<C>(qseq, chunk + 32, qpad);
-            adopt(qc);
+        // admit the column that enters the static window, keep selectors ahead of it
+        bool touched = false;
+        if (send > slot_hi) {
+            slot_hi = send;
+            if (lane == 0) {
+                hb[send & SM] = init_h<KIND>(send, qlen, w, h0, o_ins, e_ins);
+                eb[send & SM] = EINIT;
+            }
+            touched = true;
         }
-        const int j0 = chunk * C;
+        if (q_hi < send + 1 && q_hi < qpad) {
+            qb[(q_hi + lane) & SM] = (uint16_t)sel_for_code(qpre);
+            q_hi += 32;
+            qpre = (q_hi < qpad) ? qseq[q_hi + lane] : 0u;
+            touched = true;
+        }
+        if (touched) __syncwarp();
+
         const uint2 mrow = mrows[tb];
         int h1init;
         if (KIND == kKindExtend) {
@@ -171,103 +177,121 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
         } else {
             h1init = beg == 0 ? -(o_del + e_del * (i + 1)) : kNegInf;
         }
-        // lane-local active range [lo, hi) in chunk coordinates
-        int lo = beg - j0; lo = lo < 0 ? 0 : (lo > C ? C : lo);
-        int hi = end - j0; hi = hi < 0 ? 0 : (hi > C ? C : hi);
+        const int base = beg & ~(G - 1);
+        const int ntile = end >= base ? ((end - base) >> (5 + GS)) + 1 : 0;
+        int carryF = FINIT + beg * e_ins;       // max over finished tiles of u_k, seeded with F(i,beg)
+        int carryH = h1init;                    // H(i, j0-1) for lane 0 of the next tile
+        int m = 0, mj = -1;                     // row maximum, last argmax (extension)
+        int nzlo = INT_MAX, nzhi = -1;          // first / last non-zero slot after this row (extension)
+        int hq = 0;                             // H(i, qlen-1) when this lane computes it
+        uint8_t* zrow = zdir + (size_t)i * zrow_bytes;
 
-        // ---- pass 1: M and the lane maximum of u_j = t_j + (j+1)*e_ins
-        int Mv[C];
-        int U = INT_MIN;
-        int ue = (j0 + 1) * e_ins;
+        for (int tile = 0; tile < ntile; ++tile) {
+            const int j0 = base + ((tile << 5) + lane) * G;
+            const int s0 = j0 & SM;
+            const bool mine = (j0 <= end) && (j0 + G > beg);     // any slot of mine in [beg, end]
+            int hv[G], ev[G]; uint32_t qs[G];
+            int Mv[G], pre[G];
+            int lu = INT_MIN;
+            if (mine) {
+                Vec<G>::ld(hb + s0, hv); Vec<G>::ld(eb + s0, ev); Vec<G>::ldq(qb + s0, qs);
+                int ue = (j0 + 1) * e_ins;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const int raw = hs[c];
-            const int s = prmt_s8(mrow.x, mrow.y, qsel[c]);
-            int M;
-            if (KIND == kKindExtend) M = raw ? raw + s : 0; else M = raw + s;
-            Mv[c] = M;
-            int t = M - oe_ins;
-            if (KIND == kKindExtend) t = t > 0 ? t : 0;
-            const int u = t + ue;
-            ue += e_ins;
-            if (c >= lo && c < hi) U = U > u ? U : u;
-        }
-        // ---- exclusive prefix maximum across lanes, in column order
-        const int lane_beg = (beg >> CS) & 31;
-        const int rank = (lane - lane_beg) & 31;
-        const int nact = end > beg ? ((end - 1) >> CS) - (beg >> CS) + 1 : 0;   // lanes with active cells
-        int v = U;
+                for (int c = 0; c < G; ++c) {
+                    const int j = j0 + c;
+                    const int raw = hv[c];
+                    const int s = prmt_s8(mrow.x, mrow.y, qs[c]);
+                    int M;
+                    if (KIND == kKindExtend) M = raw ? raw + s : 0; else M = raw + s;
+                    Mv[c] = M;
+                    int t = M - oe_ins;
+                    if (KIND == kKindExtend) t = t > 0 ? t : 0;
+                    const int u = t + ue;
+                    ue += e_ins;
+                    pre[c] = lu;
+                    if (j >= beg && j < end) lu = lu > u ? lu : u;
+                }
+            }
+            // inclusive prefix maximum of the lane totals
+            int incl = lu;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            if (d < nact) {
-                const int o = __shfl_sync(kFull, v, (lane - d) & 31);
-                if (rank >= d) v = v > o ? v : o;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl = incl > o ? incl : o;
+            }
+            int pin = __shfl_up_sync(kFull, incl, 1);
+            if (lane == 0) pin = INT_MIN;
+            pin = pin > carryF ? pin : carryF;
+            {
+                const int tot = __shfl_sync(kFull, incl, 31);
+                carryF = carryF > tot ? carryF : tot;
+            }
+            uint32_t dirw = 0;
+            int hnew[G];
+            if (mine) {
+#pragma unroll
+                for (int c = 0; c < G; ++c) {
+                    const int j = j0 + c;
+                    const bool act = (j >= beg && j < end);
+                    const int M = Mv[c];
+                    int e = ev[c];
+                    const int px = pin > pre[c] ? pin : pre[c];
+                    const int f = px - j * e_ins;
+                    int h; uint32_t d;
+                    if (KIND == kKindExtend) {          // ties: E over M, F over both (src/ksw.c:738-741)
+                        d = M > e ? 0u : 1u; h = M > e ? M : e;
+                        d = h > f ? d : 2u;  h = h > f ? h : f;
+                    } else {                            // ties: M over E over F (src/ksw.c:598-601)
+                        d = M >= e ? 0u : 1u; h = M >= e ? M : e;
+                        d = h >= f ? d : 2u;  h = h >= f ? h : f;
+                    }
+                    hnew[c] = h;
+                    if (KIND == kKindExtend) {
+                        if (act) { mj = m > h ? mj : j; m = m > h ? m : h; }   // last argmax
+                        if (j == qlen - 1) hq = h;
+                    }
+                    int t = M - oe_del;
+                    if (KIND == kKindExtend) t = t > 0 ? t : 0;
+                    e -= e_del;
+                    d |= e > t ? 4u : 0u;
+                    e = e > t ? e : t;
+                    if (act) ev[c] = e;
+                    if (j == end) ev[c] = EINIT;                       // eh[end].e (src/ksw.c:632 / :758)
+                    t = M - oe_ins;
+                    if (KIND == kKindExtend) t = t > 0 ? t : 0;
+                    d |= (f - e_ins) > t ? 8u : 0u;
+                    dirw |= d << (4 * c);
+                }
+            }
+            // shifted H row: slot j <- H(i, j-1) for beg <= j <= end
+            const int hlast = mine ? hnew[G - 1] : 0;
+            int hleft = __shfl_up_sync(kFull, hlast, 1);
+            if (lane == 0) hleft = carryH;
+            carryH = __shfl_sync(kFull, hlast, 31);
+            if (mine) {
+#pragma unroll
+                for (int c = G - 1; c >= 0; --c) {
+                    const int j = j0 + c;
+                    int nh = c == 0 ? hleft : hnew[c - 1];
+                    if (j == beg) nh = h1init;
+                    if (j >= beg && j <= end) hv[c] = nh;
+                    if (KIND == kKindExtend) {
+                        if (j >= beg && j <= end && (hv[c] | ev[c]) != 0) {
+                            if (j < end) nzlo = nzlo < j ? nzlo : j;
+                            nzhi = nzhi > j ? nzhi : j;
+                        }
+                    }
+                }
+                Vec<G>::st(hb + s0, hv); Vec<G>::st(eb + s0, ev);
+                if (want && j0 < end) {
+                    uint8_t* p = zrow + (size_t)((tile << 5) + lane) * dir_lane_bytes(G);
+                    if (G == 4) *reinterpret_cast<uint16_t*>(p) = (uint16_t)dirw;
+                    else *p = (uint8_t)dirw;
+                }
             }
         }
-        int P = __shfl_sync(kFull, v, (lane - 1) & 31);
-        if (rank == 0) P = INT_MIN;
-        const int ja = j0 > beg ? j0 : beg;
-        {
-            const int base = (KIND == kKindGlobal ? kNegInf : 0) + beg * e_ins;
-            P = P > base ? P : base;
-        }
-        int f = P - ja * e_ins;
-
-        // ---- pass 2: H, E', F', direction nibbles, row maximum
-        int m = 0, mj = -1;
-        uint32_t dirw[NDW];
-#pragma unroll
-        for (int k = 0; k < NDW; ++k) dirw[k] = 0;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const bool act = (c >= lo && c < hi);
-            const int M = Mv[c];
-            int e = es[c];
-            int h; uint32_t d;
-            if (KIND == kKindExtend) {          // ties: E over M, F over both (src/ksw.c:738-741)
-                d = M > e ? 0u : 1u; h = M > e ? M : e;
-                d = h > f ? d : 2u;  h = h > f ? h : f;
-            } else {                            // ties: M over E over F (src/ksw.c:598-601)
-                d = M >= e ? 0u : 1u; h = M >= e ? M : e;
-                d = h >= f ? d : 2u;  h = h >= f ? h : f;
-            }
-            Mv[c] = h;                          // Mv now holds H(i, j)
-            if (KIND == kKindExtend) {
-                if (act) { mj = m > h ? mj : j0 + c; m = m > h ? m : h; }   // last argmax
-            }
-            int t = M - oe_del;
-            if (KIND == kKindExtend) t = t > 0 ? t : 0;
-            e -= e_del;
-            d |= e > t ? 4u : 0u;
-            e = e > t ? e : t;
-            if (act) es[c] = e;
-            t = M - oe_ins;
-            if (KIND == kKindExtend) t = t > 0 ? t : 0;
-            int f2 = f - e_ins;
-            d |= f2 > t ? 8u : 0u;
-            f2 = f2 > t ? f2 : t;
-            if (act) f = f2;
-            dirw[c / 8] |= d << (4 * (c & 7));
-        }
-        // ---- commit the shifted H row: slot j <- H(i, j-1) for beg <= j <= end
-        const int hleft = __shfl_sync(kFull, Mv[C - 1], (lane - 1) & 31);
-        {
-            const int clo = beg - j0, chi = end - j0;   // inclusive range [clo, chi]
-#pragma unroll
-            for (int c = C - 1; c >= 0; --c) {
-                int hv = c == 0 ? hleft : Mv[c - 1];
-                if (c == clo) hv = h1init;
-                if (c >= clo && c <= chi) hs[c] = hv;
-                if (c == chi && chi >= clo) es[c] = EINIT;
-            }
-        }
-        if (want) {
-            if (KIND == kKindExtend && lane == 0) rowmeta[i] = make_int2(beg, end);
-            if (hi > lo) {
-                const long rel = (long)i * RW + (chunk - (sbeg >> CS));
-                store_dir<C>(zdir + rel * dir_chunk_bytes(C), dirw);
-            }
-        }
+        __syncwarp();
+        if (want && KIND == kKindExtend && lane == 0) rowmeta[i] = make_int2(beg, end);
         cells += end > beg ? end - beg : 0;
         if (KIND == kKindExtend) {
             const int gm = __reduce_max_sync(kFull, m);
@@ -275,13 +299,7 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
             const int jfin = beg > end ? beg : end;          // value of j when the column loop ends
             if (jfin == qlen) {                              // src/ksw.c:759-762
                 int h1 = h1init;
-                if (end > beg) {                             // H(i, qlen-1) lives in some lane's Mv
-                    const int cq = (qlen - 1) & (C - 1);
-                    int hv = 0;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) if (c == cq) hv = Mv[c];
-                    h1 = __shfl_sync(kFull, hv, ((qlen - 1) >> CS) & 31);
-                }
+                if (end > beg) h1 = __shfl_sync(kFull, hq, ((qlen - 1 - base) >> GS) & 31);
                 mx_ie = gscore > h1 ? mx_ie : i;
                 gscore = gscore > h1 ? gscore : h1;
             }
@@ -298,22 +316,8 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
                 if (drop) { ++i; break; }
             }
             // band trim (:775-778) over the slots as they stand after this row
-            uint32_t nzmask = 0;
-#pragma unroll
-            for (int c = 0; c < C; ++c) nzmask |= ((hs[c] | es[c]) != 0 ? 1u : 0u) << c;
-            const int clo = beg - j0, chi = end - j0;        // slots [beg, end]
-            uint32_t inmask = 0;
-            if (chi >= 0 && clo < C && chi >= clo) {
-                const int a = clo < 0 ? 0 : clo, b = chi > C - 1 ? C - 1 : chi;
-                inmask = (b - a + 1 >= 32) ? 0xffffffffu : (((1u << (b - a + 1)) - 1u) << a);
-            }
-            nzmask &= inmask;
-            uint32_t lomask = nzmask;
-            if (chi >= 0 && chi < C) lomask &= ~(1u << chi);     // first scan excludes slot `end`
-            const int mylo = lomask ? j0 + __ffs(lomask) - 1 : INT_MAX;
-            const int myhi = nzmask ? j0 + 31 - __clz(nzmask) : -1;
-            int nb = __reduce_min_sync(kFull, mylo);
-            int nh = __reduce_max_sync(kFull, myhi);
+            int nb = __reduce_min_sync(kFull, nzlo);
+            int nh = __reduce_max_sync(kFull, nzhi);
             nb = nb < end ? nb : end;
             if (nh < nb) nh = nb - 1;
             beg = nb;
@@ -324,14 +328,7 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
     // ---- results
     int score = 0, ti = -1, tk = -1;
     if (KIND == kKindGlobal) {
-        // eh[qlen].h after the last row (src/ksw.c:634)
-        const int cq = qlen & (C - 1);
-        int hv = 0;
-#pragma unroll
-        for (int c = 0; c < C; ++c) if (c == cq) hv = hs[c];
-        const bool owner = chunk == (qlen >> CS);
-        const unsigned who = __ballot_sync(kFull, owner);
-        score = who ? __shfl_sync(kFull, hv, __ffs(who) - 1) : init_h<KIND>(qlen, qlen, w, h0, o_ins, e_ins);
+        score = hb[qlen & SM];                               // eh[qlen].h (src/ksw.c:634)
         ti = tlen - 1;
         tk = (ti + w + 1 < qlen ? ti + w + 1 : qlen) - 1;     // :638
     } else {
@@ -346,28 +343,35 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
         r.n_cigar = 0; r.rows = i; r.cigar_off = 0; r.cells = cells;
         *res = r;
     }
+    __syncwarp();
 }
 
 // Persistent warps: each warp pulls the next task index of its class from a
 // global counter (tasks are pre-sorted by descending cost on the host).
-template <int C, int KIND>
-__global__ void __launch_bounds__(128)
+// Dynamic shared memory: blockDim.x/32 windows of warp_smem_bytes(S).
+template <int G, int KIND>
+__global__ void __launch_bounds__(256)
 fill_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order, int n,
             const uint8_t* __restrict__ pool, uint8_t* __restrict__ zbase,
             DResult* __restrict__ results, const uint2* __restrict__ gmat,
-            unsigned int* __restrict__ counter)
+            unsigned int* __restrict__ counter, int S)
 {
     __shared__ uint2 smat[kMaxMats * 8];
+    extern __shared__ __align__(16) uint8_t dyn[];
     for (int k = threadIdx.x; k < kMaxMats * 8; k += blockDim.x) smat[k] = gmat[k];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint8_t* mine = dyn + (size_t)wid * warp_smem_bytes(S);
+    int* hb = reinterpret_cast<int*>(mine);
+    int* eb = hb + S;
+    uint16_t* qb = reinterpret_cast<uint16_t*>(eb + S);
     for (;;) {
         unsigned int t = 0;
         if (lane == 0) t = atomicAdd(counter, 1u);
         t = __shfl_sync(kFull, t, 0);
         if (t >= (unsigned)n) break;
         const int idx = order[t];
-        fill_task<C, KIND>(tasks[idx], pool, zbase, results + idx, smat, lane);
+        fill_task<G, KIND>(tasks[idx], pool, zbase, results + idx, smat, hb, eb, qb, S, lane);
     }
 }
 

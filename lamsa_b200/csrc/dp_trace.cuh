@@ -41,11 +41,12 @@ trace_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order,
     if (!T.want_dir) return;
     DResult* R = results + idx;
     int i = R->ti, k = R->tk;
-    const int w = T.w, C = 1 << T.cshift, cs = T.cshift, RW = T.row_chunks;
+    const int w = T.w, G = 1 << T.cshift, gs = T.cshift;
     const bool ext = T.kind == kKindExtend;
     const int2* __restrict__ rowmeta = reinterpret_cast<const int2*>(zbase + T.z_off);
     const uint8_t* __restrict__ zdir = zbase + T.z_off + (ext ? ext_meta_bytes(T.tlen) : 0);
-    const int cb = C >= 2 ? C / 2 : 1;
+    const int lb = G >= 2 ? G / 2 : 1;                       // bytes per lane per tile
+    const size_t zrow_bytes = (size_t)T.row_chunks * 32 * lb;
 
     CigarWriter W;
     W.top = ctmp + T.ctmp_end; W.floor = W.top - T.ctmp_cap;
@@ -64,13 +65,12 @@ trace_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order,
             computed = k >= sbeg && k < send;
         }
         if (computed) {
-            const long rel = (long)i * RW + ((k >> cs) - (sbeg >> cs));
-            uint32_t nib;
-            if (C == 1) nib = zdir[rel] & 15u;
-            else {
-                const uint8_t b = zdir[rel * cb + ((k & (C - 1)) >> 1)];
-                nib = (k & 1) ? (b >> 4) : (b & 15u);
-            }
+            // fill layout: row i stores, from column base = beg_i & ~(G-1), G nibbles per lane
+            const int base = (ext ? rb : sbeg) & ~(G - 1);
+            const int rel = k - base;
+            const uint8_t* p = zdir + (size_t)i * zrow_bytes + (size_t)(rel >> gs) * lb;
+            uint32_t v = (G == 4) ? *reinterpret_cast<const uint16_t*>(p) : *p;
+            const uint32_t nib = (v >> (4 * (rel & (G - 1)))) & 15u;
             // byte the reference would hold: f<<4 | e<<2 | h  (src/ksw.c:556)
             if (which == 0) which = nib & 3;
             else if (which == 1) which = (nib >> 2) & 1;
