@@ -14,6 +14,7 @@
 
 #include "../../include/lamsa_b200.h"
 #include "dp_fill.cuh"
+#include "dp_fill16.cuh"
 #include "dp_trace.cuh"
 #include "int_peak.cuh"
 
@@ -34,18 +35,22 @@ extern "C" const char* lb2_last_error(void) { return g_err.c_str(); }
 extern "C" void lb2_free(void* p) { free(p); }
 
 // ----------------------------------------------------------------- context --
-// A launch class = (kind, G = columns per lane per tile, S = shared-memory window slots).
-constexpr int kMinLogS = 6, kMaxLogS = 14;          // 64 .. 16384 slots (10 bytes each) per warp
+// A launch class = (kind, variant, S = shared-memory window slots).
+// variants: 0..2 int32 lanes with G = 1,2,4 columns per lane; 3,4 packed int16 with NP = 2,4 pairs per lane.
+constexpr int kMinLogS = 6, kMaxLogS = 14;          // 64 .. 16384 slots per warp
 constexpr int kNumLogS = kMaxLogS - kMinLogS + 1;
-constexpr int kNumClass = 2 * 3 * kNumLogS;
+constexpr int kNumVar = 5;
+constexpr int kNumClass = 2 * kNumVar * kNumLogS;
 constexpr size_t kMaxDynSmem = 200 * 1024;
-static inline int class_id(int kind, int gs, int logS) { return (kind * 3 + gs) * kNumLogS + (logS - kMinLogS); }
-static inline int class_kind(int c) { return c / (3 * kNumLogS); }
-static inline int class_gs(int c) { return (c / kNumLogS) % 3; }
+static inline int class_id(int kind, int var, int logS) { return (kind * kNumVar + var) * kNumLogS + (logS - kMinLogS); }
+static inline int class_kind(int c) { return c / (kNumVar * kNumLogS); }
+static inline int class_var(int c) { return (c / kNumLogS) % kNumVar; }
 static inline int class_logS(int c) { return c % kNumLogS + kMinLogS; }
-static inline int class_warps(int logS) {            // warps per block
+static inline int var_gshift(int var) { return var < 3 ? var : var - 1; }     // log2(columns per lane)
+static inline size_t var_warp_smem(int var, int S) { return var < 3 ? warp_smem_bytes(S) : warp_smem_bytes16(S); }
+static inline int class_warps(int var, int logS) {   // warps per block
     int wpb = 8;
-    while (wpb > 1 && (size_t)wpb * warp_smem_bytes(1 << logS) > 160 * 1024) wpb >>= 1;
+    while (wpb > 1 && (size_t)wpb * var_warp_smem(var, 1 << logS) > 160 * 1024) wpb >>= 1;
     return wpb;
 }
 
@@ -61,9 +66,19 @@ struct lb2_ctx {
 
 typedef void (*fill_fn)(const DTask*, const int32_t*, int, const uint8_t*, uint8_t*, DResult*,
                         const uint2*, unsigned int*, int);
-static fill_fn fill_table(int kind, int gs) {
-    if (kind == kKindGlobal) return gs == 0 ? fill_kernel<1, kKindGlobal> : gs == 1 ? fill_kernel<2, kKindGlobal> : fill_kernel<4, kKindGlobal>;
-    return gs == 0 ? fill_kernel<1, kKindExtend> : gs == 1 ? fill_kernel<2, kKindExtend> : fill_kernel<4, kKindExtend>;
+static fill_fn fill_table(int kind, int var) {
+    if (kind == kKindGlobal) {
+        switch (var) {
+            case 0: return fill_kernel<1, kKindGlobal>;   case 1: return fill_kernel<2, kKindGlobal>;
+            case 2: return fill_kernel<4, kKindGlobal>;   case 3: return fill16_kernel<2, kKindGlobal>;
+            default: return fill16_kernel<4, kKindGlobal>;
+        }
+    }
+    switch (var) {
+        case 0: return fill_kernel<1, kKindExtend>;   case 1: return fill_kernel<2, kKindExtend>;
+        case 2: return fill_kernel<4, kKindExtend>;   case 3: return fill16_kernel<2, kKindExtend>;
+        default: return fill16_kernel<4, kKindExtend>;
+    }
 }
 
 extern "C" int lb2_ctx_create(int device, lb2_ctx** out) {
@@ -86,8 +101,8 @@ extern "C" int lb2_ctx_create(int device, lb2_ctx** out) {
     CU(cudaMemGetInfo(&fr, &tot));
     c->scratch_limit = (uint64_t)(fr * 0.40);
     for (int kind = 0; kind < 2; ++kind)
-        for (int gs = 0; gs < 3; ++gs)
-            CU(cudaFuncSetAttribute(fill_table(kind, gs), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+        for (int var = 0; var < kNumVar; ++var)
+            CU(cudaFuncSetAttribute(fill_table(kind, var), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
     *out = c;
     return 0;
 }
@@ -155,12 +170,38 @@ static int extend_band(int w, int qlen, int m, const int8_t* mat, int end_bonus,
     return w;
 }
 
-// columns per lane per tile, from the widest band a row can have
-static int pick_gshift(long ncol) { return ncol <= 36 ? 0 : ncol <= 72 ? 1 : 2; }
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
+// Can every value of this task live in the packed-int16 domain of dp_fill16.cuh?
+static bool fits_int16(const lb2_task& t, int w) {
+    int maxs = 0, mins = 0;
+    for (int a = 0; a < t.m * t.m; ++a) { maxs = std::max<int>(maxs, t.mat[a]); mins = std::min<int>(mins, t.mat[a]); }
+    const long ncol = std::min<long>(t.qlen, 2L * w + 1);
+    const long maxo = std::max(t.o_del, t.o_ins), maxe = std::max(t.e_del, t.e_ins);
+    if (t.o_del < 0 || t.o_ins < 0 || maxe > 255 || maxo + maxe > 500) return false;
+    const long scan = (ncol + 300) * (long)t.e_ins;
+    if (t.kind == LB2_KIND_EXTEND) {
+        if (maxs > 1) return false;                       // M = min(H+s, 2H) needs s <= H for H >= 1
+        const long maxh = (long)t.h0 + (long)t.qlen * maxs;
+        return maxh <= 16000 && maxh + scan <= 32000;
+    }
+    const long lower = (long)(-mins) * std::min(t.qlen, t.tlen) + 2 * maxo + maxe * ((long)t.qlen + t.tlen + 2) + (maxo + maxe) + 64;
+    return lower <= 30000 && (long)t.qlen * maxs + scan <= 32000;
+}
+
+// kernel variant from the widest band a row can have
+static int pick_variant(const lb2_task& t, int w, long ncol) {
+    static const int use16 = env_int("LB2_P16", 1), p16_min = env_int("LB2_P16_MIN", 37), np4_min = env_int("LB2_NP4_MIN", 200);
+    if (use16 && ncol >= p16_min && fits_int16(t, w)) return ncol >= np4_min ? 4 : 3;
+    return ncol <= 36 ? 0 : ncol <= 72 ? 1 : 2;
+}
 // window slots: the whole eh[] array when it is small, else band window + look-ahead
 static int pick_logS(int qlen, int w) {
     const long qpad = ((long)qlen + 1 + 31) & ~31L;
-    const long need = std::min<long>(qpad, 2L * w + 72);
+    const long need = std::min<long>(qpad, 2L * w + 76);
     int l = kMinLogS;
     while ((1L << l) < need && l <= kMaxLogS) ++l;
     return l <= kMaxLogS ? l : -1;
@@ -211,7 +252,7 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     // ---- pass 1: validate, classify, lay out pool / scratch
     std::vector<uint64_t> qoff(n), toff(n), zsz(n);
     std::vector<int32_t> wfin(n), ctmpw(n);
-    std::vector<int8_t> cshift(n), matid(n), logS(n);
+    std::vector<int8_t> cshift(n), matid(n), logS(n), variant(n);
     std::vector<std::vector<int8_t>> mats;           // distinct matrices, each 64 entries (8x8, zero padded)
     b->flags.resize(n);
     uint64_t pool = 0;
@@ -233,10 +274,11 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
         if (w < 0) return fail("task %lld: negative band", (long long)i);
         wfin[i] = w;
         const long ncol_i = std::min<long>(t.qlen, 2L * w + 1);
-        const int cs = pick_gshift(ncol_i);
+        const int var = pick_variant(t, w, ncol_i);
+        const int cs = var_gshift(var);
         const int ls = pick_logS(t.qlen, w);
         if (ls < 0) return fail("task %lld: qlen %d with band %d needs a window beyond %d slots (not supported yet)", (long long)i, t.qlen, w, 1 << kMaxLogS);
-        cshift[i] = (int8_t)cs; logS[i] = (int8_t)ls;
+        cshift[i] = (int8_t)cs; logS[i] = (int8_t)ls; variant[i] = (int8_t)var;
         // matrix table
         int8_t m8[64]; memset(m8, 0, sizeof m8);
         for (int a = 0; a < t.m; ++a) for (int c = 0; c < t.m; ++c) m8[a * 8 + c] = t.mat[a * t.m + c];
@@ -296,7 +338,7 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     for (auto& wv : b->waves) {
         std::vector<int32_t> idx(wv.count);
         for (int k = 0; k < wv.count; ++k) idx[k] = wv.first + k;
-        auto cls = [&](int32_t a) { return class_id((int)tasks[a].kind, cshift[a], logS[a]); };
+        auto cls = [&](int32_t a) { return class_id((int)tasks[a].kind, variant[a], logS[a]); };
         auto cost = [&](int32_t a) {
             return (int64_t)tasks[a].tlen * std::min<int64_t>(tasks[a].qlen, 2L * wfin[a] + 1);
         };
@@ -337,7 +379,7 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
             d.mat_id = (uint8_t)matid[i]; d.cshift = (uint8_t)cshift[i];
             const long ncol = std::min<long>(t.qlen, 2L * wfin[i] + 1);
             d.row_chunks = row_tiles_for(ncol, 1 << cshift[i]);
-            d.pad = 0;
+            d.dir_fmt = variant[i] >= 3 ? 1 : 0;
             uint8_t* q = hp + qoff[i];
             const uint64_t qp = ((uint64_t)t.qlen + 1 + 31) & ~uint64_t(31);
             if (t.qlen) memcpy(q, t.query, t.qlen);
@@ -414,20 +456,20 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
         for (int k = 0; k < kNumClass; ++k) {
             const int cnt = wv.cls_off[k + 1] - wv.cls_off[k];
             if (!cnt) continue;
-            const int kind = class_kind(k), gs = class_gs(k), ls = class_logS(k);
-            const int wpb = class_warps(ls);
-            const size_t smem = (size_t)wpb * warp_smem_bytes(1 << ls);
+            const int kind = class_kind(k), var = class_var(k), ls = class_logS(k);
+            const int wpb = class_warps(var, ls);
+            const size_t smem = (size_t)wpb * var_warp_smem(var, 1 << ls);
             if (!c->occ[k]) {
                 int nb = 0;
-                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fill_table(kind, gs), wpb * 32, smem));
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fill_table(kind, var), wpb * 32, smem));
                 c->occ[k] = nb > 0 ? nb : 1;
             }
             int grid = (cnt + wpb - 1) / wpb;
             const int cap = c->sm_count * c->occ[k];
             if (grid > cap) grid = cap;
-            fill_table(kind, gs)<<<grid, wpb * 32, smem, s>>>(b->d_tasks, b->d_order + wv.first + wv.cls_off[k], cnt,
-                                                            b->d_pool, c->d_z, b->d_results, b->d_mats,
-                                                            b->d_counters + wi * kNumClass + k, 1 << ls);
+            fill_table(kind, var)<<<grid, wpb * 32, smem, s>>>(b->d_tasks, b->d_order + wv.first + wv.cls_off[k], cnt,
+                                                             b->d_pool, c->d_z, b->d_results, b->d_mats,
+                                                             b->d_counters + wi * kNumClass + k, 1 << ls);
             CU(cudaGetLastError());
             ++b->launches;
         }

@@ -32,7 +32,7 @@ struct __align__(16) DTask {
     uint64_t z_off;              // byte offset of this task's direction scratch
     uint64_t ctmp_end;           // word offset one past this task's CIGAR scratch
     int32_t ctmp_cap;            // words available below ctmp_end
-    int32_t pad;
+    int32_t dir_fmt;             // 0: canonical nibble (dp_fill.cuh), 1: raw predicates (dp_fill16.cuh)
 };
 static_assert(sizeof(DTask) == 80, "DTask layout");
 

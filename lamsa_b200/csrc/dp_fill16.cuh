@@ -1,0 +1,412 @@
+// dp_fill16.cuh -- the packed-int16 fill: same row-parallel scheme as dp_fill.cuh
+// (shared-memory eh[] window, band-following tiles, warp prefix-max for F), but
+// two adjacent query columns share one 32-bit register and every max/add is a
+// Blackwell DPX instruction on s16x2 lanes:
+//     VIMNMX.S16x2 (with the two "which operand won" predicates -> direction
+//     bits for free), VIADDMNMX.S16x2(.RELU), VIADD.16x2, PRMT for half shifts.
+// Lane L of a tile owns G = 2*NP consecutive columns = NP packed registers.
+//
+// Exactness.  The host routes a task here only when every value the reference
+// computes in int32 provably fits the int16 domain used below:
+//   extension: 0 <= H,E,F <= h0 + qlen*max(mat) (<= 16383, because 2H is formed),
+//              max(mat) <= 1, plus the row-relative scan offset (ncol+2G+2)*e_ins;
+//   global:    every finite value >= L (all-mismatch / all-gap bound) > kNeg16+512,
+//              the reference's -2^30 "minus infinity" becomes kNeg16: it only ever
+//              LOSES a max against a finite value and is subtracted from at most
+//              once before being replaced, so no decision changes.
+// Extension detail: M = H ? H+s : 0 (src/ksw.c:737) is evaluated as
+// min(H+s, 2H); for H==0 this yields min(s,0) <= 0 instead of 0, and every use
+// of M (M>e with e>=0, max(M,e), max(M-oe,0)) is identical for all M <= 0.
+//
+// Direction nibble of a cell here holds the four raw predicates
+//   bit0  (E >= M) [extension]  /  (M >= E) [global]
+//   bit1  (F >= h) [extension]  /  (h >= F) [global]
+//   bit2  (M-oe_del clamp >= E-e_del)   -> E' opened   (extension flag = !bit2)
+//   bit3  (M-oe_ins clamp >= F-e_ins)   -> F' opened   (extension flag = !bit3)
+// (DTask::dir_fmt = 1); dp_trace.cuh decodes both formats.
+#pragma once
+#include "dp_device.cuh"
+#include "dp_fill.cuh"
+
+namespace lb2 {
+
+constexpr int kNeg16 = -32000;
+
+__device__ __forceinline__ uint32_t pk2(int lo, int hi) {
+    return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
+}
+__device__ __forceinline__ uint32_t dup2(int v) { return pk2(v, v); }
+__device__ __forceinline__ int lo16(uint32_t x) { return (int)(short)(x & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t x) { return (int)x >> 16; }
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+// (f(a,b,c)) bitwise select: (a & m) | (b & ~m)
+__device__ __forceinline__ uint32_t blend(uint32_t a, uint32_t b, uint32_t m) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(m), "r"(a), "r"(b));   // m ? a : b
+    return r;
+}
+
+// selector pair for two adjacent query codes: {row[c0], sign, row[c1], sign}
+__device__ __forceinline__ uint32_t sel_for_pair(uint32_t c0, uint32_t c1) {
+    c0 &= 7u; c1 &= 7u;
+    return c0 | ((c0 | 8u) << 4) | (c1 << 8) | ((c1 | 8u) << 12);
+}
+
+template <int KIND>
+__device__ __forceinline__ int init_h16(int j, int qlen, int w, int h0, int o_ins, int e_ins) {
+    const int v = init_h<KIND>(j, qlen, w, h0, o_ins, e_ins);
+    return (KIND == kKindGlobal && v == kNegInf) ? kNeg16 : v;
+}
+
+// shared-memory bytes one warp needs for a window of S slots (h16, e16, one selector per pair)
+__host__ __device__ constexpr size_t warp_smem_bytes16(int S) { return (size_t)S * 5; }
+// per-block table of half masks: entry [lo*(G+1)+hi][p] = mask of columns c in [lo,hi) of pair p
+template <int NP> __host__ __device__ constexpr int mask_table_words() { return (2 * NP + 1) * (2 * NP + 1) * NP; }
+
+template <int NP> struct PVec;
+template <> struct PVec<2> {
+    static __device__ __forceinline__ void ld(const int16_t* p, uint32_t (&v)[2]) {
+        uint2 t = *reinterpret_cast<const uint2*>(p); v[0] = t.x; v[1] = t.y; }
+    static __device__ __forceinline__ void st(int16_t* p, const uint32_t (&v)[2]) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]); }
+    static __device__ __forceinline__ void ldq(const uint16_t* p, uint32_t (&v)[2]) {
+        uint32_t t = *reinterpret_cast<const uint32_t*>(p); v[0] = t & 0xffffu; v[1] = t >> 16; }
+    static __device__ __forceinline__ void ldm(const uint32_t* p, uint32_t (&v)[2]) {
+        uint2 t = *reinterpret_cast<const uint2*>(p); v[0] = t.x; v[1] = t.y; }
+};
+template <> struct PVec<4> {
+    static __device__ __forceinline__ void ld(const int16_t* p, uint32_t (&v)[4]) {
+        uint4 t = *reinterpret_cast<const uint4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    static __device__ __forceinline__ void st(int16_t* p, const uint32_t (&v)[4]) {
+        *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]); }
+    static __device__ __forceinline__ void ldq(const uint16_t* p, uint32_t (&v)[4]) {
+        uint2 t = *reinterpret_cast<const uint2*>(p);
+        v[0] = t.x & 0xffffu; v[1] = t.x >> 16; v[2] = t.y & 0xffffu; v[3] = t.y >> 16; }
+    static __device__ __forceinline__ void ldm(const uint32_t* p, uint32_t (&v)[4]) {
+        uint4 t = *reinterpret_cast<const uint4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+};
+
+template <int NP, int KIND>
+__device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
+                            uint8_t* __restrict__ zbase, DResult* __restrict__ res,
+                            const uint2* __restrict__ smat, const uint32_t* __restrict__ mtab,
+                            int16_t* __restrict__ hb, int16_t* __restrict__ eb, uint16_t* __restrict__ qb,
+                            const int S, const int lane)
+{
+    constexpr int G = 2 * NP;
+    constexpr int GS = (NP == 2 ? 2 : 3);
+    constexpr int EINIT = (KIND == kKindGlobal) ? kNeg16 : 0;
+    constexpr int FINIT = (KIND == kKindGlobal) ? kNeg16 : 0;
+    const int SM = S - 1;
+    const int qlen = T.qlen, tlen = T.tlen, w = T.w, h0 = T.h0;
+    const int o_del = T.o_del, e_del = T.e_del, o_ins = T.o_ins, e_ins = T.e_ins;
+    const uint8_t* __restrict__ qseq = pool + (size_t)T.q_off32 * 32;
+    const uint8_t* __restrict__ tseq = pool + (size_t)T.t_off32 * 32;
+    const bool want = T.want_dir != 0;
+    const int RT = T.row_chunks;
+    int2* __restrict__ rowmeta = reinterpret_cast<int2*>(zbase + T.z_off);
+    uint8_t* __restrict__ zdir = zbase + T.z_off + (KIND == kKindExtend ? ext_meta_bytes(tlen) : 0);
+    const size_t zrow_bytes = (size_t)RT * 32 * (G / 2);
+    const uint2* __restrict__ mrows = smat + (int)T.mat_id * 8;
+    const int qpad = (qlen + 1 + 31) & ~31;
+
+    // packed constants
+    const uint32_t NEGP = dup2(kNeg16);
+    const uint32_t N_OE_INS = dup2(-(o_ins + e_ins)), N_OE_DEL = dup2(-(o_del + e_del));
+    const uint32_t N_E_INS = dup2(-e_ins), N_E_DEL = dup2(-e_del);
+    const uint32_t TILE_STEP = dup2(32 * G * e_ins), N_TILE_STEP = dup2(-32 * G * e_ins);
+
+    // ---- window initialisation
+    int slot_hi = (w + 1 < qlen) ? w + 1 : qlen;        // slots [0, slot_hi] are initialised
+    for (int j = lane; j <= slot_hi; j += 32) {
+        hb[j & SM] = (int16_t)init_h16<KIND>(j, qlen, w, h0, o_ins, e_ins);
+        eb[j & SM] = (int16_t)EINIT;
+    }
+    int q_hi = 0;                                       // selectors of columns [.., q_hi) are in qb
+    while (q_hi < slot_hi + 1 && q_hi < qpad) {
+        if (lane < 16) {
+            const uint32_t cc = *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * lane);
+            qb[((q_hi >> 1) + lane) & (SM >> 1)] = (uint16_t)sel_for_pair(cc & 0xffu, cc >> 8);
+        }
+        q_hi += 32;
+    }
+    uint32_t qpre = (q_hi < qpad && lane < 16) ? *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * lane) : 0u;
+
+    int beg = 0, end = qlen;
+    int mx = h0, mx_i = -1, mx_j = -1, mx_ie = -1, gscore = -1, max_off = 0;
+    long long cells = 0;
+    const int tpad = (tlen + 31) & ~31;
+    uint32_t tcur = (lane < tpad) ? tseq[lane] : 0u;
+    uint32_t tnext = (32 + lane < tpad) ? tseq[32 + lane] : 0u;
+    __syncwarp();
+    int i = 0;
+    for (; i < tlen; ++i) {
+        if ((i & 31) == 0 && i) {
+            tcur = tnext;
+            tnext = (i + 32 + lane < tpad) ? tseq[i + 32 + lane] : 0u;
+        }
+        const int tb = __shfl_sync(kFull, (int)tcur, i & 31) & 7;
+        const int sbeg = i > w ? i - w : 0;
+        const int send = i + w + 1 < qlen ? i + w + 1 : qlen;
+        if (KIND == kKindExtend) {
+            if (beg < i - w) beg = i - w;
+            if (end > send) end = send;
+        } else {
+            beg = sbeg;
+            end = send;
+        }
+        bool touched = false;
+        if (send > slot_hi) {
+            slot_hi = send;
+            if (lane == 0) {
+                hb[send & SM] = (int16_t)init_h16<KIND>(send, qlen, w, h0, o_ins, e_ins);
+                eb[send & SM] = (int16_t)EINIT;
+            }
+            touched = true;
+        }
+        if (q_hi < send + 1 && q_hi < qpad) {
+            if (lane < 16) qb[((q_hi >> 1) + lane) & (SM >> 1)] = (uint16_t)sel_for_pair(qpre & 0xffu, qpre >> 8);
+            q_hi += 32;
+            qpre = (q_hi < qpad && lane < 16) ? *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * lane) : 0u;
+            touched = true;
+        }
+        if (touched) __syncwarp();
+
+        const uint2 mrow = mrows[tb];
+        int h1init;
+        if (KIND == kKindExtend) {
+            h1init = 0;
+            if (beg == 0) { h1init = h0 - (o_del + e_del * (i + 1)); if (h1init < 0) h1init = 0; }
+        } else {
+            h1init = beg == 0 ? -(o_del + e_del * (i + 1)) : kNeg16;
+        }
+        const int base = beg & ~(G - 1);
+        const int rb = beg - base, re = end - base;            // live columns, row-relative [rb, re)
+        const int ntile = end >= base ? ((end - base) >> (5 + GS)) + 1 : 0;
+        uint32_t carryF = dup2(FINIT + rb * e_ins);            // seeded with F(i,beg) in the u-domain
+        uint32_t carryH = 0;                                   // left neighbour's last pair, previous tile
+        // row-relative scan offsets of my first pair: RO1 = ((r+1)e,(r+2)e), NRO = (-r e, -(r+1)e)
+        int r0 = lane * G;
+        uint32_t RO1 = pk2((r0 + 1) * e_ins, (r0 + 2) * e_ins);
+        uint32_t NRO = pk2(-r0 * e_ins, -(r0 + 1) * e_ins);
+        uint32_t mrowmax[NP];                                  // extension: running row maxima per pair
+        int mt_lo[NP], mt_hi[NP];                              // tile of the last (tie-)update
+#pragma unroll
+        for (int p = 0; p < NP; ++p) { mrowmax[p] = 0; mt_lo[p] = -1; mt_hi[p] = -1; }
+        uint8_t* zrow = zdir + (size_t)i * zrow_bytes;
+
+        for (int tile = 0; tile < ntile; ++tile, r0 += 32 * G) {
+            const int s0 = (base + r0) & SM;
+            // lane-local live ranges, in columns 0..G
+            const int lo = __viaddmin_s32_relu(rb, -r0, G);          // max(min(rb-r0,G),0)
+            const int hi = __viaddmin_s32_relu(re, -r0, G);
+            const int hc = __viaddmin_s32_relu(re + 1, -r0, G);      // slots [beg,end] -> [lo,hc)
+            uint32_t am[NP], cm[NP];
+            PVec<NP>::ldm(mtab + (lo * (G + 1) + hi) * NP, am);
+            PVec<NP>::ldm(mtab + (lo * (G + 1) + hc) * NP, cm);
+            uint32_t H[NP], E[NP], qs[NP];
+            PVec<NP>::ld(hb + s0, H); PVec<NP>::ld(eb + s0, E); PVec<NP>::ldq(qb + (s0 >> 1), qs);
+
+            uint32_t M[NP], tI[NP], pre[NP];
+            uint32_t run = NEGP;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const uint32_t s = prmt(mrow.x, mrow.y, qs[p]);
+                if (KIND == kKindExtend) M[p] = __viaddmin_s16x2(H[p], s, __vadd2(H[p], H[p]));
+                else M[p] = __vadd2(H[p], s);
+                if (KIND == kKindExtend) tI[p] = __viaddmax_s16x2_relu(M[p], N_OE_INS, 0u);
+                else tI[p] = __vadd2(M[p], N_OE_INS);
+                uint32_t u = __vadd2(tI[p], __vadd2(RO1, dup2(2 * p * e_ins)));
+                u = blend(u, NEGP, am[p]);
+                // exclusive prefix inside the lane: (run, max(run, u.lo))
+                pre[p] = __vmaxs2(run, prmt(u, NEGP, 0x1054));
+                const uint32_t mp = __vmaxs2(u, prmt(u, 0u, 0x1032));
+                run = __vmaxs2(run, mp);
+            }
+            // inclusive prefix maximum of the lane totals (both halves carry the same value)
+            uint32_t incl = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) incl = __vmaxs2(incl, __shfl_up_sync(kFull, incl, d));
+            uint32_t pin = __shfl_up_sync(kFull, incl, 1);
+            if (lane == 0) pin = NEGP;
+            pin = __vmaxs2(pin, carryF);
+            carryF = __vmaxs2(carryF, __shfl_sync(kFull, incl, 31));
+
+            uint32_t dirw = 0;
+            uint32_t Hn[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const uint32_t px = __vmaxs2(pin, pre[p]);
+                const uint32_t nro = __vadd2(NRO, dup2(-2 * p * e_ins));
+                const uint32_t F = __vadd2(px, nro);
+                bool a_hi, a_lo, b_hi, b_lo, c_hi, c_lo, d_hi, d_lo;
+                uint32_t h;
+                if (KIND == kKindExtend) {           // ties: E over M, F over both (src/ksw.c:738-741)
+                    h = __vibmax_s16x2(E[p], M[p], &a_hi, &a_lo);
+                    h = __vibmax_s16x2(F, h, &b_hi, &b_lo);
+                } else {                             // ties: M over E over F (src/ksw.c:598-601)
+                    h = __vibmax_s16x2(M[p], E[p], &a_hi, &a_lo);
+                    h = __vibmax_s16x2(h, F, &b_hi, &b_lo);
+                }
+                Hn[p] = h;
+                uint32_t tD;
+                if (KIND == kKindExtend) tD = __viaddmax_s16x2_relu(M[p], N_OE_DEL, 0u);
+                else tD = __vadd2(M[p], N_OE_DEL);
+                const uint32_t En = __vibmax_s16x2(tD, __vadd2(E[p], N_E_DEL), &c_hi, &c_lo);
+                (void)__vibmax_s16x2(tI[p], __vadd2(F, N_E_INS), &d_hi, &d_lo);
+                E[p] = blend(En, E[p], am[p]);
+                if (a_lo) dirw |= 1u << (8 * p);
+                if (b_lo) dirw |= 2u << (8 * p);
+                if (c_lo) dirw |= 4u << (8 * p);
+                if (d_lo) dirw |= 8u << (8 * p);
+                if (a_hi) dirw |= 16u << (8 * p);
+                if (b_hi) dirw |= 32u << (8 * p);
+                if (c_hi) dirw |= 64u << (8 * p);
+                if (d_hi) dirw |= 128u << (8 * p);
+                if (KIND == kKindExtend) {
+                    bool m_hi, m_lo;
+                    const uint32_t hm = h | ~am[p];              // inactive columns read -1: never >= max
+                    mrowmax[p] = __vibmax_s16x2(hm, mrowmax[p], &m_hi, &m_lo);
+                    if (m_lo) mt_lo[p] = tile;
+                    if (m_hi) mt_hi[p] = tile;
+                }
+            }
+            // shifted H row: slot j <- H(i, j-1); my first slot takes the left neighbour's last column
+            uint32_t left = __shfl_up_sync(kFull, Hn[NP - 1], 1);
+            if (lane == 0) left = carryH;
+            carryH = __shfl_sync(kFull, Hn[NP - 1], 31);
+#pragma unroll
+            for (int p = NP - 1; p >= 0; --p) {
+                const uint32_t prev = p == 0 ? left : Hn[p - 1];
+                const uint32_t sh = prmt(prev, Hn[p], 0x5432);    // (prev.hi, Hn[p].lo)
+                H[p] = blend(sh, H[p], cm[p]);
+            }
+            if (hc > lo) { PVec<NP>::st(hb + s0, H); PVec<NP>::st(eb + s0, E); }
+            if (want && hi > lo) {
+                uint8_t* zp = zrow + (size_t)((tile << 5) + lane) * (G / 2);
+                if (NP == 2) *reinterpret_cast<uint16_t*>(zp) = (uint16_t)dirw;
+                else *reinterpret_cast<uint32_t*>(zp) = dirw;
+            }
+            RO1 = __vadd2(RO1, TILE_STEP);
+            NRO = __vadd2(NRO, N_TILE_STEP);
+        }
+        __syncwarp();
+        // single-slot fix-ups of the row: eh[beg].h = first-column value, eh[end].e = init
+        if (lane == 0 && end >= beg) {
+            hb[beg & SM] = (int16_t)h1init;
+            eb[end & SM] = (int16_t)EINIT;
+        }
+        if (want && KIND == kKindExtend && lane == 0) rowmeta[i] = make_int2(beg, end);
+        __syncwarp();
+        cells += end > beg ? end - beg : 0;
+        if (KIND == kKindExtend) {
+            // row maximum and its LAST column (src/ksw.c:743-744)
+            int m = 0, mj = -1;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const int vlo = lo16(mrowmax[p]), vhi = hi16(mrowmax[p]);
+                const int clo = mt_lo[p] < 0 ? -1 : base + ((mt_lo[p] << 5) + lane) * G + 2 * p;
+                const int chi = mt_hi[p] < 0 ? -1 : base + ((mt_hi[p] << 5) + lane) * G + 2 * p + 1;
+                if (clo >= 0 && (vlo > m || (vlo == m && clo > mj))) { m = vlo; mj = clo; }
+                if (chi >= 0 && (vhi > m || (vhi == m && chi > mj))) { m = vhi; mj = chi; }
+            }
+            const int gm = __reduce_max_sync(kFull, m);
+            const int gmj = __reduce_max_sync(kFull, m == gm ? mj : -1);
+            const int jfin = beg > end ? beg : end;
+            if (jfin == qlen) {                              // src/ksw.c:759-762
+                const int h1 = end > beg ? (int)hb[qlen & SM] : h1init;     // eh[end].h == H(i, qlen-1)
+                mx_ie = gscore > h1 ? mx_ie : i;
+                gscore = gscore > h1 ? gscore : h1;
+            }
+            if (gm == 0) { ++i; break; }                     // :763
+            if (gm > mx) {
+                mx = gm; mx_i = i; mx_j = gmj;
+                int off = gmj - i; off = off < 0 ? -off : off;
+                max_off = max_off > off ? max_off : off;
+            } else if (T.zdrop > 0) {                        // :767-773
+                const int di = i - mx_i, dj = gmj - mx_j;
+                bool drop;
+                if (di > dj) drop = mx - gm - (di - dj) * e_del > T.zdrop;
+                else         drop = mx - gm - (dj - di) * e_ins > T.zdrop;
+                if (drop) { ++i; break; }
+            }
+            // band trim (:775-778): first non-zero slot in [beg,end), last one in [beg',end]
+            int nb = end;
+            for (int st = beg; st < end; st += 32) {
+                const int j = st + lane;
+                const bool nz = j < end && (hb[j & SM] != 0 || eb[j & SM] != 0);
+                const unsigned bal = __ballot_sync(kFull, nz);
+                if (bal) { nb = st + __ffs(bal) - 1; break; }
+            }
+            int nh = nb - 1;
+            for (int st = end; st >= nb; st -= 32) {
+                const int j = st - lane;
+                const bool nz = j >= nb && (hb[j & SM] != 0 || eb[j & SM] != 0);
+                const unsigned bal = __ballot_sync(kFull, nz);
+                if (bal) { nh = st - (__ffs(bal) - 1); break; }
+            }
+            beg = nb;
+            end = nh + 2 < qlen ? nh + 2 : qlen;
+        }
+    }
+
+    // ---- results
+    int score = 0, ti = -1, tk = -1;
+    if (KIND == kKindGlobal) {
+        score = (int)hb[qlen & SM];                          // eh[qlen].h (src/ksw.c:634)
+        ti = tlen - 1;
+        tk = (ti + w + 1 < qlen ? ti + w + 1 : qlen) - 1;     // :638
+    } else {
+        score = mx;
+        if (gscore <= 0 || gscore <= mx - T.end_bonus) { ti = mx_i; tk = mx_j; }   // :785-789
+        else { ti = mx_ie; tk = qlen - 1; }
+    }
+    if (lane == 0) {
+        DResult r;
+        r.score = score; r.max_i = mx_i; r.max_j = mx_j; r.max_ie = mx_ie;
+        r.gscore = gscore; r.max_off = max_off; r.ti = ti; r.tk = tk;
+        r.n_cigar = 0; r.rows = i; r.cigar_off = 0; r.cells = cells;
+        *res = r;
+    }
+    __syncwarp();
+}
+
+template <int NP, int KIND>
+__global__ void __launch_bounds__(256)
+fill16_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order, int n,
+              const uint8_t* __restrict__ pool, uint8_t* __restrict__ zbase,
+              DResult* __restrict__ results, const uint2* __restrict__ gmat,
+              unsigned int* __restrict__ counter, int S)
+{
+    constexpr int G = 2 * NP;
+    __shared__ uint2 smat[kMaxMats * 8];
+    __shared__ __align__(16) uint32_t mtab[mask_table_words<NP>()];
+    extern __shared__ __align__(16) uint8_t dyn[];
+    for (int k = threadIdx.x; k < kMaxMats * 8; k += blockDim.x) smat[k] = gmat[k];
+    for (int k = threadIdx.x; k < mask_table_words<NP>(); k += blockDim.x) {
+        const int p = k % NP, lohi = k / NP, lo = lohi / (G + 1), hi = lohi % (G + 1);
+        const int c0 = 2 * p, c1 = 2 * p + 1;
+        mtab[k] = ((c0 >= lo && c0 < hi) ? 0x0000ffffu : 0u) | ((c1 >= lo && c1 < hi) ? 0xffff0000u : 0u);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint8_t* mine = dyn + (size_t)wid * warp_smem_bytes16(S);
+    int16_t* hb = reinterpret_cast<int16_t*>(mine);
+    int16_t* eb = hb + S;
+    uint16_t* qb = reinterpret_cast<uint16_t*>(eb + S);
+    for (;;) {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(counter, 1u);
+        t = __shfl_sync(kFull, t, 0);
+        if (t >= (unsigned)n) break;
+        const int idx = order[t];
+        fill_task16<NP, KIND>(tasks[idx], pool, zbase, results + idx, smat, mtab, hb, eb, qb, S, lane);
+    }
+}
+
+}  // namespace lb2

@@ -69,8 +69,15 @@ trace_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order,
             const int base = (ext ? rb : sbeg) & ~(G - 1);
             const int rel = k - base;
             const uint8_t* p = zdir + (size_t)i * zrow_bytes + (size_t)(rel >> gs) * lb;
-            uint32_t v = (G == 4) ? *reinterpret_cast<const uint16_t*>(p) : *p;
-            const uint32_t nib = (v >> (4 * (rel & (G - 1)))) & 15u;
+            uint32_t v = (G == 8) ? *reinterpret_cast<const uint32_t*>(p)
+                       : (G == 4) ? *reinterpret_cast<const uint16_t*>(p) : *p;
+            uint32_t nib = (v >> (4 * (rel & (G - 1)))) & 15u;
+            if (T.dir_fmt == 1) {
+                // raw predicates of dp_fill16.cuh -> canonical {source of H, E extended, F extended}
+                const uint32_t b0 = nib & 1u, b1 = (nib >> 1) & 1u;
+                const uint32_t pe = ext ? b0 : b0 ^ 1u, pf = ext ? b1 : b1 ^ 1u;
+                nib = (pf ? 2u : pe) | ((~nib) & 12u);
+            }
             // byte the reference would hold: f<<4 | e<<2 | h  (src/ksw.c:556)
             if (which == 0) which = nib & 3;
             else if (which == 1) which = (nib >> 2) & 1;
