@@ -450,6 +450,7 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
     CU(cudaEventRecord(b->ev[0], s));
     float fill_acc = 0, trace_acc = 0;
     const bool one_wave = b->waves.size() == 1;
+    static const int class_timing = env_int("LB2_CLASS_TIMING", 0);
     for (size_t wi = 0; wi < b->waves.size(); ++wi) {
         const Wave& wv = b->waves[wi];
         if (!one_wave) CU(cudaEventRecord(b->ev[1], s));
@@ -467,9 +468,23 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
             int grid = (cnt + wpb - 1) / wpb;
             const int cap = c->sm_count * c->occ[k];
             if (grid > cap) grid = cap;
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (class_timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, s); }
             fill_table(kind, var)<<<grid, wpb * 32, smem, s>>>(b->d_tasks, b->d_order + wv.first + wv.cls_off[k], cnt,
                                                              b->d_pool, c->d_z, b->d_results, b->d_mats,
                                                              b->d_counters + wi * kNumClass + k, 1 << ls);
+            if (class_timing) {
+                cudaEventRecord(t1, s); cudaEventSynchronize(t1);
+                float ms = 0; cudaEventElapsedTime(&ms, t0, t1);
+                double est = 0;
+                for (int q = 0; q < cnt; ++q) {
+                    const DTask& d = b->h_tasks[b->h_order[wv.first + wv.cls_off[k] + q]];
+                    est += (double)d.tlen * std::min<long>(d.qlen, 2L * d.w + 1);
+                }
+                fprintf(stderr, "[lb2] wave %zu kind %d var %d S %5d: %7d tasks grid %4d x %d warps occ %d  %8.3f ms  static cells %.3e  (%.1f Gcell/s static)\n",
+                        wi, kind, var, 1 << ls, cnt, grid, wpb, c->occ[k], ms, est, est / ms / 1e6);
+                cudaEventDestroy(t0); cudaEventDestroy(t1);
+            }
             CU(cudaGetLastError());
             ++b->launches;
         }
