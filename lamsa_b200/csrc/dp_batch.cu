@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -54,8 +55,35 @@ static inline int class_warps(int var, int logS) {   // warps per block
     return wpb;
 }
 
+// Grow-only staging owned by a batch while it lives and parked in the context
+// in between, so that a producer that submits batch after batch (or the drop-in
+// entry points, one task at a time) never re-allocates pinned or device memory.
+struct Buffers {
+    uint8_t* h_pool = nullptr;  size_t h_pool_cap = 0;
+    DTask* h_tasks = nullptr;   DResult* h_results = nullptr;  int32_t* h_order = nullptr;  size_t h_n_cap = 0;
+    uint2* h_mats = nullptr;
+    uint8_t* d_pool = nullptr;  size_t d_pool_cap = 0;
+    DTask* d_tasks = nullptr;   DResult* d_results = nullptr;  int32_t* d_order = nullptr;  size_t d_n_cap = 0;
+    uint2* d_mats = nullptr;
+    int32_t* d_cdense = nullptr; size_t dense_cap = 0;
+    unsigned long long* d_cursor = nullptr;
+    unsigned int* d_counters = nullptr;  size_t counters_cap = 0;
+    int* d_err = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool valid = false;
+    void release() {
+        cudaFreeHost(h_pool); cudaFreeHost(h_tasks); cudaFreeHost(h_results); cudaFreeHost(h_order); cudaFreeHost(h_mats);
+        cudaFree(d_pool); cudaFree(d_tasks); cudaFree(d_results); cudaFree(d_order); cudaFree(d_mats);
+        cudaFree(d_cdense); cudaFree(d_cursor); cudaFree(d_counters); cudaFree(d_err);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        *this = Buffers();
+    }
+};
+
 struct lb2_ctx {
     int device = 0;
+    std::mutex mu;
+    Buffers parked;                                     // buffers of the last destroyed batch
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     uint64_t scratch_limit = 0;
@@ -112,6 +140,7 @@ extern "C" void lb2_ctx_destroy(lb2_ctx* c) {
     cudaSetDevice(c->device);
     if (c->d_z) cudaFree(c->d_z);
     if (c->d_ctmp) cudaFree(c->d_ctmp);
+    if (c->parked.valid) c->parked.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -132,25 +161,19 @@ struct Wave {
 struct lb2_batch {
     lb2_ctx* ctx = nullptr;
     int64_t n = 0;
-    // pinned host staging
-    uint8_t* h_pool = nullptr;  size_t pool_bytes = 0;
-    DTask* h_tasks = nullptr;
-    int32_t* h_order = nullptr;
-    uint2* h_mats = nullptr;
+    Buffers B;
+    size_t pool_bytes = 0;
+    uint64_t dense_cap = 0;
+    int n_counters = 0;
+    // aliases into B (set by lb2_batch_create)
+    uint8_t* h_pool = nullptr; DTask* h_tasks = nullptr; int32_t* h_order = nullptr; uint2* h_mats = nullptr;
     DResult* h_results = nullptr;
-    // device
-    uint8_t* d_pool = nullptr;
-    DTask* d_tasks = nullptr;
-    int32_t* d_order = nullptr;
-    uint2* d_mats = nullptr;
-    DResult* d_results = nullptr;
-    int32_t* d_cdense = nullptr;  uint64_t dense_cap = 0;
-    unsigned long long* d_cursor = nullptr;
-    unsigned int* d_counters = nullptr;  int n_counters = 0;
-    int* d_err = nullptr;
+    uint8_t* d_pool = nullptr; DTask* d_tasks = nullptr; int32_t* d_order = nullptr; uint2* d_mats = nullptr;
+    DResult* d_results = nullptr; int32_t* d_cdense = nullptr; unsigned long long* d_cursor = nullptr;
+    unsigned int* d_counters = nullptr; int* d_err = nullptr;
     std::vector<Wave> waves;
     std::vector<uint8_t> flags;      // per task: LB2_FLAG_*
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // aliases of B.ev
     int64_t h2d_bytes = 0, d2h_bytes = 0, launches = 0;
     float fill_ms = 0, trace_ms = 0;
     bool uploaded = false, computed = false;
@@ -209,13 +232,12 @@ static int pick_logS(int qlen, int w) {
 
 extern "C" void lb2_batch_destroy(lb2_batch* b) {
     if (!b) return;
-    if (b->ctx) cudaSetDevice(b->ctx->device);
-    cudaFreeHost(b->h_pool); cudaFreeHost(b->h_tasks); cudaFreeHost(b->h_order);
-    cudaFreeHost(b->h_mats); cudaFreeHost(b->h_results);
-    cudaFree(b->d_pool); cudaFree(b->d_tasks); cudaFree(b->d_order); cudaFree(b->d_mats);
-    cudaFree(b->d_results); cudaFree(b->d_cdense); cudaFree(b->d_cursor);
-    cudaFree(b->d_counters); cudaFree(b->d_err);
-    for (auto& e : b->ev) if (e) cudaEventDestroy(e);
+    if (b->ctx) {
+        cudaSetDevice(b->ctx->device);
+        std::lock_guard<std::mutex> lk(b->ctx->mu);
+        if (b->B.valid && !b->ctx->parked.valid) { b->ctx->parked = b->B; b->B = Buffers(); }
+    }
+    if (b->B.valid) b->B.release();
     delete b;
 }
 
@@ -305,11 +327,29 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
 
     // ---- waves: consecutive tasks whose scratch fits the limit, then class/cost order inside a wave
     b->pool_bytes = pool + 64;
-    CU(cudaMallocHost(&b->h_pool, b->pool_bytes));
-    CU(cudaMallocHost(&b->h_tasks, sizeof(DTask) * std::max<int64_t>(n, 1)));
-    CU(cudaMallocHost(&b->h_order, sizeof(int32_t) * std::max<int64_t>(n, 1)));
-    CU(cudaMallocHost(&b->h_mats, sizeof(uint2) * kMaxMats * 8));
-    CU(cudaMallocHost(&b->h_results, sizeof(DResult) * std::max<int64_t>(n, 1)));
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (ctx->parked.valid) { b->B = ctx->parked; ctx->parked = Buffers(); }
+    }
+    Buffers& B = b->B;
+    B.valid = true;
+    const size_t n1c = (size_t)std::max<int64_t>(n, 1);
+    if (B.h_pool_cap < b->pool_bytes) {
+        cudaFreeHost(B.h_pool); B.h_pool = nullptr; B.h_pool_cap = 0;
+        const size_t cap = b->pool_bytes + b->pool_bytes / 8;
+        CU(cudaMallocHost(&B.h_pool, cap)); B.h_pool_cap = cap;
+    }
+    if (B.h_n_cap < n1c) {
+        cudaFreeHost(B.h_tasks); cudaFreeHost(B.h_results); cudaFreeHost(B.h_order);
+        B.h_tasks = nullptr; B.h_results = nullptr; B.h_order = nullptr; B.h_n_cap = 0;
+        const size_t cap = n1c + n1c / 8;
+        CU(cudaMallocHost(&B.h_tasks, sizeof(DTask) * cap));
+        CU(cudaMallocHost(&B.h_results, sizeof(DResult) * cap));
+        CU(cudaMallocHost(&B.h_order, sizeof(int32_t) * cap));
+        B.h_n_cap = cap;
+    }
+    if (!B.h_mats) CU(cudaMallocHost(&B.h_mats, sizeof(uint2) * kMaxMats * 8));
+    b->h_pool = B.h_pool; b->h_tasks = B.h_tasks; b->h_results = B.h_results; b->h_order = B.h_order; b->h_mats = B.h_mats;
     memset(b->h_mats, 0, sizeof(uint2) * kMaxMats * 8);
     for (size_t k = 0; k < mats.size(); ++k)
         for (int r = 0; r < 8; ++r) memcpy(&b->h_mats[k * 8 + r], mats[k].data() + r * 8, 8);
@@ -391,20 +431,39 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
         }
     });
 
-    // ---- device allocations
-    const int64_t n1 = std::max<int64_t>(n, 1);
-    CU(cudaMalloc(&b->d_pool, b->pool_bytes));
-    CU(cudaMalloc(&b->d_tasks, sizeof(DTask) * n1));
-    CU(cudaMalloc(&b->d_order, sizeof(int32_t) * n1));
-    CU(cudaMalloc(&b->d_mats, sizeof(uint2) * kMaxMats * 8));
-    CU(cudaMalloc(&b->d_results, sizeof(DResult) * n1));
+    // ---- device allocations (grow-only, reused across batches)
+    if (B.d_pool_cap < b->pool_bytes) {
+        cudaFree(B.d_pool); B.d_pool = nullptr; B.d_pool_cap = 0;
+        const size_t cap = b->pool_bytes + b->pool_bytes / 8;
+        CU(cudaMalloc(&B.d_pool, cap)); B.d_pool_cap = cap;
+    }
+    if (B.d_n_cap < n1c) {
+        cudaFree(B.d_tasks); cudaFree(B.d_results); cudaFree(B.d_order);
+        B.d_tasks = nullptr; B.d_results = nullptr; B.d_order = nullptr; B.d_n_cap = 0;
+        const size_t cap = n1c + n1c / 8;
+        CU(cudaMalloc(&B.d_tasks, sizeof(DTask) * cap));
+        CU(cudaMalloc(&B.d_results, sizeof(DResult) * cap));
+        CU(cudaMalloc(&B.d_order, sizeof(int32_t) * cap));
+        B.d_n_cap = cap;
+    }
+    if (!B.d_mats) CU(cudaMalloc(&B.d_mats, sizeof(uint2) * kMaxMats * 8));
     b->dense_cap = dense + 16;
-    CU(cudaMalloc(&b->d_cdense, sizeof(int32_t) * b->dense_cap));
-    CU(cudaMalloc(&b->d_cursor, sizeof(unsigned long long)));
+    if (B.dense_cap < b->dense_cap) {
+        cudaFree(B.d_cdense); B.d_cdense = nullptr; B.dense_cap = 0;
+        const size_t cap = b->dense_cap + b->dense_cap / 8;
+        CU(cudaMalloc(&B.d_cdense, sizeof(int32_t) * cap)); B.dense_cap = cap;
+    }
+    if (!B.d_cursor) CU(cudaMalloc(&B.d_cursor, sizeof(unsigned long long)));
     b->n_counters = (int)b->waves.size() * kNumClass + 1;
-    CU(cudaMalloc(&b->d_counters, sizeof(unsigned int) * b->n_counters));
-    CU(cudaMalloc(&b->d_err, sizeof(int)));
-    for (auto& e : b->ev) CU(cudaEventCreate(&e));
+    if (B.counters_cap < (size_t)b->n_counters) {
+        cudaFree(B.d_counters); B.d_counters = nullptr; B.counters_cap = 0;
+        CU(cudaMalloc(&B.d_counters, sizeof(unsigned int) * b->n_counters * 2)); B.counters_cap = (size_t)b->n_counters * 2;
+    }
+    if (!B.d_err) CU(cudaMalloc(&B.d_err, sizeof(int)));
+    for (auto& e : B.ev) if (!e) CU(cudaEventCreate(&e));
+    b->d_pool = B.d_pool; b->d_tasks = B.d_tasks; b->d_results = B.d_results; b->d_order = B.d_order; b->d_mats = B.d_mats;
+    b->d_cdense = B.d_cdense; b->d_cursor = B.d_cursor; b->d_counters = B.d_counters; b->d_err = B.d_err;
+    for (int k = 0; k < 4; ++k) b->ev[k] = B.ev[k];
     // grow the context's scratch
     uint64_t zmax = 16, cmax = 16;
     for (auto& wv : b->waves) { zmax = std::max(zmax, wv.z_bytes); cmax = std::max(cmax, wv.ctmp_words); }

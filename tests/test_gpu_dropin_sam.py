@@ -1,0 +1,57 @@
+"""GPU suite: whole-program drop-in check.  oracle/_ref/lamsa_dropin is the
+reference's own `lamsa` with ONLY ksw.c replaced by liblamsa_b200.so (built by
+`make -C oracle dropin` where the reference tree exists).  It is run with `-N`
+(reuse the recorded GEM seed map) on fixtures produced by the unmodified
+reference (oracle/make_sam_fixtures.py) and its SAM must be identical, record
+for record, to the reference's (only the @PG command line is excluded)."""
+import lzma
+import os
+import shutil
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin")
+FIXTURES = [
+    ("small", os.path.join(ROOT, "tests", "golden", "sam_small")),
+    ("c1", os.path.join(ROOT, "oracle", "_ref", "sam_c1")),
+    ("c3_reduced_pacbio", os.path.join(ROOT, "oracle", "_ref", "sam_c3s")),
+    ("c4_reduced_sv", os.path.join(ROOT, "oracle", "_ref", "sam_c4s")),
+]
+
+
+def stage(src, dst):
+    os.makedirs(dst)
+    for name in os.listdir(src):
+        p = os.path.join(src, name)
+        if name.endswith(".xz"):
+            with lzma.open(p, "rb") as f, open(os.path.join(dst, name[:-3]), "wb") as g:
+                g.write(f.read())
+        else:
+            shutil.copy(p, os.path.join(dst, name))
+
+
+@pytest.mark.parametrize("name,src", FIXTURES, ids=[f[0] for f in FIXTURES])
+@pytest.mark.parametrize("threads", [1, 4])
+def test_dropin_sam_identical_to_reference(tmp_path, name, src, threads):
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/lamsa_dropin not built (needs the reference tree at build time)")
+    if not os.path.isdir(src):
+        pytest.skip(f"fixture {src} not present")
+    if threads != 1 and name not in ("small", "c1"):
+        pytest.skip("multi-thread run only on two fixtures")
+    work = str(tmp_path / name)
+    stage(src, work)
+    opts = open(os.path.join(work, "cmd.txt")).read().split()
+    with open(os.path.join(work, "out.sam"), "w") as f:
+        r = subprocess.run([EXE, "aln", "-t", str(threads), "-N", *opts, "ref.fa", "reads.fa"], cwd=work, stdout=f,
+                           stderr=subprocess.PIPE, timeout=1200)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    got = [l for l in open(os.path.join(work, "out.sam")) if not l.startswith("@PG")]
+    exp = list(open(os.path.join(work, "expected.sam")))
+    assert len(got) == len(exp), (len(got), len(exp))
+    diff = [(i, a, b) for i, (a, b) in enumerate(zip(got, exp)) if a != b]
+    assert not diff, f"{len(diff)} differing SAM lines; first: {diff[0][1][:300]!r} vs {diff[0][2][:300]!r}"
