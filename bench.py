@@ -204,16 +204,10 @@ def main():
     e2e_s = float(np.mean(e2e_secs))
 
     # ---- reduce over ranks: max time, summed cells
-    tmax, cells_all, ops_all, e2e_max = dev_ms, cells, ops_per_step, e2e_s
-    if dist is not None:
-        t = torch.tensor([dev_ms, e2e_s, fill_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tmax, e2e_max, fill_max = t.tolist()
-        c = torch.tensor([cells, ops_per_step], device="cuda", dtype=torch.float64)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        cells_all, ops_all = int(c[0].item()), int(c[1].item())
-    else:
-        fill_max = fill_ms
+    from lamsa_b200 import sharding
+    (tmax, e2e_max, fill_max), (cells_all, ops_all) = sharding.reduce_metrics(
+        dist, "cuda", [dev_ms, e2e_s, fill_ms], [cells, ops_per_step])
+    cells_all, ops_all = int(cells_all), int(ops_all)
     ms_step = tmax / a.steps
     value = cells_all / (ms_step * 1e-3) / 1e9
 
