@@ -194,7 +194,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         b = lamsa_b200.Batch(ctx, tasks, keep)       # == lb2_dp_run, staged so the byte counters can be read
-        b.upload(); b.compute(); r2, c2 = b.download()
+        b.upload(); b.compute(); r2, c2 = b.download(copy=False)   # results + CIGARs land in host memory
         st2 = b.stats()
         b.close()
         barrier()

@@ -178,6 +178,10 @@ int  lb2_batch_upload(lb2_batch *b);                       /* H2D, async on the 
 int  lb2_batch_compute(lb2_batch *b, float *kernel_ms);    /* fill + traceback kernels; CUDA-event ms or NULL */
 int  lb2_batch_download(lb2_batch *b, lb2_result *results,
                         cigar32_t **cigar_pool, int64_t *cigar_pool_n);
+/* as lb2_batch_download, but the CIGAR pool is a view into pinned staging owned by
+ * the batch (valid until lb2_batch_destroy or the next download; do not free) */
+int  lb2_batch_download_view(lb2_batch *b, lb2_result *results,
+                             const cigar32_t **cigar_pool, int64_t *cigar_pool_n);
 int  lb2_batch_stats(const lb2_batch *b, int64_t *h2d_bytes, int64_t *d2h_bytes,
                      int64_t *launches, float *fill_ms, float *trace_ms);
 void lb2_batch_destroy(lb2_batch *b);

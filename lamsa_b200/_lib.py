@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblamsa_b200.so")
+LIB_PATH = os.environ.get("LB2_LIB_PATH") or os.path.join(HERE, "liblamsa_b200.so")   # env override: kernel experiments
 
 KIND_GLOBAL, KIND_EXTEND = 0, 1
 FLAG_CIGAR = 1
@@ -72,7 +72,7 @@ EXPORTS = [
     "ksw_global2", "ksw_global", "ksw_extend2", "ksw_extend", "ksw_extend_core", "ksw_extend_c",
     "ksw_extend_r", "ksw_bi_extend", "sw_mid_fix",
     "lb2_ctx_create", "lb2_ctx_destroy", "lb2_last_error", "lb2_ctx_set_scratch_limit", "lb2_dp_run",
-    "lb2_batch_create", "lb2_batch_upload", "lb2_batch_compute", "lb2_batch_download", "lb2_batch_stats",
+    "lb2_batch_create", "lb2_batch_upload", "lb2_batch_compute", "lb2_batch_download", "lb2_batch_download_view", "lb2_batch_stats",
     "lb2_batch_destroy", "lb2_free", "lb2_int_peak",
 ]
 
@@ -100,6 +100,7 @@ def load_library():
     lib.lb2_batch_upload.argtypes = [P]
     lib.lb2_batch_compute.argtypes = [P, C.POINTER(C.c_float)]
     lib.lb2_batch_download.argtypes = [P, P, C.POINTER(P), C.POINTER(I64)]
+    lib.lb2_batch_download_view.argtypes = [P, P, C.POINTER(P), C.POINTER(I64)]
     lib.lb2_batch_stats.argtypes = [P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64),
                                     C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.lb2_batch_destroy.argtypes = [P]

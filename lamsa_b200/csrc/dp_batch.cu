@@ -62,6 +62,7 @@ struct Buffers {
     uint8_t* h_pool = nullptr;  size_t h_pool_cap = 0;
     DTask* h_tasks = nullptr;   DResult* h_results = nullptr;  int32_t* h_order = nullptr;  size_t h_n_cap = 0;
     uint2* h_mats = nullptr;
+    cigar32_t* h_cigar = nullptr; size_t h_cigar_cap = 0;      // pinned landing zone of the dense CIGAR pool
     uint8_t* d_pool = nullptr;  size_t d_pool_cap = 0;
     DTask* d_tasks = nullptr;   DResult* d_results = nullptr;  int32_t* d_order = nullptr;  size_t d_n_cap = 0;
     uint2* d_mats = nullptr;
@@ -73,6 +74,7 @@ struct Buffers {
     bool valid = false;
     void release() {
         cudaFreeHost(h_pool); cudaFreeHost(h_tasks); cudaFreeHost(h_results); cudaFreeHost(h_order); cudaFreeHost(h_mats);
+        cudaFreeHost(h_cigar);
         cudaFree(d_pool); cudaFree(d_tasks); cudaFree(d_results); cudaFree(d_order); cudaFree(d_mats);
         cudaFree(d_cdense); cudaFree(d_cursor); cudaFree(d_counters); cudaFree(d_err);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -90,6 +92,11 @@ struct lb2_ctx {
     uint8_t* d_z = nullptr;    size_t z_cap = 0;        // direction nibbles (+ row bands)
     int32_t* d_ctmp = nullptr; size_t ctmp_cap = 0;     // per-task reversed CIGAR scratch (words)
     int occ[kNumClass] = {0};                           // resident blocks per SM, filled lazily
+    // side streams: the launch classes of a wave run concurrently, so the drain of one
+    // class (few long tasks left) is filled by the blocks of the next
+    static constexpr int kAux = 4;
+    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[kAux] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 typedef void (*fill_fn)(const DTask*, const int32_t*, int, const uint8_t*, uint8_t*, DResult*,
@@ -125,6 +132,11 @@ extern "C" int lb2_ctx_create(int device, lb2_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int k = 0; k < lb2_ctx::kAux; ++k) {
+        CU(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->join_ev[k], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
     size_t fr = 0, tot = 0;
     CU(cudaMemGetInfo(&fr, &tot));
     c->scratch_limit = (uint64_t)(fr * 0.40);
@@ -142,6 +154,11 @@ extern "C" void lb2_ctx_destroy(lb2_ctx* c) {
     if (c->d_ctmp) cudaFree(c->d_ctmp);
     if (c->parked.valid) c->parked.release();
     if (c->stream) cudaStreamDestroy(c->stream);
+    for (int k = 0; k < lb2_ctx::kAux; ++k) {
+        if (c->aux[k]) cudaStreamDestroy(c->aux[k]);
+        if (c->join_ev[k]) cudaEventDestroy(c->join_ev[k]);
+    }
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     delete c;
 }
 
@@ -217,14 +234,16 @@ static bool fits_int16(const lb2_task& t, int w) {
 
 // kernel variant from the widest band a row can have
 static int pick_variant(const lb2_task& t, int w, long ncol) {
-    static const int use16 = env_int("LB2_P16", 1), p16_min = env_int("LB2_P16_MIN", 37), np4_min = env_int("LB2_NP4_MIN", 200);
-    if (use16 && ncol >= p16_min && fits_int16(t, w)) return ncol >= np4_min ? 4 : 3;
+    static const int use16 = env_int("LB2_P16", 1), p16_min = env_int("LB2_P16_MIN", 37),
+                     np4_min = env_int("LB2_NP4_MIN", 200), np4_min_ext = env_int("LB2_NP4_MIN_EXT", 1000000);
+    if (use16 && ncol >= p16_min && fits_int16(t, w))
+        return ncol >= (t.kind == LB2_KIND_EXTEND ? np4_min_ext : np4_min) ? 4 : 3;
     return ncol <= 36 ? 0 : ncol <= 72 ? 1 : 2;
 }
 // window slots: the whole eh[] array when it is small, else band window + look-ahead
 static int pick_logS(int qlen, int w) {
     const long qpad = ((long)qlen + 1 + 31) & ~31L;
-    const long need = std::min<long>(qpad, 2L * w + 76);
+    const long need = std::min<long>(qpad, 2L * w + 140);
     int l = kMinLogS;
     while ((1L << l) < need && l <= kMaxLogS) ++l;
     return l <= kMaxLogS ? l : -1;
@@ -271,57 +290,74 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     b->ctx = ctx; b->n = n;
     struct Guard { lb2_batch* b; bool ok = false; ~Guard() { if (!ok) lb2_batch_destroy(b); } } guard{b};
 
-    // ---- pass 1: validate, classify, lay out pool / scratch
+    // ---- pass 1 (parallel): validate, final band, kernel variant, sizes
     std::vector<uint64_t> qoff(n), toff(n), zsz(n);
     std::vector<int32_t> wfin(n), ctmpw(n);
     std::vector<int8_t> cshift(n), matid(n), logS(n), variant(n);
     std::vector<std::vector<int8_t>> mats;           // distinct matrices, each 64 entries (8x8, zero padded)
+    std::mutex mats_mu;
+    std::mutex err_mu; int64_t err_i = -1; std::string err_msg;
     b->flags.resize(n);
-    uint64_t pool = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        const lb2_task& t = tasks[i];
-        if (t.qlen < 0 || t.tlen < 0) return fail("task %lld: qlen %d tlen %d", (long long)i, t.qlen, t.tlen);
-        if (t.kind != LB2_KIND_GLOBAL && t.kind != LB2_KIND_EXTEND) return fail("task %lld: kind %d", (long long)i, t.kind);
-        if (t.m < 1 || t.m > 8 || !t.mat) return fail("task %lld: alphabet size %d unsupported (1..8)", (long long)i, t.m);
-        if ((t.qlen && !t.query) || (t.tlen && !t.target)) return fail("task %lld: NULL sequence", (long long)i);
-        if (t.e_del <= 0 || t.e_ins <= 0) return fail("task %lld: gap extension penalties must be > 0", (long long)i);
-        int w = t.w;
-        if (t.kind == LB2_KIND_GLOBAL) {
-            const int dl = std::abs(t.qlen - t.tlen);
-            w = dl + 3 < w ? w : dl + 3;                                  // src/ksw.c:549
-        } else {
-            if (t.h0 <= 0) return fail("task %lld: h0 must be > 0 (src/ksw.c:682)", (long long)i);
-            w = extend_band(w, t.qlen, t.m, t.mat, t.end_bonus, t.o_del, t.e_del, t.o_ins, t.e_ins);
-        }
-        if (w < 0) return fail("task %lld: negative band", (long long)i);
-        wfin[i] = w;
-        const long ncol_i = std::min<long>(t.qlen, 2L * w + 1);
-        const int var = pick_variant(t, w, ncol_i);
-        const int cs = var_gshift(var);
-        const int ls = pick_logS(t.qlen, w);
-        if (ls < 0) return fail("task %lld: qlen %d with band %d needs a window beyond %d slots (not supported yet)", (long long)i, t.qlen, w, 1 << kMaxLogS);
-        cshift[i] = (int8_t)cs; logS[i] = (int8_t)ls; variant[i] = (int8_t)var;
-        // matrix table
+    auto set_err = [&](int64_t i, const char* fmt, ...) {
+        char buf[256]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        std::lock_guard<std::mutex> lk(err_mu);
+        if (err_i < 0 || i < err_i) { err_i = i; err_msg = buf; }
+    };
+    auto matrix_id = [&](const lb2_task& t) -> int {
         int8_t m8[64]; memset(m8, 0, sizeof m8);
         for (int a = 0; a < t.m; ++a) for (int c = 0; c < t.m; ++c) m8[a * 8 + c] = t.mat[a * t.m + c];
-        int id = -1;
-        for (size_t k = 0; k < mats.size(); ++k) if (!memcmp(mats[k].data(), m8, 64)) { id = (int)k; break; }
-        if (id < 0) {
-            if ((int)mats.size() == kMaxMats) return fail("more than %d distinct scoring matrices in one batch", kMaxMats);
-            mats.emplace_back(m8, m8 + 64); id = (int)mats.size() - 1;
+        std::lock_guard<std::mutex> lk(mats_mu);
+        for (size_t k = 0; k < mats.size(); ++k) if (!memcmp(mats[k].data(), m8, 64)) return (int)k;
+        if ((int)mats.size() == kMaxMats) return -1;
+        mats.emplace_back(m8, m8 + 64);
+        return (int)mats.size() - 1;
+    };
+    parallel_for(n, [&](int64_t lo_i, int64_t hi_i) {
+        const int8_t* last_mat = nullptr; int last_m = 0, last_id = -1;     // per-thread cache: tasks share matrices
+        for (int64_t i = lo_i; i < hi_i; ++i) {
+            const lb2_task& t = tasks[i];
+            if (t.qlen < 0 || t.tlen < 0) { set_err(i, "task %lld: qlen %d tlen %d", (long long)i, t.qlen, t.tlen); return; }
+            if (t.kind != LB2_KIND_GLOBAL && t.kind != LB2_KIND_EXTEND) { set_err(i, "task %lld: kind %d", (long long)i, t.kind); return; }
+            if (t.m < 1 || t.m > 8 || !t.mat) { set_err(i, "task %lld: alphabet size %d unsupported (1..8)", (long long)i, t.m); return; }
+            if ((t.qlen && !t.query) || (t.tlen && !t.target)) { set_err(i, "task %lld: NULL sequence", (long long)i); return; }
+            if (t.e_del <= 0 || t.e_ins <= 0) { set_err(i, "task %lld: gap extension penalties must be > 0", (long long)i); return; }
+            int w = t.w;
+            if (t.kind == LB2_KIND_GLOBAL) {
+                const int dl = std::abs(t.qlen - t.tlen);
+                w = dl + 3 < w ? w : dl + 3;                                  // src/ksw.c:549
+            } else {
+                if (t.h0 <= 0) { set_err(i, "task %lld: h0 must be > 0 (src/ksw.c:682)", (long long)i); return; }
+                w = extend_band(w, t.qlen, t.m, t.mat, t.end_bonus, t.o_del, t.e_del, t.o_ins, t.e_ins);
+            }
+            if (w < 0) { set_err(i, "task %lld: negative band", (long long)i); return; }
+            wfin[i] = w;
+            const long ncol_i = std::min<long>(t.qlen, 2L * w + 1);
+            const int var = pick_variant(t, w, ncol_i);
+            const int cs = var_gshift(var);
+            const int ls = pick_logS(t.qlen, w);
+            if (ls < 0) { set_err(i, "task %lld: qlen %d with band %d needs a window beyond %d slots (not supported yet)", (long long)i, t.qlen, w, 1 << kMaxLogS); return; }
+            cshift[i] = (int8_t)cs; logS[i] = (int8_t)ls; variant[i] = (int8_t)var;
+            if (t.mat != last_mat || t.m != last_m) {
+                last_id = matrix_id(t); last_mat = t.mat; last_m = t.m;
+                if (last_id < 0) { set_err(i, "more than %d distinct scoring matrices in one batch", kMaxMats); return; }
+            }
+            matid[i] = (int8_t)last_id;
+            b->flags[i] = (uint8_t)t.flags;
+            if (t.flags & LB2_FLAG_CIGAR) {
+                const int G = 1 << cs;
+                const int rt = row_tiles_for(ncol_i, G);
+                uint64_t z = (uint64_t)t.tlen * rt * 32 * dir_lane_bytes(G);
+                if (t.kind == LB2_KIND_EXTEND) z += ext_meta_bytes(t.tlen);
+                zsz[i] = (z + 15) & ~uint64_t(15);
+                ctmpw[i] = t.qlen + t.tlen + 2;
+            } else { zsz[i] = 0; ctmpw[i] = 0; }
         }
-        matid[i] = (int8_t)id;
-        b->flags[i] = (uint8_t)t.flags;
-        qoff[i] = pool; pool += ((uint64_t)t.qlen + 1 + 31) & ~uint64_t(31);
-        toff[i] = pool; pool += ((uint64_t)t.tlen + 31) & ~uint64_t(31);
-        if (t.flags & LB2_FLAG_CIGAR) {
-            const int G = 1 << cs;
-            const int rt = row_tiles_for(ncol_i, G);
-            uint64_t z = (uint64_t)t.tlen * rt * 32 * dir_lane_bytes(G);
-            if (t.kind == LB2_KIND_EXTEND) z += ext_meta_bytes(t.tlen);
-            zsz[i] = (z + 15) & ~uint64_t(15);
-            ctmpw[i] = t.qlen + t.tlen + 2;
-        } else { zsz[i] = 0; ctmpw[i] = 0; }
+    });
+    if (err_i >= 0) return fail("%s", err_msg.c_str());
+    uint64_t pool = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        qoff[i] = pool; pool += ((uint64_t)tasks[i].qlen + 1 + 31) & ~uint64_t(31);
+        toff[i] = pool; pool += ((uint64_t)tasks[i].tlen + 31) & ~uint64_t(31);
     }
     if (pool >> 37) return fail("sequence pool of %llu bytes is too large for one batch", (unsigned long long)pool);
 
@@ -374,28 +410,28 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
             i = j;
         }
     }
-    // order + per-wave offsets
+    // order + per-wave offsets: counting sort by (class, descending log-spaced cost bin) -- the
+    // persistent warps only need an approximately longest-first order
     for (auto& wv : b->waves) {
-        std::vector<int32_t> idx(wv.count);
-        for (int k = 0; k < wv.count; ++k) idx[k] = wv.first + k;
-        auto cls = [&](int32_t a) { return class_id((int)tasks[a].kind, variant[a], logS[a]); };
-        auto cost = [&](int32_t a) {
-            return (int64_t)tasks[a].tlen * std::min<int64_t>(tasks[a].qlen, 2L * wfin[a] + 1);
+        constexpr int kBins = 48;
+        auto key = [&](int64_t a) {
+            const int64_t cost = (int64_t)tasks[a].tlen * std::min<int64_t>(tasks[a].qlen, 2L * wfin[a] + 1) + 1;
+            int bin = 0;                                      // ~3 bins per octave
+            { int64_t c = cost; int l2 = 63 - __builtin_clzll((unsigned long long)c);
+              const int frac = l2 >= 2 ? (int)((c >> (l2 - 2)) & 3) : 0;
+              bin = std::min(kBins - 1, std::max(0, (l2 * 4 + frac) / 3 - 4)); }
+            return class_id((int)tasks[a].kind, variant[a], logS[a]) * kBins + (kBins - 1 - bin);
         };
-        std::sort(idx.begin(), idx.end(), [&](int32_t a, int32_t c) {
-            const int ca = cls(a), cc = cls(c);
-            if (ca != cc) return ca < cc;
-            const int64_t xa = cost(a), xc = cost(c);
-            if (xa != xc) return xa > xc;
-            return a < c;
+        std::vector<int32_t> keys(wv.count);
+        std::vector<int32_t> hist((size_t)kNumClass * kBins + 1, 0);
+        parallel_for(wv.count, [&](int64_t lo_i, int64_t hi_i) {
+            for (int64_t k = lo_i; k < hi_i; ++k) keys[k] = key(wv.first + k);
         });
-        int pos = 0;
-        for (int c = 0; c < kNumClass; ++c) {
-            wv.cls_off[c] = pos;
-            while (pos < wv.count && cls(idx[pos]) == c) ++pos;
-        }
-        wv.cls_off[kNumClass] = pos;
-        memcpy(b->h_order + wv.first, idx.data(), sizeof(int32_t) * wv.count);
+        for (int k = 0; k < wv.count; ++k) ++hist[keys[k] + 1];
+        for (size_t k = 1; k < hist.size(); ++k) hist[k] += hist[k - 1];
+        for (int c = 0; c <= kNumClass; ++c) wv.cls_off[c] = hist[(size_t)c * kBins];
+        int32_t* ord = b->h_order + wv.first;
+        for (int k = 0; k < wv.count; ++k) ord[hist[keys[k]]++] = wv.first + k;
         uint64_t z = 0, cw = 0;
         for (int k = 0; k < wv.count; ++k) {          // scratch offsets follow the original order
             const int64_t a = wv.first + k;
@@ -513,7 +549,15 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
     for (size_t wi = 0; wi < b->waves.size(); ++wi) {
         const Wave& wv = b->waves[wi];
         if (!one_wave) CU(cudaEventRecord(b->ev[1], s));
-        for (int k = 0; k < kNumClass; ++k) {
+        static const int multi = env_int("LB2_MULTI_STREAM", 1);
+        const bool fan = multi && !class_timing;
+        if (fan) {
+            CU(cudaEventRecord(c->fork_ev, s));
+            for (int k = 0; k < lb2_ctx::kAux; ++k) CU(cudaStreamWaitEvent(c->aux[k], c->fork_ev, 0));
+        }
+        int nlaunch = 0;
+        // heaviest classes first (class ids grow with window size / lanes per tile)
+        for (int k = kNumClass - 1; k >= 0; --k) {
             const int cnt = wv.cls_off[k + 1] - wv.cls_off[k];
             if (!cnt) continue;
             const int kind = class_kind(k), var = class_var(k), ls = class_logS(k);
@@ -529,7 +573,8 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
             if (grid > cap) grid = cap;
             cudaEvent_t t0 = nullptr, t1 = nullptr;
             if (class_timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, s); }
-            fill_table(kind, var)<<<grid, wpb * 32, smem, s>>>(b->d_tasks, b->d_order + wv.first + wv.cls_off[k], cnt,
+            cudaStream_t ls_ = fan ? c->aux[nlaunch++ % lb2_ctx::kAux] : s;
+            fill_table(kind, var)<<<grid, wpb * 32, smem, ls_>>>(b->d_tasks, b->d_order + wv.first + wv.cls_off[k], cnt,
                                                              b->d_pool, c->d_z, b->d_results, b->d_mats,
                                                              b->d_counters + wi * kNumClass + k, 1 << ls);
             if (class_timing) {
@@ -546,6 +591,12 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
             }
             CU(cudaGetLastError());
             ++b->launches;
+        }
+        if (fan) {
+            for (int k = 0; k < lb2_ctx::kAux; ++k) {
+                CU(cudaEventRecord(c->join_ev[k], c->aux[k]));
+                CU(cudaStreamWaitEvent(s, c->join_ev[k], 0));
+            }
         }
         CU(cudaEventRecord(b->ev[2], s));
         if (wv.ctmp_words) {
@@ -586,7 +637,7 @@ static int cigar_capacity(int n) {      // capacity after the doubling pushes of
     int m = 4; while (m < n) m <<= 1; return m;
 }
 
-extern "C" int lb2_batch_download(lb2_batch* b, lb2_result* results, cigar32_t** cigar_pool, int64_t* cigar_pool_n) {
+static int download_impl(lb2_batch* b, lb2_result* results, bool want_cigar, unsigned long long* used_out) {
     if (!b || (b->n && !results)) return fail("lb2_batch_download: NULL argument");
     if (!b->computed) return fail("lb2_batch_download before lb2_batch_compute");
     lb2_ctx* c = b->ctx;
@@ -596,22 +647,20 @@ extern "C" int lb2_batch_download(lb2_batch* b, lb2_result* results, cigar32_t**
     CU(cudaMemcpyAsync(&used, b->d_cursor, sizeof used, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(b->h_results, b->d_results, sizeof(DResult) * std::max<int64_t>(b->n, 1), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    cigar32_t* pool = nullptr;
-    if (cigar_pool) {
-        pool = (cigar32_t*)malloc(sizeof(cigar32_t) * (used ? used : 1));
-        if (!pool) return fail("out of host memory for %llu CIGAR words", used);
-        if (used) {
-            CU(cudaMemcpyAsync(pool, b->d_cdense, sizeof(cigar32_t) * used, cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
+    if (want_cigar && used) {
+        Buffers& B = b->B;
+        if (B.h_cigar_cap < used) {
+            cudaFreeHost(B.h_cigar); B.h_cigar = nullptr; B.h_cigar_cap = 0;
+            const size_t cap = used + used / 8 + 1024;
+            CU(cudaMallocHost(&B.h_cigar, cap * sizeof(cigar32_t))); B.h_cigar_cap = cap;
         }
-        *cigar_pool = pool;
+        CU(cudaMemcpyAsync(B.h_cigar, b->d_cdense, sizeof(cigar32_t) * used, cudaMemcpyDeviceToHost, s));
     }
-    if (cigar_pool_n) *cigar_pool_n = (int64_t)used;
-    b->d2h_bytes = (int64_t)sizeof(DResult) * b->n + (cigar_pool ? (int64_t)used * 4 : 0) + 8;
+    b->d2h_bytes = (int64_t)sizeof(DResult) * b->n + (want_cigar ? (int64_t)used * 4 : 0) + 8;
     const DResult* hr = b->h_results;
     const DTask* ht = b->h_tasks;
     const uint8_t* fl = b->flags.data();
-    parallel_for(b->n, [=](int64_t a, int64_t e) {
+    parallel_for(b->n, [=](int64_t a, int64_t e) {          // overlaps the CIGAR copy
         for (int64_t i = a; i < e; ++i) {
             const DResult& r = hr[i];
             lb2_result& o = results[i];
@@ -627,6 +676,32 @@ extern "C" int lb2_batch_download(lb2_batch* b, lb2_result* results, cigar32_t**
             o.cigar_off = r.cigar_off; o.cells = r.cells;
         }
     });
+    CU(cudaStreamSynchronize(s));
+    *used_out = used;
+    return 0;
+}
+
+extern "C" int lb2_batch_download(lb2_batch* b, lb2_result* results, cigar32_t** cigar_pool, int64_t* cigar_pool_n) {
+    unsigned long long used = 0;
+    if (download_impl(b, results, cigar_pool != nullptr, &used)) return 1;
+    if (cigar_pool) {
+        cigar32_t* pool = (cigar32_t*)malloc(sizeof(cigar32_t) * (used ? used : 1));
+        if (!pool) return fail("out of host memory for %llu CIGAR words", used);
+        const cigar32_t* src = b->B.h_cigar;
+        parallel_for((int64_t)used, [=](int64_t a, int64_t e) { memcpy(pool + a, src + a, sizeof(cigar32_t) * (size_t)(e - a)); });
+        *cigar_pool = pool;
+    }
+    if (cigar_pool_n) *cigar_pool_n = (int64_t)used;
+    return 0;
+}
+
+// Same as lb2_batch_download, but the CIGAR pool is handed out in place (pinned
+// staging owned by the batch; valid until the batch is destroyed or downloaded again).
+extern "C" int lb2_batch_download_view(lb2_batch* b, lb2_result* results, const cigar32_t** cigar_pool, int64_t* cigar_pool_n) {
+    unsigned long long used = 0;
+    if (download_impl(b, results, cigar_pool != nullptr, &used)) return 1;
+    if (cigar_pool) *cigar_pool = b->B.h_cigar;
+    if (cigar_pool_n) *cigar_pool_n = (int64_t)used;
     return 0;
 }
 

@@ -28,6 +28,10 @@
 #include "dp_device.cuh"
 #include "dp_fill.cuh"
 
+#ifndef LB2_FILL16_MIN_BLOCKS
+#define LB2_FILL16_MIN_BLOCKS 1
+#endif
+
 namespace lb2 {
 
 constexpr int kNeg16 = -32000;
@@ -100,133 +104,144 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
 {
     constexpr int G = 2 * NP;
     constexpr int GS = (NP == 2 ? 2 : 3);
-    constexpr int EINIT = (KIND == kKindGlobal) ? kNeg16 : 0;
-    constexpr int FINIT = (KIND == kKindGlobal) ? kNeg16 : 0;
-    const int SM = S - 1;
+    constexpr bool EXT = (KIND == kKindExtend);
+    constexpr int EINIT = EXT ? 0 : kNeg16;
+    constexpr int FINIT = EXT ? 0 : kNeg16;
+    constexpr int POISON = EXT ? 0 : kNeg16;           // H of dead slots left of the band (see below)
+    const int SM = S - 1, SMQ = SM >> 1;
     const int qlen = T.qlen, tlen = T.tlen, w = T.w, h0 = T.h0;
     const int o_del = T.o_del, e_del = T.e_del, o_ins = T.o_ins, e_ins = T.e_ins;
     const uint8_t* __restrict__ qseq = pool + (size_t)T.q_off32 * 32;
     const uint8_t* __restrict__ tseq = pool + (size_t)T.t_off32 * 32;
     const bool want = T.want_dir != 0;
-    const int RT = T.row_chunks;
     int2* __restrict__ rowmeta = reinterpret_cast<int2*>(zbase + T.z_off);
-    uint8_t* __restrict__ zdir = zbase + T.z_off + (KIND == kKindExtend ? ext_meta_bytes(tlen) : 0);
-    const size_t zrow_bytes = (size_t)RT * 32 * (G / 2);
+    uint8_t* __restrict__ zdir = zbase + T.z_off + (EXT ? ext_meta_bytes(tlen) : 0) + (size_t)lane * (G / 2);
+    const size_t zrow_bytes = (size_t)T.row_chunks * 32 * (G / 2);
     const uint2* __restrict__ mrows = smat + (int)T.mat_id * 8;
     const int qpad = (qlen + 1 + 31) & ~31;
+    const int tpad = (tlen + 31) & ~31;
 
     // packed constants
     const uint32_t NEGP = dup2(kNeg16);
     const uint32_t N_OE_INS = dup2(-(o_ins + e_ins)), N_OE_DEL = dup2(-(o_del + e_del));
     const uint32_t N_E_INS = dup2(-e_ins), N_E_DEL = dup2(-e_del);
     const uint32_t TILE_STEP = dup2(32 * G * e_ins), N_TILE_STEP = dup2(-32 * G * e_ins);
+    // row-relative scan offsets of my pairs in tile 0: RO1 = ((r+1)e,(r+2)e), NRO = (-r e, -(r+1)e)
+    uint32_t RO1_0[NP], NRO_0[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const int r = lane * G + 2 * p;
+        RO1_0[p] = pk2((r + 1) * e_ins, (r + 2) * e_ins);
+        NRO_0[p] = pk2(-r * e_ins, -(r + 1) * e_ins);
+    }
 
-    // ---- window initialisation
+    // ---- window initialisation: slots [0, send_0]; selectors for columns [0, w+66)
     int slot_hi = (w + 1 < qlen) ? w + 1 : qlen;        // slots [0, slot_hi] are initialised
     for (int j = lane; j <= slot_hi; j += 32) {
         hb[j & SM] = (int16_t)init_h16<KIND>(j, qlen, w, h0, o_ins, e_ins);
         eb[j & SM] = (int16_t)EINIT;
     }
     int q_hi = 0;                                       // selectors of columns [.., q_hi) are in qb
-    while (q_hi < slot_hi + 1 && q_hi < qpad) {
-        if (lane < 16) {
-            const uint32_t cc = *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * lane);
-            qb[((q_hi >> 1) + lane) & (SM >> 1)] = (uint16_t)sel_for_pair(cc & 0xffu, cc >> 8);
+    {
+        const int want_q = w + 66 < qpad ? w + 66 : qpad;
+        while (q_hi < want_q) {
+            if (lane < 16) {
+                const uint32_t cc = *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * lane);
+                qb[((q_hi >> 1) + lane) & SMQ] = (uint16_t)sel_for_pair(cc & 0xffu, cc >> 8);
+            }
+            q_hi += 32;
         }
-        q_hi += 32;
     }
     uint32_t qpre = (q_hi < qpad && lane < 16) ? *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * lane) : 0u;
+    uint32_t tcur = 0u;
+    uint32_t tnext = (lane < tpad) ? tseq[lane] : 0u;
 
     int beg = 0, end = qlen;
     int mx = h0, mx_i = -1, mx_j = -1, mx_ie = -1, gscore = -1, max_off = 0;
     long long cells = 0;
-    const int tpad = (tlen + 31) & ~31;
-    uint32_t tcur = (lane < tpad) ? tseq[lane] : 0u;
-    uint32_t tnext = (32 + lane < tpad) ? tseq[32 + lane] : 0u;
-    __syncwarp();
     int i = 0;
     for (; i < tlen; ++i) {
-        if ((i & 31) == 0 && i) {
+        if ((i & 31) == 0) {                            // every 32 rows: next target codes, next 32 selectors
             tcur = tnext;
             tnext = (i + 32 + lane < tpad) ? tseq[i + 32 + lane] : 0u;
+            if (i && q_hi < qpad) {
+                if (lane < 16) qb[((q_hi >> 1) + lane) & SMQ] = (uint16_t)sel_for_pair(qpre & 0xffu, qpre >> 8);
+                q_hi += 32;
+                qpre = (q_hi < qpad && lane < 16) ? *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * lane) : 0u;
+            }
         }
         const int tb = __shfl_sync(kFull, (int)tcur, i & 31) & 7;
-        const int sbeg = i > w ? i - w : 0;
         const int send = i + w + 1 < qlen ? i + w + 1 : qlen;
-        if (KIND == kKindExtend) {
+        if (EXT) {
             if (beg < i - w) beg = i - w;
             if (end > send) end = send;
         } else {
-            beg = sbeg;
+            beg = i > w ? i - w : 0;
             end = send;
         }
-        bool touched = false;
-        if (send > slot_hi) {
-            slot_hi = send;
-            if (lane == 0) {
-                hb[send & SM] = (int16_t)init_h16<KIND>(send, qlen, w, h0, o_ins, e_ins);
-                eb[send & SM] = (int16_t)EINIT;
-            }
-            touched = true;
+        const int base = beg & ~(G - 1);
+        // admit the column entering the static window; poison the dead slots [base, beg): the row
+        // computes them unmasked, and H = POISON keeps their u below the F(i,beg) seed
+        if (lane == 0 && send > slot_hi) {
+            hb[send & SM] = (int16_t)init_h16<KIND>(send, qlen, w, h0, o_ins, e_ins);
+            eb[send & SM] = (int16_t)EINIT;
         }
-        if (q_hi < send + 1 && q_hi < qpad) {
-            if (lane < 16) qb[((q_hi >> 1) + lane) & (SM >> 1)] = (uint16_t)sel_for_pair(qpre & 0xffu, qpre >> 8);
-            q_hi += 32;
-            qpre = (q_hi < qpad && lane < 16) ? *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * lane) : 0u;
-            touched = true;
-        }
-        if (touched) __syncwarp();
+        slot_hi = send > slot_hi ? send : slot_hi;
+        if (lane < G - 1 && base + lane < beg) hb[(base + lane) & SM] = (int16_t)POISON;
+        __syncwarp();
 
         const uint2 mrow = mrows[tb];
         int h1init;
-        if (KIND == kKindExtend) {
+        if (EXT) {
             h1init = 0;
             if (beg == 0) { h1init = h0 - (o_del + e_del * (i + 1)); if (h1init < 0) h1init = 0; }
         } else {
             h1init = beg == 0 ? -(o_del + e_del * (i + 1)) : kNeg16;
         }
-        const int base = beg & ~(G - 1);
         const int rb = beg - base, re = end - base;            // live columns, row-relative [rb, re)
         const int ntile = end >= base ? ((end - base) >> (5 + GS)) + 1 : 0;
         uint32_t carryF = dup2(FINIT + rb * e_ins);            // seeded with F(i,beg) in the u-domain
         uint32_t carryH = 0;                                   // left neighbour's last pair, previous tile
-        // row-relative scan offsets of my first pair: RO1 = ((r+1)e,(r+2)e), NRO = (-r e, -(r+1)e)
-        int r0 = lane * G;
-        uint32_t RO1 = pk2((r0 + 1) * e_ins, (r0 + 2) * e_ins);
-        uint32_t NRO = pk2(-r0 * e_ins, -(r0 + 1) * e_ins);
+        uint32_t RO1[NP], NRO[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) { RO1[p] = RO1_0[p]; NRO[p] = NRO_0[p]; }
         uint32_t mrowmax[NP];                                  // extension: running row maxima per pair
         int mt_lo[NP], mt_hi[NP];                              // tile of the last (tie-)update
 #pragma unroll
         for (int p = 0; p < NP; ++p) { mrowmax[p] = 0; mt_lo[p] = -1; mt_hi[p] = -1; }
-        uint8_t* zrow = zdir + (size_t)i * zrow_bytes;
+        uint8_t* zp = zdir + (size_t)i * zrow_bytes;
+        int r0 = lane * G;
 
-        for (int tile = 0; tile < ntile; ++tile, r0 += 32 * G) {
+        for (int tile = 0; tile < ntile; ++tile, r0 += 32 * G, zp += 32 * (G / 2)) {
             const int s0 = (base + r0) & SM;
-            // lane-local live ranges, in columns 0..G
-            const int lo = __viaddmin_s32_relu(rb, -r0, G);          // max(min(rb-r0,G),0)
-            const int hi = __viaddmin_s32_relu(re, -r0, G);
-            const int hc = __viaddmin_s32_relu(re + 1, -r0, G);      // slots [beg,end] -> [lo,hc)
-            uint32_t am[NP], cm[NP];
-            PVec<NP>::ldm(mtab + (lo * (G + 1) + hi) * NP, am);
-            PVec<NP>::ldm(mtab + (lo * (G + 1) + hc) * NP, cm);
             uint32_t H[NP], E[NP], qs[NP];
             PVec<NP>::ld(hb + s0, H); PVec<NP>::ld(eb + s0, E); PVec<NP>::ldq(qb + (s0 >> 1), qs);
+            uint32_t am[NP], cm[NP];
+            if (EXT) {
+                // lane-local live ranges in columns 0..G: cells [lo,hi), slots [lo,hc)
+                const int lo = __viaddmin_s32_relu(rb, -r0, G);          // max(min(rb-r0,G),0)
+                const int hi = __viaddmin_s32_relu(re, -r0, G);
+                const int hc = __viaddmin_s32_relu(re + 1, -r0, G);
+                PVec<NP>::ldm(mtab + (lo * (G + 1) + hi) * NP, am);
+                PVec<NP>::ldm(mtab + (lo * (G + 1) + hc) * NP, cm);
+            }
 
             uint32_t M[NP], tI[NP], pre[NP];
             uint32_t run = NEGP;
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
                 const uint32_t s = prmt(mrow.x, mrow.y, qs[p]);
-                if (KIND == kKindExtend) M[p] = __viaddmin_s16x2(H[p], s, __vadd2(H[p], H[p]));
-                else M[p] = __vadd2(H[p], s);
-                if (KIND == kKindExtend) tI[p] = __viaddmax_s16x2_relu(M[p], N_OE_INS, 0u);
-                else tI[p] = __vadd2(M[p], N_OE_INS);
-                uint32_t u = __vadd2(tI[p], __vadd2(RO1, dup2(2 * p * e_ins)));
-                u = blend(u, NEGP, am[p]);
+                if (EXT) {
+                    M[p] = __viaddmin_s16x2(H[p], s, __vadd2(H[p], H[p]));
+                    tI[p] = __viaddmax_s16x2_relu(M[p], N_OE_INS, 0u);
+                } else {
+                    M[p] = __vadd2(H[p], s);
+                    tI[p] = __vadd2(M[p], N_OE_INS);
+                }
+                const uint32_t u = __vadd2(tI[p], RO1[p]);
                 // exclusive prefix inside the lane: (run, max(run, u.lo))
                 pre[p] = __vmaxs2(run, prmt(u, NEGP, 0x1054));
-                const uint32_t mp = __vmaxs2(u, prmt(u, 0u, 0x1032));
-                run = __vmaxs2(run, mp);
+                run = __vimax3_s16x2(run, u, prmt(u, 0u, 0x1032));
             }
             // inclusive prefix maximum of the lane totals (both halves carry the same value)
             uint32_t incl = run;
@@ -241,12 +256,10 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
             uint32_t Hn[NP];
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-                const uint32_t px = __vmaxs2(pin, pre[p]);
-                const uint32_t nro = __vadd2(NRO, dup2(-2 * p * e_ins));
-                const uint32_t F = __vadd2(px, nro);
+                const uint32_t F = __vadd2(__vmaxs2(pin, pre[p]), NRO[p]);
                 bool a_hi, a_lo, b_hi, b_lo, c_hi, c_lo, d_hi, d_lo;
                 uint32_t h;
-                if (KIND == kKindExtend) {           // ties: E over M, F over both (src/ksw.c:738-741)
+                if (EXT) {                           // ties: E over M, F over both (src/ksw.c:738-741)
                     h = __vibmax_s16x2(E[p], M[p], &a_hi, &a_lo);
                     h = __vibmax_s16x2(F, h, &b_hi, &b_lo);
                 } else {                             // ties: M over E over F (src/ksw.c:598-601)
@@ -255,26 +268,22 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
                 }
                 Hn[p] = h;
                 uint32_t tD;
-                if (KIND == kKindExtend) tD = __viaddmax_s16x2_relu(M[p], N_OE_DEL, 0u);
+                if (EXT) tD = __viaddmax_s16x2_relu(M[p], N_OE_DEL, 0u);
                 else tD = __vadd2(M[p], N_OE_DEL);
                 const uint32_t En = __vibmax_s16x2(tD, __vadd2(E[p], N_E_DEL), &c_hi, &c_lo);
                 (void)__vibmax_s16x2(tI[p], __vadd2(F, N_E_INS), &d_hi, &d_lo);
-                E[p] = blend(En, E[p], am[p]);
-                if (a_lo) dirw |= 1u << (8 * p);
-                if (b_lo) dirw |= 2u << (8 * p);
-                if (c_lo) dirw |= 4u << (8 * p);
-                if (d_lo) dirw |= 8u << (8 * p);
-                if (a_hi) dirw |= 16u << (8 * p);
-                if (b_hi) dirw |= 32u << (8 * p);
-                if (c_hi) dirw |= 64u << (8 * p);
-                if (d_hi) dirw |= 128u << (8 * p);
-                if (KIND == kKindExtend) {
+                E[p] = EXT ? blend(En, E[p], am[p]) : En;
+                dirw |= ((a_lo ? 1u : 0u) | (b_lo ? 2u : 0u) | (c_lo ? 4u : 0u) | (d_lo ? 8u : 0u) |
+                         (a_hi ? 16u : 0u) | (b_hi ? 32u : 0u) | (c_hi ? 64u : 0u) | (d_hi ? 128u : 0u)) << (8 * p);
+                if (EXT) {
                     bool m_hi, m_lo;
                     const uint32_t hm = h | ~am[p];              // inactive columns read -1: never >= max
                     mrowmax[p] = __vibmax_s16x2(hm, mrowmax[p], &m_hi, &m_lo);
                     if (m_lo) mt_lo[p] = tile;
                     if (m_hi) mt_hi[p] = tile;
                 }
+                RO1[p] = __vadd2(RO1[p], TILE_STEP);
+                NRO[p] = __vadd2(NRO[p], N_TILE_STEP);
             }
             // shifted H row: slot j <- H(i, j-1); my first slot takes the left neighbour's last column
             uint32_t left = __shfl_up_sync(kFull, Hn[NP - 1], 1);
@@ -282,18 +291,15 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
             carryH = __shfl_sync(kFull, Hn[NP - 1], 31);
 #pragma unroll
             for (int p = NP - 1; p >= 0; --p) {
-                const uint32_t prev = p == 0 ? left : Hn[p - 1];
-                const uint32_t sh = prmt(prev, Hn[p], 0x5432);    // (prev.hi, Hn[p].lo)
-                H[p] = blend(sh, H[p], cm[p]);
+                const uint32_t sh = prmt(p == 0 ? left : Hn[p - 1], Hn[p], 0x5432);    // (prev.hi, Hn[p].lo)
+                H[p] = EXT ? blend(sh, H[p], cm[p]) : sh;
             }
-            if (hc > lo) { PVec<NP>::st(hb + s0, H); PVec<NP>::st(eb + s0, E); }
-            if (want && hi > lo) {
-                uint8_t* zp = zrow + (size_t)((tile << 5) + lane) * (G / 2);
+            // lanes right of `end` hold nothing of this row (and would alias live slots of the window)
+            if (r0 <= re) { PVec<NP>::st(hb + s0, H); PVec<NP>::st(eb + s0, E); }
+            if (want && r0 < re) {
                 if (NP == 2) *reinterpret_cast<uint16_t*>(zp) = (uint16_t)dirw;
                 else *reinterpret_cast<uint32_t*>(zp) = dirw;
             }
-            RO1 = __vadd2(RO1, TILE_STEP);
-            NRO = __vadd2(NRO, N_TILE_STEP);
         }
         __syncwarp();
         // single-slot fix-ups of the row: eh[beg].h = first-column value, eh[end].e = init
@@ -301,17 +307,18 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
             hb[beg & SM] = (int16_t)h1init;
             eb[end & SM] = (int16_t)EINIT;
         }
-        if (want && KIND == kKindExtend && lane == 0) rowmeta[i] = make_int2(beg, end);
-        __syncwarp();
+        if (EXT && want && lane == 0) rowmeta[i] = make_int2(beg, end);
         cells += end > beg ? end - beg : 0;
-        if (KIND == kKindExtend) {
+        if (EXT) {
+            __syncwarp();
             // row maximum and its LAST column (src/ksw.c:743-744)
             int m = 0, mj = -1;
+            const int cbase = base + lane * G;
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
                 const int vlo = lo16(mrowmax[p]), vhi = hi16(mrowmax[p]);
-                const int clo = mt_lo[p] < 0 ? -1 : base + ((mt_lo[p] << 5) + lane) * G + 2 * p;
-                const int chi = mt_hi[p] < 0 ? -1 : base + ((mt_hi[p] << 5) + lane) * G + 2 * p + 1;
+                const int clo = mt_lo[p] < 0 ? -1 : cbase + (mt_lo[p] << (5 + GS)) + 2 * p;
+                const int chi = mt_hi[p] < 0 ? -1 : cbase + (mt_hi[p] << (5 + GS)) + 2 * p + 1;
                 if (clo >= 0 && (vlo > m || (vlo == m && clo > mj))) { m = vlo; mj = clo; }
                 if (chi >= 0 && (vhi > m || (vhi == m && chi > mj))) { m = vhi; mj = chi; }
             }
@@ -354,10 +361,11 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
             end = nh + 2 < qlen ? nh + 2 : qlen;
         }
     }
+    __syncwarp();
 
     // ---- results
     int score = 0, ti = -1, tk = -1;
-    if (KIND == kKindGlobal) {
+    if (!EXT) {
         score = (int)hb[qlen & SM];                          // eh[qlen].h (src/ksw.c:634)
         ti = tlen - 1;
         tk = (ti + w + 1 < qlen ? ti + w + 1 : qlen) - 1;     // :638
@@ -377,7 +385,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
 }
 
 template <int NP, int KIND>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LB2_FILL16_MIN_BLOCKS)
 fill16_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order, int n,
               const uint8_t* __restrict__ pool, uint8_t* __restrict__ zbase,
               DResult* __restrict__ results, const uint2* __restrict__ gmat,

@@ -98,16 +98,20 @@ class Batch:
             raise _err(self.lib, "lb2_batch_compute")
         return ms.value
 
-    def download(self, want_cigar=True):
+    def download(self, want_cigar=True, copy=True):
+        """-> (results, cigar words).  copy=False returns a view into the batch's pinned
+        staging (valid until close() or the next download)."""
         res = np.zeros(self.n, dtype=RESULT_DTYPE)
         pool, pn = C.c_void_p(), C.c_int64()
-        if self.lib.lb2_batch_download(self.handle, res.ctypes.data,
-                                       C.byref(pool) if want_cigar else None, C.byref(pn)):
+        fn = self.lib.lb2_batch_download if copy else self.lib.lb2_batch_download_view
+        if fn(self.handle, res.ctypes.data, C.byref(pool) if want_cigar else None, C.byref(pn)):
             raise _err(self.lib, "lb2_batch_download")
         cig = np.zeros(0, dtype=np.int32)
-        if want_cigar:
-            if pn.value:
-                cig = np.ctypeslib.as_array(C.cast(pool, C.POINTER(C.c_int32)), shape=(pn.value,)).copy()
+        if want_cigar and pn.value:
+            cig = np.ctypeslib.as_array(C.cast(pool, C.POINTER(C.c_int32)), shape=(pn.value,))
+            if copy:
+                cig = cig.copy()
+        if want_cigar and copy:
             self.lib.lb2_free(pool)
         return res, cig
 
