@@ -36,20 +36,23 @@ extern "C" const char* lb2_last_error(void) { return g_err.c_str(); }
 extern "C" void lb2_free(void* p) { free(p); }
 
 // ----------------------------------------------------------------- context --
-// A launch class = (kind, variant, S = shared-memory window slots).
-// variants: 0..2 int32 lanes with G = 1,2,4 columns per lane; 3,4 packed int16 with NP = 2,4 pairs per lane.
-constexpr int kMinLogS = 6, kMaxLogS = 14;          // 64 .. 16384 slots per warp
+// A launch class = (kind, variant, S = window slots).
+// variants: 0..2 int32 lanes with G = 1,2,4 columns per lane; 3,4 packed int16 with NP = 2,4 pairs
+// per lane; 5 = int32 G=4 with the window in global memory (does not fit shared memory).
+constexpr int kMinLogS = 6, kMaxLogS = 18;          // 64 .. 262144 slots per warp
 constexpr int kNumLogS = kMaxLogS - kMinLogS + 1;
-constexpr int kNumVar = 5;
+constexpr int kNumVar = 6;
+constexpr int kVarGmem = 5;
 constexpr int kNumClass = 2 * kNumVar * kNumLogS;
 constexpr size_t kMaxDynSmem = 200 * 1024;
 static inline int class_id(int kind, int var, int logS) { return (kind * kNumVar + var) * kNumLogS + (logS - kMinLogS); }
 static inline int class_kind(int c) { return c / (kNumVar * kNumLogS); }
 static inline int class_var(int c) { return (c / kNumLogS) % kNumVar; }
 static inline int class_logS(int c) { return c % kNumLogS + kMinLogS; }
-static inline int var_gshift(int var) { return var < 3 ? var : var - 1; }     // log2(columns per lane)
-static inline size_t var_warp_smem(int var, int S) { return var < 3 ? warp_smem_bytes(S) : warp_smem_bytes16(S); }
+static inline int var_gshift(int var) { return var == kVarGmem ? 2 : var < 3 ? var : var - 1; }     // log2(columns per lane)
+static inline size_t var_warp_smem(int var, int S) { return var == 3 || var == 4 ? warp_smem_bytes16(S) : warp_smem_bytes(S); }
 static inline int class_warps(int var, int logS) {   // warps per block
+    if (var == kVarGmem) return 4;
     int wpb = 8;
     while (wpb > 1 && (size_t)wpb * var_warp_smem(var, 1 << logS) > 160 * 1024) wpb >>= 1;
     return wpb;
@@ -91,6 +94,7 @@ struct lb2_ctx {
     uint64_t scratch_limit = 0;
     uint8_t* d_z = nullptr;    size_t z_cap = 0;        // direction nibbles (+ row bands)
     int32_t* d_ctmp = nullptr; size_t ctmp_cap = 0;     // per-task reversed CIGAR scratch (words)
+    uint8_t* d_gwin = nullptr; size_t gwin_cap = 0;     // eh[] windows too large for shared memory
     int occ[kNumClass] = {0};                           // resident blocks per SM, filled lazily
     // side streams: the launch classes of a wave run concurrently, so the drain of one
     // class (few long tasks left) is filled by the blocks of the next
@@ -100,19 +104,19 @@ struct lb2_ctx {
 };
 
 typedef void (*fill_fn)(const DTask*, const int32_t*, int, const uint8_t*, uint8_t*, DResult*,
-                        const uint2*, unsigned int*, int);
+                        const uint2*, unsigned int*, int, uint8_t*);
 static fill_fn fill_table(int kind, int var) {
     if (kind == kKindGlobal) {
         switch (var) {
-            case 0: return fill_kernel<1, kKindGlobal>;   case 1: return fill_kernel<2, kKindGlobal>;
-            case 2: return fill_kernel<4, kKindGlobal>;   case 3: return fill16_kernel<2, kKindGlobal>;
-            default: return fill16_kernel<4, kKindGlobal>;
+            case 0: return fill_kernel<1, kKindGlobal, false>;   case 1: return fill_kernel<2, kKindGlobal, false>;
+            case 2: return fill_kernel<4, kKindGlobal, false>;   case 3: return fill16_kernel<2, kKindGlobal>;
+            case 4: return fill16_kernel<4, kKindGlobal>;        default: return fill_kernel<4, kKindGlobal, true>;
         }
     }
     switch (var) {
-        case 0: return fill_kernel<1, kKindExtend>;   case 1: return fill_kernel<2, kKindExtend>;
-        case 2: return fill_kernel<4, kKindExtend>;   case 3: return fill16_kernel<2, kKindExtend>;
-        default: return fill16_kernel<4, kKindExtend>;
+        case 0: return fill_kernel<1, kKindExtend, false>;   case 1: return fill_kernel<2, kKindExtend, false>;
+        case 2: return fill_kernel<4, kKindExtend, false>;   case 3: return fill16_kernel<2, kKindExtend>;
+        case 4: return fill16_kernel<4, kKindExtend>;        default: return fill_kernel<4, kKindExtend, true>;
     }
 }
 
@@ -152,6 +156,7 @@ extern "C" void lb2_ctx_destroy(lb2_ctx* c) {
     cudaSetDevice(c->device);
     if (c->d_z) cudaFree(c->d_z);
     if (c->d_ctmp) cudaFree(c->d_ctmp);
+    if (c->d_gwin) cudaFree(c->d_gwin);
     if (c->parked.valid) c->parked.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     for (int k = 0; k < lb2_ctx::kAux; ++k) {
@@ -233,11 +238,15 @@ static bool fits_int16(const lb2_task& t, int w) {
 }
 
 // kernel variant from the widest band a row can have
-static int pick_variant(const lb2_task& t, int w, long ncol) {
+static int pick_variant(const lb2_task& t, int w, long ncol, int logS) {
+    const int S_ = 1 << logS;
+    static const int force_gmem = env_int("LB2_FORCE_GMEM", 0);              // test hook
+    if (force_gmem || warp_smem_bytes16(S_) > kMaxDynSmem) return kVarGmem;   // window beyond shared memory
     static const int use16 = env_int("LB2_P16", 1), p16_min = env_int("LB2_P16_MIN", 37),
                      np4_min = env_int("LB2_NP4_MIN", 200), np4_min_ext = env_int("LB2_NP4_MIN_EXT", 1000000);
     if (use16 && ncol >= p16_min && fits_int16(t, w))
         return ncol >= (t.kind == LB2_KIND_EXTEND ? np4_min_ext : np4_min) ? 4 : 3;
+    if (warp_smem_bytes(S_) > kMaxDynSmem) return kVarGmem;
     return ncol <= 36 ? 0 : ncol <= 72 ? 1 : 2;
 }
 // window slots: the whole eh[] array when it is small, else band window + look-ahead
@@ -332,9 +341,9 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
             if (w < 0) { set_err(i, "task %lld: negative band", (long long)i); return; }
             wfin[i] = w;
             const long ncol_i = std::min<long>(t.qlen, 2L * w + 1);
-            const int var = pick_variant(t, w, ncol_i);
-            const int cs = var_gshift(var);
             const int ls = pick_logS(t.qlen, w);
+            const int var = ls < 0 ? 0 : pick_variant(t, w, ncol_i, ls);
+            const int cs = var_gshift(var);
             if (ls < 0) { set_err(i, "task %lld: qlen %d with band %d needs a window beyond %d slots (not supported yet)", (long long)i, t.qlen, w, 1 << kMaxLogS); return; }
             cshift[i] = (int8_t)cs; logS[i] = (int8_t)ls; variant[i] = (int8_t)var;
             if (t.mat != last_mat || t.m != last_m) {
@@ -455,7 +464,7 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
             d.mat_id = (uint8_t)matid[i]; d.cshift = (uint8_t)cshift[i];
             const long ncol = std::min<long>(t.qlen, 2L * wfin[i] + 1);
             d.row_chunks = row_tiles_for(ncol, 1 << cshift[i]);
-            d.dir_fmt = variant[i] >= 3 ? 1 : 0;
+            d.dir_fmt = (variant[i] == 3 || variant[i] == 4) ? 1 : 0;
             uint8_t* q = hp + qoff[i];
             const uint64_t qp = ((uint64_t)t.qlen + 1 + 31) & ~uint64_t(31);
             if (t.qlen) memcpy(q, t.query, t.qlen);
@@ -562,7 +571,7 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
             if (!cnt) continue;
             const int kind = class_kind(k), var = class_var(k), ls = class_logS(k);
             const int wpb = class_warps(var, ls);
-            const size_t smem = (size_t)wpb * var_warp_smem(var, 1 << ls);
+            const size_t smem = var == kVarGmem ? 0 : (size_t)wpb * var_warp_smem(var, 1 << ls);
             if (!c->occ[k]) {
                 int nb = 0;
                 CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fill_table(kind, var), wpb * 32, smem));
@@ -571,12 +580,24 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
             int grid = (cnt + wpb - 1) / wpb;
             const int cap = c->sm_count * c->occ[k];
             if (grid > cap) grid = cap;
+            if (var == kVarGmem) {                    // per-warp windows in global scratch (one class at a time)
+                if (grid > c->sm_count) grid = c->sm_count;
+                const size_t need = (size_t)grid * wpb * warp_smem_bytes(1 << ls);
+                if (c->gwin_cap < need) {
+                    CU(cudaStreamSynchronize(s));
+                    for (int q = 0; q < lb2_ctx::kAux; ++q) CU(cudaStreamSynchronize(c->aux[q]));
+                    if (c->d_gwin) CU(cudaFree(c->d_gwin));
+                    c->d_gwin = nullptr; c->gwin_cap = 0;
+                    CU(cudaMalloc(&c->d_gwin, need)); c->gwin_cap = need;
+                }
+            }
             cudaEvent_t t0 = nullptr, t1 = nullptr;
             if (class_timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, s); }
-            cudaStream_t ls_ = fan ? c->aux[nlaunch++ % lb2_ctx::kAux] : s;
+            // global-window classes share one scratch: keep them all on aux[0] (in order)
+            cudaStream_t ls_ = fan ? c->aux[var == kVarGmem ? 0 : nlaunch++ % lb2_ctx::kAux] : s;
             fill_table(kind, var)<<<grid, wpb * 32, smem, ls_>>>(b->d_tasks, b->d_order + wv.first + wv.cls_off[k], cnt,
                                                              b->d_pool, c->d_z, b->d_results, b->d_mats,
-                                                             b->d_counters + wi * kNumClass + k, 1 << ls);
+                                                             b->d_counters + wi * kNumClass + k, 1 << ls, c->d_gwin);
             if (class_timing) {
                 cudaEventRecord(t1, s); cudaEventSynchronize(t1);
                 float ms = 0; cudaEventElapsedTime(&ms, t0, t1);

@@ -348,20 +348,25 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
 
 // Persistent warps: each warp pulls the next task index of its class from a
 // global counter (tasks are pre-sorted by descending cost on the host).
-// Dynamic shared memory: blockDim.x/32 windows of warp_smem_bytes(S).
-template <int G, int KIND>
+// The eh[] windows live in dynamic shared memory (blockDim.x/32 windows of
+// warp_smem_bytes(S)); GW = true is the variant for windows that do not fit
+// there (bands of tens of thousands of columns, `-V 10000` gaps): the same
+// code over a per-warp slice of an L2-resident global scratch.
+template <int G, int KIND, bool GW>
 __global__ void __launch_bounds__(256)
 fill_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order, int n,
             const uint8_t* __restrict__ pool, uint8_t* __restrict__ zbase,
             DResult* __restrict__ results, const uint2* __restrict__ gmat,
-            unsigned int* __restrict__ counter, int S)
+            unsigned int* __restrict__ counter, int S, uint8_t* __restrict__ gwin)
 {
     __shared__ uint2 smat[kMaxMats * 8];
     extern __shared__ __align__(16) uint8_t dyn[];
     for (int k = threadIdx.x; k < kMaxMats * 8; k += blockDim.x) smat[k] = gmat[k];
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint8_t* mine = dyn + (size_t)wid * warp_smem_bytes(S);
+    uint8_t* mine;
+    if (GW) mine = gwin + ((size_t)blockIdx.x * (blockDim.x >> 5) + wid) * warp_smem_bytes(S);
+    else mine = dyn + (size_t)wid * warp_smem_bytes(S);
     int* hb = reinterpret_cast<int*>(mine);
     int* eb = hb + S;
     uint16_t* qb = reinterpret_cast<uint16_t*>(eb + S);

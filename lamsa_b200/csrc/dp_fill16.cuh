@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256, LB2_FILL16_MIN_BLOCKS)
 fill16_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order, int n,
               const uint8_t* __restrict__ pool, uint8_t* __restrict__ zbase,
               DResult* __restrict__ results, const uint2* __restrict__ gmat,
-              unsigned int* __restrict__ counter, int S)
+              unsigned int* __restrict__ counter, int S, uint8_t* __restrict__ /*gwin: unused*/)
 {
     constexpr int G = 2 * NP;
     __shared__ uint2 smat[kMaxMats * 8];

@@ -8,7 +8,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "../../include/lamsa_b200.h"
 
@@ -30,25 +34,93 @@ lb2_ctx* default_ctx() {
     return g_ctx;
 }
 
-// run one task; returns malloc'd CIGAR (or NULL) through *cig
-void run_one(const lb2_task& t, lb2_result* r, cigar32_t** cig) {
+// ---- combining submitter ----------------------------------------------------
+// The reference calls ksw_* from n_thread pthreads, one read per thread
+// (src/lamsa_aln.c:838-842), each call blocking.  Instead of one launch per
+// call, callers park their task in a shared queue; one of them (the leader)
+// waits a short gather window, submits everything queued as ONE batch and hands
+// the results back.  With `lamsa aln -t 128` a launch carries up to 128 tasks
+// without touching the reference's sources.  A lone caller (or -t 1) degrades to
+// a batch of one after an empty gather window, so nothing can deadlock.
+struct Pending {
+    lb2_task task;
+    lb2_result* res;
+    cigar32_t** cig;        // NULL: caller wants no CIGAR
+    bool done;
+};
+
+std::mutex q_mu;
+std::condition_variable q_cv;
+std::vector<Pending*> q_wait;
+bool q_leader = false;
+int q_last_batch = 1;
+
+int gather_us() {
+    static const int v = [] { const char* e = getenv("LB2_GATHER_US"); return e && *e ? atoi(e) : 40; }();
+    return v;
+}
+
+void submit_batch(std::vector<Pending*>& batch) {
     lb2_ctx* c = default_ctx();
+    const int64_t n = (int64_t)batch.size();
+    std::vector<lb2_task> tasks((size_t)n);
+    std::vector<lb2_result> results((size_t)n);
+    for (int64_t i = 0; i < n; ++i) tasks[(size_t)i] = batch[(size_t)i]->task;
     cigar32_t* pool = nullptr; int64_t pn = 0;
     int rc;
     {
         std::lock_guard<std::mutex> lk(g_mu);      // one stream per context
-        rc = lb2_dp_run(c, 1, &t, r, cig ? &pool : nullptr, &pn);
+        rc = lb2_dp_run(c, n, tasks.data(), results.data(), &pool, &pn);
     }
     if (rc) { fprintf(stderr, "[lamsa_b200] DP launch failed: %s\n", lb2_last_error()); exit(1); }
-    if (cig) {
-        if (r->n_cigar > 0) {
-            // hand back exactly the capacity the reference would have grown to
-            cigar32_t* out = (cigar32_t*)malloc(sizeof(cigar32_t) * (size_t)r->reserved);
-            memcpy(out, pool + r->cigar_off, sizeof(cigar32_t) * (size_t)r->n_cigar);
-            *cig = out;
-        } else *cig = nullptr;
-        lb2_free(pool);
+    for (int64_t i = 0; i < n; ++i) {
+        Pending* p = batch[(size_t)i];
+        const lb2_result& r = results[(size_t)i];
+        *p->res = r;
+        if (p->cig) {
+            if (r.n_cigar > 0) {
+                // hand back exactly the capacity the reference would have grown to
+                cigar32_t* out = (cigar32_t*)malloc(sizeof(cigar32_t) * (size_t)r.reserved);
+                memcpy(out, pool + r.cigar_off, sizeof(cigar32_t) * (size_t)r.n_cigar);
+                *p->cig = out;
+            } else *p->cig = nullptr;
+        }
     }
+    lb2_free(pool);
+}
+
+// run one task; returns malloc'd CIGAR (or NULL) through *cig
+void run_one(const lb2_task& t, lb2_result* r, cigar32_t** cig) {
+    Pending me{t, r, cig, false};
+    std::unique_lock<std::mutex> lk(q_mu);
+    q_wait.push_back(&me);
+    for (;;) {
+        if (me.done) return;
+        if (!q_leader) break;                      // nobody is collecting: I lead
+        q_cv.wait(lk);
+    }
+    q_leader = true;
+    // gather window: only worth waiting when the previous batch showed company
+    if (q_last_batch > 1 && gather_us() > 0) {
+        size_t seen = q_wait.size();
+        for (int spin = 0; spin < 8; ++spin) {
+            lk.unlock();
+            std::this_thread::sleep_for(std::chrono::microseconds(gather_us()));
+            lk.lock();
+            if (q_wait.size() == seen) break;      // arrivals stopped
+            seen = q_wait.size();
+        }
+    }
+    std::vector<Pending*> batch;
+    batch.swap(q_wait);
+    q_last_batch = (int)batch.size();
+    lk.unlock();
+    submit_batch(batch);
+    lk.lock();
+    for (Pending* p : batch) p->done = true;
+    q_leader = false;
+    lk.unlock();
+    q_cv.notify_all();
 }
 
 // ---- CIGAR list helpers (src/frag_check.h:139-188) -------------------------

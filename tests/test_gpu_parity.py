@@ -94,3 +94,36 @@ def test_dropin_entry_points(ctx):
         rc, qle2, tle2, cg2, _ = lamsa_b200.ksw_extend_c(ql, qb, tl, tb, 5, mat, 10, 19, AP)
         assert (qle2, tle2, cg2) == (qle, tle, cg)
         assert rc == (0 if qle == ql else 1 if tle == tl else 2)
+
+
+def test_gpu_huge_windows(ctx):
+    """Bands of ~10^4 columns (`-V 10000` gaps): windows beyond shared memory run the
+    global-memory-window variant; a 32768-slot packed window still fits shared memory."""
+    rng = np.random.default_rng(31)
+    mat = lamsa_b200.default_matrix(1, 3)
+    keep, rows = [mat], []
+
+    def add(kind, q, t, w, h0=0, zdrop=0, pen=(5, 2, 5, 2), end_bonus=5):
+        qb = np.concatenate((q, np.zeros(8, np.uint8))).astype(np.uint8)
+        tb = np.concatenate((t, np.zeros(8, np.uint8))).astype(np.uint8)
+        keep.extend([qb, tb])
+        r = np.zeros(1, dtype=lamsa_b200.TASK_DTYPE)
+        r["kind"], r["flags"], r["qlen"], r["tlen"] = kind, 1, len(q), len(t)
+        r["query"], r["target"], r["w"], r["h0"] = qb.ctypes.data, tb.ctypes.data, w, h0
+        r["o_del"], r["e_del"], r["o_ins"], r["e_ins"] = pen
+        r["end_bonus"], r["zdrop"], r["m"], r["mat"] = end_bonus, zdrop, 5, mat.ctypes.data
+        rows.append(r)
+
+    q = rng.integers(0, 4, size=20000, dtype=np.uint8)
+    t_del = np.concatenate((q[:4000], q[13000:]))            # 9 kbp deletion in the target
+    add(0, q, t_del, 10)                                     # global: w -> |dl|+3 = 9003, int32, global window
+    add(1, q, t_del, 12000, h0=100)                          # extension, band clamp ~1e4
+    add(1, q, q.copy(), 12000, h0=100, zdrop=100)            # long perfect extension (h0+qlen > int16 budget)
+    q2 = rng.integers(0, 4, size=9000, dtype=np.uint8)
+    t2 = np.concatenate((q2[:3000], rng.integers(0, 4, size=6000, dtype=np.uint8), q2[3000:]))
+    add(0, q2, t2, 50, pen=(1, 1, 1, 1))                     # global with a 6 kbp insertion in the target: packed, S=32768
+    tasks = np.concatenate(rows)
+    res, cig = ctx.run(tasks, keep)
+    ores, ocig, _ = _oracle.oracle_run(tasks, 4)
+    bad = _oracle.compare(tasks, res, cig, ores, ocig, what="huge", check_cells=True)
+    assert not bad, "\n".join(bad)
