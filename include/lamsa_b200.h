@@ -130,7 +130,9 @@ typedef struct lb2_ctx lb2_ctx;        /* one per (process, GPU) */
 typedef struct lb2_batch lb2_batch;    /* packed, device-resident task set */
 
 enum { LB2_KIND_GLOBAL = 0, LB2_KIND_EXTEND = 1 };
-enum { LB2_FLAG_CIGAR = 1 };           /* produce the traceback / CIGAR */
+enum { LB2_FLAG_CIGAR = 1,             /* produce the traceback / CIGAR                                   */
+       LB2_FLAG_TARGET_PAC = 2,        /* target = window [target_pac, +tlen) of the resident reference   */
+       LB2_FLAG_TARGET_REV = 4 };      /* ... read back to front (what ksw_extend_r does, src/ksw.c:829)  */
 
 /* One DP task.  `w` is the band as the CALLER would pass it to the reference;
  * the adjustments of src/ksw.c:549 and :696-704 are applied by the library. */
@@ -146,6 +148,7 @@ typedef struct {
     int32_t end_bonus, zdrop;     /* extension only                              */
     int32_t m;                    /* alphabet size, 1..8                         */
     const int8_t *mat;            /* m*m scores, host memory                     */
+    int64_t target_pac;           /* LB2_FLAG_TARGET_PAC: pac coordinate of the window's first base  */
 } lb2_task;
 
 typedef struct {
@@ -158,6 +161,13 @@ typedef struct {
     int64_t cigar_off;            /* first word inside the batch's CIGAR pool    */
     int64_t cells;                /* inner-loop bodies evaluated     */
 } lb2_result;
+
+/* Keep the reference's 2-bit packed FORWARD sequence resident on the GPU (the .pac
+ * image `lamsa aln` loads at src/lamsa_aln.c:1238-1239; base k is
+ * pac[k>>2] >> ((~k&3)<<1) & 3, src/bntseq.c:242).  Tasks flagged LB2_FLAG_TARGET_PAC
+ * then carry (target_pac, tlen) instead of unpacked bytes: replaces the per-call
+ * pac2fa_core unpack (src/bntseq.c:465-477) and the H2D copy of target bytes. */
+int  lb2_ctx_set_reference(lb2_ctx *ctx, const uint8_t *pac, int64_t l_pac);
 
 /* All functions return 0 on success, non-zero on error (message via lb2_last_error). */
 int  lb2_ctx_create(int device, lb2_ctx **out);

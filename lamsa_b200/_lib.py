@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LB2_LIB_PATH") or os.path.join(HERE, "liblamsa_b200.so")   # env override: kernel experiments
 
 KIND_GLOBAL, KIND_EXTEND = 0, 1
-FLAG_CIGAR = 1
+FLAG_CIGAR, FLAG_TARGET_PAC, FLAG_TARGET_REV = 1, 2, 4
 
 
 class LibraryMissing(RuntimeError):
@@ -21,8 +21,9 @@ TASK_DTYPE = np.dtype([
     ("query", "<u8"), ("target", "<u8"),
     ("w", "<i4"), ("h0", "<i4"), ("o_del", "<i4"), ("e_del", "<i4"), ("o_ins", "<i4"), ("e_ins", "<i4"),
     ("end_bonus", "<i4"), ("zdrop", "<i4"), ("m", "<i4"), ("_pad", "<i4"), ("mat", "<u8"),
+    ("target_pac", "<i8"),
 ], align=True)
-assert TASK_DTYPE.itemsize == 80
+assert TASK_DTYPE.itemsize == 88
 
 RESULT_DTYPE = np.dtype([
     ("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"), ("gscore", "<i4"),
@@ -71,7 +72,7 @@ PARA_FIELDS = [
 EXPORTS = [
     "ksw_global2", "ksw_global", "ksw_extend2", "ksw_extend", "ksw_extend_core", "ksw_extend_c",
     "ksw_extend_r", "ksw_bi_extend", "sw_mid_fix",
-    "lb2_ctx_create", "lb2_ctx_destroy", "lb2_last_error", "lb2_ctx_set_scratch_limit", "lb2_dp_run",
+    "lb2_ctx_create", "lb2_ctx_destroy", "lb2_last_error", "lb2_ctx_set_scratch_limit", "lb2_ctx_set_reference", "lb2_dp_run",
     "lb2_batch_create", "lb2_batch_upload", "lb2_batch_compute", "lb2_batch_download", "lb2_batch_download_view", "lb2_batch_stats",
     "lb2_batch_destroy", "lb2_free", "lb2_int_peak",
 ]
@@ -95,6 +96,7 @@ def load_library():
     lib.lb2_ctx_destroy.argtypes = [P]
     lib.lb2_ctx_destroy.restype = None
     lib.lb2_ctx_set_scratch_limit.argtypes = [P, C.c_uint64]
+    lib.lb2_ctx_set_reference.argtypes = [P, P, I64]
     lib.lb2_dp_run.argtypes = [P, I64, P, P, C.POINTER(P), C.POINTER(I64)]
     lib.lb2_batch_create.argtypes = [P, I64, P, C.POINTER(P)]
     lib.lb2_batch_upload.argtypes = [P]

@@ -95,6 +95,7 @@ struct lb2_ctx {
     uint8_t* d_z = nullptr;    size_t z_cap = 0;        // direction nibbles (+ row bands)
     int32_t* d_ctmp = nullptr; size_t ctmp_cap = 0;     // per-task reversed CIGAR scratch (words)
     uint8_t* d_gwin = nullptr; size_t gwin_cap = 0;     // eh[] windows too large for shared memory
+    uint8_t* d_pac = nullptr;  int64_t l_pac = 0;       // resident 2-bit forward reference (lb2_ctx_set_reference)
     int occ[kNumClass] = {0};                           // resident blocks per SM, filled lazily
     // side streams: the launch classes of a wave run concurrently, so the drain of one
     // class (few long tasks left) is filled by the blocks of the next
@@ -103,7 +104,7 @@ struct lb2_ctx {
     cudaEvent_t fork_ev = nullptr, join_ev[kAux] = {nullptr, nullptr, nullptr, nullptr};
 };
 
-typedef void (*fill_fn)(const DTask*, const int32_t*, int, const uint8_t*, uint8_t*, DResult*,
+typedef void (*fill_fn)(const DTask*, const int32_t*, int, const uint8_t*, const uint8_t*, uint8_t*, DResult*,
                         const uint2*, unsigned int*, int, uint8_t*);
 static fill_fn fill_table(int kind, int var) {
     if (kind == kKindGlobal) {
@@ -157,6 +158,7 @@ extern "C" void lb2_ctx_destroy(lb2_ctx* c) {
     if (c->d_z) cudaFree(c->d_z);
     if (c->d_ctmp) cudaFree(c->d_ctmp);
     if (c->d_gwin) cudaFree(c->d_gwin);
+    if (c->d_pac) cudaFree(c->d_pac);
     if (c->parked.valid) c->parked.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     for (int k = 0; k < lb2_ctx::kAux; ++k) {
@@ -165,6 +167,20 @@ extern "C" void lb2_ctx_destroy(lb2_ctx* c) {
     }
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     delete c;
+}
+
+extern "C" int lb2_ctx_set_reference(lb2_ctx* c, const uint8_t* pac, int64_t l_pac) {
+    if (!c || !pac || l_pac <= 0) return fail("lb2_ctx_set_reference: bad argument");
+    if (l_pac >= ((int64_t)1 << 32)) return fail("lb2_ctx_set_reference: %lld bases exceed the 32-bit window coordinate", (long long)l_pac);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_pac) CU(cudaFree(c->d_pac));
+    c->d_pac = nullptr; c->l_pac = 0;
+    const size_t bytes = (size_t)(l_pac / 4 + 1);
+    CU(cudaMalloc(&c->d_pac, bytes + 16));
+    CU(cudaMemcpy(c->d_pac, pac, bytes, cudaMemcpyHostToDevice));
+    c->l_pac = l_pac;
+    return 0;
 }
 
 extern "C" int lb2_ctx_set_scratch_limit(lb2_ctx* c, uint64_t bytes) {
@@ -328,7 +344,11 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
             if (t.qlen < 0 || t.tlen < 0) { set_err(i, "task %lld: qlen %d tlen %d", (long long)i, t.qlen, t.tlen); return; }
             if (t.kind != LB2_KIND_GLOBAL && t.kind != LB2_KIND_EXTEND) { set_err(i, "task %lld: kind %d", (long long)i, t.kind); return; }
             if (t.m < 1 || t.m > 8 || !t.mat) { set_err(i, "task %lld: alphabet size %d unsupported (1..8)", (long long)i, t.m); return; }
-            if ((t.qlen && !t.query) || (t.tlen && !t.target)) { set_err(i, "task %lld: NULL sequence", (long long)i); return; }
+            const bool tpac = (t.flags & LB2_FLAG_TARGET_PAC) != 0;
+            if ((t.qlen && !t.query) || (t.tlen && !tpac && !t.target)) { set_err(i, "task %lld: NULL sequence", (long long)i); return; }
+            if (tpac && (!ctx->d_pac || t.target_pac < 0 || t.target_pac + t.tlen > ctx->l_pac)) {
+                set_err(i, "task %lld: reference window [%lld,+%d) outside the resident reference (%lld bases)", (long long)i,
+                        (long long)t.target_pac, t.tlen, (long long)ctx->l_pac); return; }
             if (t.e_del <= 0 || t.e_ins <= 0) { set_err(i, "task %lld: gap extension penalties must be > 0", (long long)i); return; }
             int w = t.w;
             if (t.kind == LB2_KIND_GLOBAL) {
@@ -366,7 +386,8 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     uint64_t pool = 0;
     for (int64_t i = 0; i < n; ++i) {
         qoff[i] = pool; pool += ((uint64_t)tasks[i].qlen + 1 + 31) & ~uint64_t(31);
-        toff[i] = pool; pool += ((uint64_t)tasks[i].tlen + 31) & ~uint64_t(31);
+        toff[i] = pool;
+        if (!(tasks[i].flags & LB2_FLAG_TARGET_PAC)) pool += ((uint64_t)tasks[i].tlen + 31) & ~uint64_t(31);
     }
     if (pool >> 37) return fail("sequence pool of %llu bytes is too large for one batch", (unsigned long long)pool);
 
@@ -456,11 +477,15 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
         for (int64_t i = a; i < e; ++i) {
             const lb2_task& t = tasks[i];
             DTask& d = ht[i];
-            d.q_off32 = (uint32_t)(qoff[i] >> 5); d.t_off32 = (uint32_t)(toff[i] >> 5);
+            const bool tpac = (t.flags & LB2_FLAG_TARGET_PAC) != 0;
+            d.q_off32 = (uint32_t)(qoff[i] >> 5);
+            d.t_off32 = tpac ? (uint32_t)t.target_pac : (uint32_t)(toff[i] >> 5);
             d.qlen = t.qlen; d.tlen = t.tlen; d.w = wfin[i]; d.h0 = t.h0;
             d.o_del = t.o_del; d.e_del = t.e_del; d.o_ins = t.o_ins; d.e_ins = t.e_ins;
             d.end_bonus = t.end_bonus; d.zdrop = t.zdrop;
-            d.kind = (uint8_t)t.kind; d.want_dir = (t.flags & LB2_FLAG_CIGAR) ? 1 : 0;
+            d.kind = (uint8_t)t.kind;
+            d.want_dir = (uint8_t)(((t.flags & LB2_FLAG_CIGAR) ? kWantDir : 0) | (tpac ? kTargetPac : 0) |
+                                   ((tpac && (t.flags & LB2_FLAG_TARGET_REV)) ? kTargetRev : 0));
             d.mat_id = (uint8_t)matid[i]; d.cshift = (uint8_t)cshift[i];
             const long ncol = std::min<long>(t.qlen, 2L * wfin[i] + 1);
             d.row_chunks = row_tiles_for(ncol, 1 << cshift[i]);
@@ -469,10 +494,12 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
             const uint64_t qp = ((uint64_t)t.qlen + 1 + 31) & ~uint64_t(31);
             if (t.qlen) memcpy(q, t.query, t.qlen);
             memset(q + t.qlen, 0, qp - t.qlen);
-            uint8_t* tt = hp + toff[i];
-            const uint64_t tp = ((uint64_t)t.tlen + 31) & ~uint64_t(31);
-            if (t.tlen) memcpy(tt, t.target, t.tlen);
-            memset(tt + t.tlen, 0, tp - t.tlen);
+            if (!tpac) {
+                uint8_t* tt = hp + toff[i];
+                const uint64_t tp = ((uint64_t)t.tlen + 31) & ~uint64_t(31);
+                if (t.tlen) memcpy(tt, t.target, t.tlen);
+                memset(tt + t.tlen, 0, tp - t.tlen);
+            }
         }
     });
 
@@ -596,7 +623,7 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
             // global-window classes share one scratch: keep them all on aux[0] (in order)
             cudaStream_t ls_ = fan ? c->aux[var == kVarGmem ? 0 : nlaunch++ % lb2_ctx::kAux] : s;
             fill_table(kind, var)<<<grid, wpb * 32, smem, ls_>>>(b->d_tasks, b->d_order + wv.first + wv.cls_off[k], cnt,
-                                                             b->d_pool, c->d_z, b->d_results, b->d_mats,
+                                                             b->d_pool, c->d_pac, c->d_z, b->d_results, b->d_mats,
                                                              b->d_counters + wi * kNumClass + k, 1 << ls, c->d_gwin);
             if (class_timing) {
                 cudaEventRecord(t1, s); cudaEventSynchronize(t1);

@@ -16,18 +16,19 @@ constexpr int kMaxMats = 16;             // distinct scoring matrices per batch
 constexpr int kKindGlobal = 0;
 constexpr int kKindExtend = 1;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kWantDir = 1, kTargetPac = 2, kTargetRev = 4;    // bits of DTask::want_dir
 
 // One DP task as the kernels see it.  Sequences live in one pooled byte array
 // (`pool`), every sequence starting on a 32-byte boundary and padded so that a
 // whole column chunk can always be fetched with one aligned vector load.
 struct __align__(16) DTask {
-    uint32_t q_off32, t_off32;   // offsets into pool, in 32-byte units
+    uint32_t q_off32, t_off32;   // offsets into pool, in 32-byte units (t_off32: pac coordinate when kTargetPac)
     int32_t qlen, tlen;
     int32_t w;                   // FINAL band: after src/ksw.c:549 resp. :696-704
     int32_t h0;
     int32_t o_del, e_del, o_ins, e_ins;
     int32_t end_bonus, zdrop;
-    uint8_t kind, want_dir, mat_id, cshift;   // cshift = log2(G), G = columns per lane per tile
+    uint8_t kind, want_dir /* bit0 directions, kTargetPac, kTargetRev */, mat_id, cshift;   // cshift = log2(G), G = columns per lane per tile
     int32_t row_chunks;          // tiles (32*G columns) of direction nibbles stored per row
     uint64_t z_off;              // byte offset of this task's direction scratch
     uint64_t ctmp_end;           // word offset one past this task's CIGAR scratch
@@ -46,11 +47,38 @@ struct __align__(16) DResult {
 };
 static_assert(sizeof(DResult) == 64, "DResult layout");
 
+// Target code of row `idx`: from the pooled bytes, or from the resident 2-bit reference
+// (bntseq layout: base k = pac[k>>2] >> ((~k&3)<<1) & 3, reference src/bntseq.c:242).
+struct TargetSrc {
+    const uint8_t* bytes;      // pooled codes (padded to a multiple of 32)
+    const uint8_t* pac;        // resident reference, or nullptr
+    uint32_t coor;             // pac coordinate of the window's first base
+    int tlen, tpad, rev;
+    __device__ __forceinline__ uint32_t at(int idx) const {
+        if (idx >= tpad) return 0u;
+        if (!pac) return bytes[idx];
+        if (idx >= tlen) return 0u;
+        const uint64_t k = (uint64_t)coor + (uint32_t)(rev ? tlen - 1 - idx : idx);
+        return (pac[k >> 2] >> ((~k & 3u) << 1)) & 3u;
+    }
+};
+__device__ __forceinline__ TargetSrc make_target(const struct DTask& T, const uint8_t* pool, const uint8_t* pac);
+
 // direction nibble: bits0-1 source of H (0 diagonal, 1 E, 2 F), bit2 E was an
 // extension, bit3 F was an extension.  The reference byte (src/ksw.c:556) is
 // nib&3 | (nib&4) | (nib&8)<<2.
 __host__ __device__ inline uint64_t ext_meta_bytes(int tlen) {
     return ((uint64_t)tlen * 8 + 15) & ~uint64_t(15);
+}
+
+__device__ __forceinline__ TargetSrc make_target(const DTask& T, const uint8_t* pool, const uint8_t* pac) {
+    TargetSrc t;
+    const bool p = (T.want_dir & kTargetPac) != 0;
+    t.bytes = pool + (p ? 0 : (size_t)T.t_off32 * 32);
+    t.pac = p ? pac : nullptr;
+    t.coor = T.t_off32;
+    t.tlen = T.tlen; t.tpad = (T.tlen + 31) & ~31; t.rev = (T.want_dir & kTargetRev) ? 1 : 0;
+    return t;
 }
 
 }  // namespace lb2

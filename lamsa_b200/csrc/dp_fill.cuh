@@ -92,7 +92,7 @@ __host__ __device__ inline int row_tiles_for(long ncol, int G) { return (int)((n
 __host__ __device__ constexpr size_t warp_smem_bytes(int S) { return (size_t)S * 10; }
 
 template <int G, int KIND>
-__device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
+__device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool, const uint8_t* __restrict__ pac,
                           uint8_t* __restrict__ zbase, DResult* __restrict__ res,
                           const uint2* __restrict__ smat /* [kMaxMats][8] */,
                           int* __restrict__ hb, int* __restrict__ eb, uint16_t* __restrict__ qb,
@@ -106,8 +106,8 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
     const int o_del = T.o_del, e_del = T.e_del, o_ins = T.o_ins, e_ins = T.e_ins;
     const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
     const uint8_t* __restrict__ qseq = pool + (size_t)T.q_off32 * 32;
-    const uint8_t* __restrict__ tseq = pool + (size_t)T.t_off32 * 32;
-    const bool want = T.want_dir != 0;
+    const TargetSrc tsrc = make_target(T, pool, pac);
+    const bool want = (T.want_dir & kWantDir) != 0;
     const int RT = T.row_chunks;                        // tiles per stored row
     int2* __restrict__ rowmeta = reinterpret_cast<int2*>(zbase + T.z_off);
     uint8_t* __restrict__ zdir = zbase + T.z_off + (KIND == kKindExtend ? ext_meta_bytes(tlen) : 0);
@@ -132,14 +132,14 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
     int mx = h0, mx_i = -1, mx_j = -1, mx_ie = -1, gscore = -1, max_off = 0;
     long long cells = 0;
     const int tpad = (tlen + 31) & ~31;
-    uint32_t tcur = (lane < tpad) ? tseq[lane] : 0u;
-    uint32_t tnext = (32 + lane < tpad) ? tseq[32 + lane] : 0u;
+    uint32_t tcur = tsrc.at(lane);
+    uint32_t tnext = tsrc.at(32 + lane);
     __syncwarp();
     int i = 0;
     for (; i < tlen; ++i) {
         if ((i & 31) == 0 && i) {
             tcur = tnext;
-            tnext = (i + 32 + lane < tpad) ? tseq[i + 32 + lane] : 0u;
+            tnext = tsrc.at(i + 32 + lane);
         }
         const int tb = __shfl_sync(kFull, (int)tcur, i & 31) & 7;
         const int sbeg = i > w ? i - w : 0;
@@ -355,7 +355,7 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool,
 template <int G, int KIND, bool GW>
 __global__ void __launch_bounds__(256)
 fill_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order, int n,
-            const uint8_t* __restrict__ pool, uint8_t* __restrict__ zbase,
+            const uint8_t* __restrict__ pool, const uint8_t* __restrict__ pac, uint8_t* __restrict__ zbase,
             DResult* __restrict__ results, const uint2* __restrict__ gmat,
             unsigned int* __restrict__ counter, int S, uint8_t* __restrict__ gwin)
 {
@@ -376,7 +376,7 @@ fill_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order, 
         t = __shfl_sync(kFull, t, 0);
         if (t >= (unsigned)n) break;
         const int idx = order[t];
-        fill_task<G, KIND>(tasks[idx], pool, zbase, results + idx, smat, hb, eb, qb, S, lane);
+        fill_task<G, KIND>(tasks[idx], pool, pac, zbase, results + idx, smat, hb, eb, qb, S, lane);
     }
 }
 

@@ -96,7 +96,7 @@ template <> struct PVec<4> {
 };
 
 template <int NP, int KIND>
-__device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
+__device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, const uint8_t* __restrict__ pac,
                             uint8_t* __restrict__ zbase, DResult* __restrict__ res,
                             const uint2* __restrict__ smat, const uint32_t* __restrict__ mtab,
                             int16_t* __restrict__ hb, int16_t* __restrict__ eb, uint16_t* __restrict__ qb,
@@ -112,8 +112,8 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
     const int qlen = T.qlen, tlen = T.tlen, w = T.w, h0 = T.h0;
     const int o_del = T.o_del, e_del = T.e_del, o_ins = T.o_ins, e_ins = T.e_ins;
     const uint8_t* __restrict__ qseq = pool + (size_t)T.q_off32 * 32;
-    const uint8_t* __restrict__ tseq = pool + (size_t)T.t_off32 * 32;
-    const bool want = T.want_dir != 0;
+    const TargetSrc tsrc = make_target(T, pool, pac);
+    const bool want = (T.want_dir & kWantDir) != 0;
     int2* __restrict__ rowmeta = reinterpret_cast<int2*>(zbase + T.z_off);
     uint8_t* __restrict__ zdir = zbase + T.z_off + (EXT ? ext_meta_bytes(tlen) : 0) + (size_t)lane * (G / 2);
     const size_t zrow_bytes = (size_t)T.row_chunks * 32 * (G / 2);
@@ -154,7 +154,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
     }
     uint32_t qpre = (q_hi < qpad && lane < 16) ? *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * lane) : 0u;
     uint32_t tcur = 0u;
-    uint32_t tnext = (lane < tpad) ? tseq[lane] : 0u;
+    uint32_t tnext = tsrc.at(lane);
 
     int beg = 0, end = qlen;
     int mx = h0, mx_i = -1, mx_j = -1, mx_ie = -1, gscore = -1, max_off = 0;
@@ -163,7 +163,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
     for (; i < tlen; ++i) {
         if ((i & 31) == 0) {                            // every 32 rows: next target codes, next 32 selectors
             tcur = tnext;
-            tnext = (i + 32 + lane < tpad) ? tseq[i + 32 + lane] : 0u;
+            tnext = tsrc.at(i + 32 + lane);
             if (i && q_hi < qpad) {
                 if (lane < 16) qb[((q_hi >> 1) + lane) & SMQ] = (uint16_t)sel_for_pair(qpre & 0xffu, qpre >> 8);
                 q_hi += 32;
@@ -387,7 +387,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool,
 template <int NP, int KIND>
 __global__ void __launch_bounds__(256, LB2_FILL16_MIN_BLOCKS)
 fill16_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order, int n,
-              const uint8_t* __restrict__ pool, uint8_t* __restrict__ zbase,
+              const uint8_t* __restrict__ pool, const uint8_t* __restrict__ pac, uint8_t* __restrict__ zbase,
               DResult* __restrict__ results, const uint2* __restrict__ gmat,
               unsigned int* __restrict__ counter, int S, uint8_t* __restrict__ /*gwin: unused*/)
 {
@@ -413,7 +413,7 @@ fill16_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order
         t = __shfl_sync(kFull, t, 0);
         if (t >= (unsigned)n) break;
         const int idx = order[t];
-        fill_task16<NP, KIND>(tasks[idx], pool, zbase, results + idx, smat, mtab, hb, eb, qb, S, lane);
+        fill_task16<NP, KIND>(tasks[idx], pool, pac, zbase, results + idx, smat, mtab, hb, eb, qb, S, lane);
     }
 }
 

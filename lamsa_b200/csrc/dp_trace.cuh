@@ -38,7 +38,7 @@ trace_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order,
     if (t >= n) return;
     const int idx = order[t];
     const DTask T = tasks[idx];
-    if (!T.want_dir) return;
+    if (!(T.want_dir & kWantDir)) return;
     DResult* R = results + idx;
     int i = R->ti, k = R->tk;
     const int w = T.w, G = 1 << T.cshift, gs = T.cshift;

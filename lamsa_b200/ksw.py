@@ -46,6 +46,12 @@ class Context:
         if self.lib.lb2_ctx_set_scratch_limit(self.handle, int(nbytes)):
             raise _err(self.lib, "lb2_ctx_set_scratch_limit")
 
+    def set_reference(self, pac, l_pac):
+        """Upload the 2-bit packed forward reference (bntseq .pac layout) once; see lb2_ctx_set_reference."""
+        pac = np.ascontiguousarray(pac, dtype=np.uint8)
+        if self.lib.lb2_ctx_set_reference(self.handle, pac.ctypes.data, int(l_pac)):
+            raise _err(self.lib, "lb2_ctx_set_reference")
+
     def int_peak(self):
         a, b = C.c_double(), C.c_double()
         sm, khz = C.c_int(), C.c_int()

@@ -60,7 +60,7 @@ def test_para_layout_matches_reference_header():
 
 def test_task_and_result_struct_sizes():
     # must match the C structs in include/lamsa_b200.h (checked by the oracle's batch driver too)
-    assert _lib.TASK_DTYPE.itemsize == 80 and _lib.RESULT_DTYPE.itemsize == 48
+    assert _lib.TASK_DTYPE.itemsize == 88 and _lib.RESULT_DTYPE.itemsize == 48
     assert _lib.TASK_DTYPE.fields["mat"][1] == 72 and _lib.RESULT_DTYPE.fields["cells"][1] == 40
 
 

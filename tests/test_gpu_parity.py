@@ -127,3 +127,41 @@ def test_gpu_huge_windows(ctx):
     ores, ocig, _ = _oracle.oracle_run(tasks, 4)
     bad = _oracle.compare(tasks, res, cig, ores, ocig, what="huge", check_cells=True)
     assert not bad, "\n".join(bad)
+
+
+def test_gpu_reference_windows_from_resident_pac(ctx):
+    """f1: targets named as (pac coordinate, length) windows of the resident 2-bit reference
+    (bntseq .pac layout, reference src/bntseq.c:242) give the same results as unpacked bytes;
+    LB2_FLAG_TARGET_REV reads the window back to front (ksw_extend_r, src/ksw.c:829)."""
+    rng = np.random.default_rng(41)
+    L = 300_000
+    ref = rng.integers(0, 4, size=L, dtype=np.uint8)
+    pad = np.concatenate((ref, np.zeros((-L) % 4 + 4, np.uint8)))
+    q4 = pad[: (len(pad) // 4) * 4].reshape(-1, 4)
+    pac = (q4[:, 0] << 6 | q4[:, 1] << 4 | q4[:, 2] << 2 | q4[:, 3]).astype(np.uint8)      # MSB-first
+    c2 = lamsa_b200.Context(0)
+    c2.set_reference(pac, L)
+    base, keep = workload.gen_microbench(4000, seed=42, qmax=400)
+    n = len(base)
+    tl = base["tlen"].astype(np.int64)
+    coor = rng.integers(0, L - 600, size=n).astype(np.int64)
+    rev = (np.arange(n) % 3 == 0) & (base["kind"] == 1)
+    # explicit-bytes twin of every window (what pac2fa_core + the reversal would hand to ksw)
+    toff = np.concatenate(([0], np.cumsum(tl)[:-1]))
+    tbytes = np.empty(int(tl.sum()) + 64, dtype=np.uint8)
+    for i in range(n):
+        wseg = ref[coor[i]: coor[i] + tl[i]]
+        tbytes[toff[i]: toff[i] + tl[i]] = wseg[::-1] if rev[i] else wseg
+    explicit = base.copy()
+    explicit["target"] = tbytes.ctypes.data + toff.astype(np.uint64)
+    bypac = base.copy()
+    bypac["target"] = 0
+    bypac["target_pac"] = coor
+    bypac["flags"] = base["flags"] | lamsa_b200.FLAG_TARGET_PAC | np.where(rev, lamsa_b200.FLAG_TARGET_REV, 0)
+    ores, ocig, _ = _oracle.oracle_run(explicit)
+    res, cig = c2.run(bypac, keep)
+    c2.close()
+    bad = _oracle.compare(explicit, res, cig, ores, ocig, what="pac-window", check_cells=True)
+    assert not bad, "\n".join(bad)
+    with pytest.raises(RuntimeError):          # windows need a resident reference
+        ctx.run(bypac[:4], keep)
