@@ -113,6 +113,8 @@ def main():
     a = ap.parse_args()
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world > 1 and "LB2_HOST_THREADS" not in os.environ:      # ranks share the host cores for packing
+        os.environ["LB2_HOST_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     from lamsa_b200 import workload
     workload_name = (f"ksw microbenchmark C2: {a.tasks} tasks/GPU, qlen U[50,1000], w U[10,200], "
                      "half ksw_global2 / half ksw_extend_core, CIGAR on")

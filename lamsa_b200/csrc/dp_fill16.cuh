@@ -29,7 +29,7 @@
 #include "dp_fill.cuh"
 
 #ifndef LB2_FILL16_MIN_BLOCKS
-#define LB2_FILL16_MIN_BLOCKS 1
+#define LB2_FILL16_MIN_BLOCKS 2
 #endif
 
 namespace lb2 {
@@ -311,19 +311,21 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
         cells += end > beg ? end - beg : 0;
         if (EXT) {
             __syncwarp();
-            // row maximum and its LAST column (src/ksw.c:743-744)
-            int m = 0, mj = -1;
-            const int cbase = base + lane * G;
+            // row maximum and its LAST column (src/ksw.c:743-744): one key per accumulator,
+            // value in the high half, column+1 in the low half (values <= 16000, columns < 65535
+            // on this path), so a single max-reduction yields both; untouched accumulators are key 0
+            // = (m 0, mj -1), the reference's initial state
+            uint32_t key = 0;
+            const int cbase = base + lane * G + 1;
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-                const int vlo = lo16(mrowmax[p]), vhi = hi16(mrowmax[p]);
-                const int clo = mt_lo[p] < 0 ? -1 : cbase + (mt_lo[p] << (5 + GS)) + 2 * p;
-                const int chi = mt_hi[p] < 0 ? -1 : cbase + (mt_hi[p] << (5 + GS)) + 2 * p + 1;
-                if (clo >= 0 && (vlo > m || (vlo == m && clo > mj))) { m = vlo; mj = clo; }
-                if (chi >= 0 && (vhi > m || (vhi == m && chi > mj))) { m = vhi; mj = chi; }
+                const uint32_t klo = (mrowmax[p] << 16) | (uint32_t)(mt_lo[p] < 0 ? 0 : cbase + (mt_lo[p] << (5 + GS)) + 2 * p);
+                const uint32_t khi = (mrowmax[p] & 0xffff0000u) | (uint32_t)(mt_hi[p] < 0 ? 0 : cbase + (mt_hi[p] << (5 + GS)) + 2 * p + 1);
+                key = key > klo ? key : klo;
+                key = key > khi ? key : khi;
             }
-            const int gm = __reduce_max_sync(kFull, m);
-            const int gmj = __reduce_max_sync(kFull, m == gm ? mj : -1);
+            const uint32_t gkey = __reduce_max_sync(kFull, key);
+            const int gm = (int)(gkey >> 16), gmj = (int)(gkey & 0xffffu) - 1;
             const int jfin = beg > end ? beg : end;
             if (jfin == qlen) {                              // src/ksw.c:759-762
                 const int h1 = end > beg ? (int)hb[qlen & SM] : h1init;     // eh[end].h == H(i, qlen-1)
@@ -343,19 +345,29 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
                 if (drop) { ++i; break; }
             }
             // band trim (:775-778): first non-zero slot in [beg,end), last one in [beg',end]
-            int nb = end;
-            for (int st = beg; st < end; st += 32) {
-                const int j = st + lane;
-                const bool nz = j < end && (hb[j & SM] != 0 || eb[j & SM] != 0);
+            int nb = end, nh;
+            if (end - beg < 32) {                            // whole band under one ballot
+                const int j = beg + lane;
+                const bool nz = j <= end && (hb[j & SM] != 0 || eb[j & SM] != 0);
                 const unsigned bal = __ballot_sync(kFull, nz);
-                if (bal) { nb = st + __ffs(bal) - 1; break; }
-            }
-            int nh = nb - 1;
-            for (int st = end; st >= nb; st -= 32) {
-                const int j = st - lane;
-                const bool nz = j >= nb && (hb[j & SM] != 0 || eb[j & SM] != 0);
-                const unsigned bal = __ballot_sync(kFull, nz);
-                if (bal) { nh = st - (__ffs(bal) - 1); break; }
+                const unsigned lowb = bal & ~(1u << (end - beg));          // first scan excludes slot `end`
+                if (lowb) nb = beg + __ffs(lowb) - 1;
+                const unsigned hib = bal & (0xffffffffu << (nb - beg));     // second scan starts at beg'
+                nh = hib ? beg + 31 - __clz(hib) : nb - 1;
+            } else {
+                for (int st = beg; st < end; st += 32) {
+                    const int j = st + lane;
+                    const bool nz = j < end && (hb[j & SM] != 0 || eb[j & SM] != 0);
+                    const unsigned bal = __ballot_sync(kFull, nz);
+                    if (bal) { nb = st + __ffs(bal) - 1; break; }
+                }
+                nh = nb - 1;
+                for (int st = end; st >= nb; st -= 32) {
+                    const int j = st - lane;
+                    const bool nz = j >= nb && (hb[j & SM] != 0 || eb[j & SM] != 0);
+                    const unsigned bal = __ballot_sync(kFull, nz);
+                    if (bal) { nh = st - (__ffs(bal) - 1); break; }
+                }
             }
             beg = nb;
             end = nh + 2 < qlen ? nh + 2 : qlen;
