@@ -220,6 +220,13 @@ def main():
         cpu = {"value": g, "unit": "GCUPS", "cores": threads, "kind": kind,
                "sample": f"first {n} tasks of the same workload ({ccells} cells, {secs:.2f} s wall), pthread pool"}
 
+    traffic, traffic_note = None, "no ncu capture committed"
+    try:        # dram bytes of the dominant kernel from the committed ncu capture, scaled to this task count
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * a.tasks / tj["tasks"]
+        traffic_note = f"{tj['dominant_kernel']}: dram read+write per launch from {tj['source']}, scaled x{a.tasks / tj['tasks']:g}"
+    except Exception:
+        pass
     if rank == 0:
         peak_tops = peak["gops_s16x2"] / 1e3
         fill_step_ms = fill_max / a.steps
@@ -246,7 +253,7 @@ def main():
                          "ops_per_cell": {"extend": OPS_EXTEND, "global": OPS_GLOBAL},
                          "hbm": {"algorithmic_bytes": seq_bytes + 2 * dir_bytes + cigar_bytes,
                                  "achieved_gbs": (seq_bytes + 2 * dir_bytes + cigar_bytes) / (ms_step * 1e-3) / 1e9},
-                         "traffic": None},
+                         "traffic": traffic, "traffic_note": traffic_note},
             "int_peak": peak,
         }
         if cpu:

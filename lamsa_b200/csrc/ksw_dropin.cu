@@ -4,7 +4,8 @@
 // that the reference keeps in its wrappers (src/ksw.c:809-926) and the CIGAR
 // list helpers those wrappers use (src/frag_check.h:139-188).
 //
-// A call made outside a batch scope submits a batch of one task and blocks.
+// Calls block; concurrent callers (the reference's n_thread workers) are combined
+// into one GPU batch by the submitter below.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
