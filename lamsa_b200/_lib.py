@@ -72,7 +72,7 @@ PARA_FIELDS = [
 EXPORTS = [
     "ksw_global2", "ksw_global", "ksw_extend2", "ksw_extend", "ksw_extend_core", "ksw_extend_c",
     "ksw_extend_r", "ksw_bi_extend", "sw_mid_fix",
-    "lb2_ctx_create", "lb2_ctx_destroy", "lb2_last_error", "lb2_ctx_set_scratch_limit", "lb2_ctx_set_reference", "lb2_dp_run",
+    "lb2_ctx_create", "lb2_ctx_destroy", "lb2_last_error", "lb2_ctx_set_scratch_limit", "lb2_ctx_set_reference", "lb2_ctx_last_run_stats", "lb2_ctx_set_chunk_tasks", "lb2_dp_run",
     "lb2_batch_create", "lb2_batch_upload", "lb2_batch_compute", "lb2_batch_download", "lb2_batch_download_view", "lb2_batch_stats",
     "lb2_batch_destroy", "lb2_free", "lb2_int_peak",
 ]
@@ -97,6 +97,8 @@ def load_library():
     lib.lb2_ctx_destroy.restype = None
     lib.lb2_ctx_set_scratch_limit.argtypes = [P, C.c_uint64]
     lib.lb2_ctx_set_reference.argtypes = [P, P, I64]
+    lib.lb2_ctx_set_chunk_tasks.argtypes = [P, I64]
+    lib.lb2_ctx_last_run_stats.argtypes = [P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64)]
     lib.lb2_dp_run.argtypes = [P, I64, P, P, C.POINTER(P), C.POINTER(I64)]
     lib.lb2_batch_create.argtypes = [P, I64, P, C.POINTER(P)]
     lib.lb2_batch_upload.argtypes = [P]

@@ -74,6 +74,7 @@ struct Buffers {
     unsigned int* d_counters = nullptr;  size_t counters_cap = 0;
     int* d_err = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t up_ev = nullptr;                        // H2D of this batch finished
     bool valid = false;
     void release() {
         cudaFreeHost(h_pool); cudaFreeHost(h_tasks); cudaFreeHost(h_results); cudaFreeHost(h_order); cudaFreeHost(h_mats);
@@ -81,6 +82,7 @@ struct Buffers {
         cudaFree(d_pool); cudaFree(d_tasks); cudaFree(d_results); cudaFree(d_order); cudaFree(d_mats);
         cudaFree(d_cdense); cudaFree(d_cursor); cudaFree(d_counters); cudaFree(d_err);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (up_ev) cudaEventDestroy(up_ev);
         *this = Buffers();
     }
 };
@@ -88,7 +90,10 @@ struct Buffers {
 struct lb2_ctx {
     int device = 0;
     std::mutex mu;
-    Buffers parked;                                     // buffers of the last destroyed batch
+    Buffers parked[2];                                  // buffers of the last destroyed batches (two: lb2_dp_run pipelines)
+    cudaStream_t copy = nullptr;                        // H2D of batch k+1 overlaps the kernels of batch k
+    int64_t run_h2d = 0, run_d2h = 0, run_launches = 0; // counters of the last lb2_dp_run
+    int64_t chunk_tasks = 262144;                       // lb2_dp_run pipelines chunks of about this many tasks
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     uint64_t scratch_limit = 0;
@@ -137,6 +142,7 @@ extern "C" int lb2_ctx_create(int device, lb2_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
     for (int k = 0; k < lb2_ctx::kAux; ++k) {
         CU(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->join_ev[k], cudaEventDisableTiming));
@@ -159,7 +165,8 @@ extern "C" void lb2_ctx_destroy(lb2_ctx* c) {
     if (c->d_ctmp) cudaFree(c->d_ctmp);
     if (c->d_gwin) cudaFree(c->d_gwin);
     if (c->d_pac) cudaFree(c->d_pac);
-    if (c->parked.valid) c->parked.release();
+    for (auto& p : c->parked) if (p.valid) p.release();
+    if (c->copy) cudaStreamDestroy(c->copy);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (int k = 0; k < lb2_ctx::kAux; ++k) {
         if (c->aux[k]) cudaStreamDestroy(c->aux[k]);
@@ -180,6 +187,12 @@ extern "C" int lb2_ctx_set_reference(lb2_ctx* c, const uint8_t* pac, int64_t l_p
     CU(cudaMalloc(&c->d_pac, bytes + 16));
     CU(cudaMemcpy(c->d_pac, pac, bytes, cudaMemcpyHostToDevice));
     c->l_pac = l_pac;
+    return 0;
+}
+
+extern "C" int lb2_ctx_set_chunk_tasks(lb2_ctx* c, int64_t tasks) {
+    if (!c || tasks < 1) return fail("lb2_ctx_set_chunk_tasks: bad argument");
+    c->chunk_tasks = tasks;
     return 0;
 }
 
@@ -214,7 +227,8 @@ struct lb2_batch {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // aliases of B.ev
     int64_t h2d_bytes = 0, d2h_bytes = 0, launches = 0;
     float fill_ms = 0, trace_ms = 0;
-    bool uploaded = false, computed = false;
+    bool uploaded = false, enqueued = false, computed = false;
+    std::vector<cudaEvent_t> wave_ev;      // only when scratch forces several waves
 };
 
 // src/ksw.c:696-704 -- double division, truncation toward zero
@@ -279,9 +293,11 @@ extern "C" void lb2_batch_destroy(lb2_batch* b) {
     if (b->ctx) {
         cudaSetDevice(b->ctx->device);
         std::lock_guard<std::mutex> lk(b->ctx->mu);
-        if (b->B.valid && !b->ctx->parked.valid) { b->ctx->parked = b->B; b->B = Buffers(); }
+        for (auto& p : b->ctx->parked)
+            if (b->B.valid && !p.valid) { p = b->B; b->B = Buffers(); }
     }
     if (b->B.valid) b->B.release();
+    for (auto& e : b->wave_ev) cudaEventDestroy(e);
     delete b;
 }
 
@@ -395,7 +411,11 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     b->pool_bytes = pool + 64;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
-        if (ctx->parked.valid) { b->B = ctx->parked; ctx->parked = Buffers(); }
+        // prefer the parked set whose pinned pool is large enough
+        int pick = -1;
+        for (int k = 0; k < 2; ++k)
+            if (ctx->parked[k].valid && (pick < 0 || ctx->parked[k].h_pool_cap >= b->pool_bytes)) pick = k;
+        if (pick >= 0) { b->B = ctx->parked[pick]; ctx->parked[pick] = Buffers(); }
     }
     Buffers& B = b->B;
     B.valid = true;
@@ -533,6 +553,7 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     }
     if (!B.d_err) CU(cudaMalloc(&B.d_err, sizeof(int)));
     for (auto& e : B.ev) if (!e) CU(cudaEventCreate(&e));
+    if (!B.up_ev) CU(cudaEventCreateWithFlags(&B.up_ev, cudaEventDisableTiming));
     b->d_pool = B.d_pool; b->d_tasks = B.d_tasks; b->d_results = B.d_results; b->d_order = B.d_order; b->d_mats = B.d_mats;
     b->d_cdense = B.d_cdense; b->d_cursor = B.d_cursor; b->d_counters = B.d_counters; b->d_err = B.d_err;
     for (int k = 0; k < 4; ++k) b->ev[k] = B.ev[k];
@@ -559,32 +580,40 @@ extern "C" int lb2_batch_upload(lb2_batch* b) {
     lb2_ctx* c = b->ctx;
     CU(cudaSetDevice(c->device));
     const int64_t n1 = std::max<int64_t>(b->n, 1);
-    CU(cudaMemcpyAsync(b->d_pool, b->h_pool, b->pool_bytes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(b->d_tasks, b->h_tasks, sizeof(DTask) * n1, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(b->d_order, b->h_order, sizeof(int32_t) * n1, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(b->d_mats, b->h_mats, sizeof(uint2) * kMaxMats * 8, cudaMemcpyHostToDevice, c->stream));
+    cudaStream_t s = c->copy;
+    CU(cudaMemcpyAsync(b->d_pool, b->h_pool, b->pool_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->d_tasks, b->h_tasks, sizeof(DTask) * n1, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->d_order, b->h_order, sizeof(int32_t) * n1, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->d_mats, b->h_mats, sizeof(uint2) * kMaxMats * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaEventRecord(b->B.up_ev, s));
     b->h2d_bytes = (int64_t)b->pool_bytes + (int64_t)(sizeof(DTask) + 4) * n1 + (int64_t)sizeof(uint2) * kMaxMats * 8;
     b->uploaded = true;
     return 0;
 }
 
-extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
+// Enqueue every kernel of the batch on the context's compute stream(s); no host sync.
+static int compute_enqueue(lb2_batch* b) {
     if (!b) return fail("batch is NULL");
     if (!b->uploaded) return fail("lb2_batch_compute before lb2_batch_upload");
     lb2_ctx* c = b->ctx;
     CU(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
+    CU(cudaStreamWaitEvent(s, b->B.up_ev, 0));
     CU(cudaMemsetAsync(b->d_cursor, 0, sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned int) * b->n_counters, s));
     CU(cudaMemsetAsync(b->d_err, 0, sizeof(int), s));
     b->launches = 0; b->fill_ms = 0; b->trace_ms = 0;
     CU(cudaEventRecord(b->ev[0], s));
-    float fill_acc = 0, trace_acc = 0;
     const bool one_wave = b->waves.size() == 1;
+    for (auto& e : b->wave_ev) cudaEventDestroy(e);
+    b->wave_ev.clear();
     static const int class_timing = env_int("LB2_CLASS_TIMING", 0);
     for (size_t wi = 0; wi < b->waves.size(); ++wi) {
         const Wave& wv = b->waves[wi];
-        if (!one_wave) CU(cudaEventRecord(b->ev[1], s));
+        if (!one_wave) {       // per-wave (start, fills done, trace done) events, read back in compute_finish
+            for (int q = 0; q < 3; ++q) { cudaEvent_t e; CU(cudaEventCreate(&e)); b->wave_ev.push_back(e); }
+            CU(cudaEventRecord(b->wave_ev[wi * 3], s));
+        }
         static const int multi = env_int("LB2_MULTI_STREAM", 1);
         const bool fan = multi && !class_timing;
         if (fan) {
@@ -646,7 +675,7 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
                 CU(cudaStreamWaitEvent(s, c->join_ev[k], 0));
             }
         }
-        CU(cudaEventRecord(b->ev[2], s));
+        CU(cudaEventRecord(one_wave ? b->ev[2] : b->wave_ev[wi * 3 + 1], s));
         if (wv.ctmp_words) {
             trace_kernel<<<(wv.count + 127) / 128, 128, 0, s>>>(b->d_tasks, b->d_order + wv.first, wv.count,
                                                                 c->d_z, b->d_results, c->d_ctmp, b->d_cdense,
@@ -654,21 +683,32 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
             CU(cudaGetLastError());
             ++b->launches;
         }
-        CU(cudaEventRecord(b->ev[3], s));
-        if (!one_wave) {      // per-wave split needs a sync; only taken when scratch forces several waves
-            CU(cudaEventSynchronize(b->ev[3]));
-            float a = 0, t = 0;
-            CU(cudaEventElapsedTime(&a, b->ev[1], b->ev[2]));
-            CU(cudaEventElapsedTime(&t, b->ev[2], b->ev[3]));
-            fill_acc += a; trace_acc += t;
-        }
+        if (!one_wave) CU(cudaEventRecord(b->wave_ev[wi * 3 + 2], s));
     }
+    CU(cudaEventRecord(b->ev[3], s));
+    b->enqueued = true;
+    return 0;
+}
+
+// Wait for the batch's kernels, read the event timings and the device error flag.
+static int compute_finish(lb2_batch* b, float* kernel_ms) {
+    if (!b || !b->enqueued) return fail("lb2_batch_compute: nothing enqueued");
+    lb2_ctx* c = b->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
     CU(cudaEventSynchronize(b->ev[3]));
-    float total = 0;
+    float total = 0, fill_acc = 0, trace_acc = 0;
     CU(cudaEventElapsedTime(&total, b->ev[0], b->ev[3]));
-    if (one_wave) {
+    if (b->waves.size() == 1) {
         CU(cudaEventElapsedTime(&fill_acc, b->ev[0], b->ev[2]));
         CU(cudaEventElapsedTime(&trace_acc, b->ev[2], b->ev[3]));
+    } else {
+        for (size_t wi = 0; wi * 3 + 2 < b->wave_ev.size(); ++wi) {
+            float a = 0, t = 0;
+            CU(cudaEventElapsedTime(&a, b->wave_ev[wi * 3], b->wave_ev[wi * 3 + 1]));
+            CU(cudaEventElapsedTime(&t, b->wave_ev[wi * 3 + 1], b->wave_ev[wi * 3 + 2]));
+            fill_acc += a; trace_acc += t;
+        }
     }
     b->fill_ms = fill_acc; b->trace_ms = trace_acc;
     if (kernel_ms) *kernel_ms = total;
@@ -677,7 +717,13 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
     CU(cudaStreamSynchronize(s));
     if (err) return fail("traceback kernel reported CIGAR scratch overflow (code %d)", err);
     b->computed = true;
+    b->enqueued = false;
     return 0;
+}
+
+extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
+    if (compute_enqueue(b)) return 1;
+    return compute_finish(b, kernel_ms);
 }
 
 static int cigar_capacity(int n) {      // capacity after the doubling pushes of src/ksw.c:506-516
@@ -764,15 +810,64 @@ extern "C" int lb2_batch_stats(const lb2_batch* b, int64_t* h2d, int64_t* d2h, i
     return 0;
 }
 
+// One-shot run.  Large batches are cut into chunks and pipelined: while the GPU
+// runs chunk k, the host packs chunk k+1 and its H2D copy goes out on the copy
+// stream; results and CIGAR words are appended in task order.
 extern "C" int lb2_dp_run(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_result* results,
                           cigar32_t** cigar_pool, int64_t* cigar_pool_n) {
-    lb2_batch* b = nullptr;
-    if (lb2_batch_create(ctx, n, tasks, &b)) return 1;
-    int rc = lb2_batch_upload(b);
-    if (!rc) rc = lb2_batch_compute(b, nullptr);
-    if (!rc) rc = lb2_batch_download(b, results, cigar_pool, cigar_pool_n);
-    lb2_batch_destroy(b);
-    return rc;
+    if (!ctx) return fail("ctx is NULL");
+    static const int64_t chunk_env = env_int("LB2_CHUNK_TASKS", 0);
+    const int64_t chunk_min = chunk_env > 0 ? chunk_env : ctx->chunk_tasks;
+    int64_t K = chunk_min > 0 ? n / chunk_min : 1;
+    K = std::max<int64_t>(1, std::min<int64_t>(K, 16));
+    ctx->run_h2d = ctx->run_d2h = ctx->run_launches = 0;
+    cigar32_t* pool = nullptr; int64_t pool_n = 0, pool_cap = 0;
+    lb2_batch* prev = nullptr; int64_t prev_lo = 0;
+    int rc = 0;
+    auto drain = [&](lb2_batch* b, int64_t lo) -> int {       // finish + download chunk starting at task `lo`
+        if (compute_finish(b, nullptr)) return 1;
+        const cigar32_t* view = nullptr; int64_t used = 0;
+        if (lb2_batch_download_view(b, results + lo, cigar_pool ? &view : nullptr, &used)) return 1;
+        ctx->run_h2d += b->h2d_bytes; ctx->run_d2h += b->d2h_bytes; ctx->run_launches += b->launches;
+        if (cigar_pool) {
+            if (pool_n + used > pool_cap) {
+                pool_cap = std::max<int64_t>((pool_n + used) * (K > 1 ? 2 : 1), 1024);
+                cigar32_t* np = (cigar32_t*)realloc(pool, sizeof(cigar32_t) * (size_t)pool_cap);
+                if (!np) return fail("out of host memory for the CIGAR pool");
+                pool = np;
+            }
+            cigar32_t* dst = pool + pool_n;
+            parallel_for(used, [=](int64_t a, int64_t e) { memcpy(dst + a, view + a, sizeof(cigar32_t) * (size_t)(e - a)); });
+            if (pool_n) {
+                lb2_result* r = results + lo; const int64_t cnt = b->n, base = pool_n;
+                parallel_for(cnt, [=](int64_t a, int64_t e) { for (int64_t i = a; i < e; ++i) r[i].cigar_off += base; });
+            }
+        }
+        pool_n += used;
+        return 0;
+    };
+    for (int64_t k = 0; k < K && !rc; ++k) {
+        const int64_t lo = n * k / K, hi = n * (k + 1) / K;
+        lb2_batch* b = nullptr;
+        if (lb2_batch_create(ctx, hi - lo, tasks + lo, &b)) { rc = 1; break; }      // host packing
+        if (lb2_batch_upload(b) || compute_enqueue(b)) { lb2_batch_destroy(b); rc = 1; break; }
+        if (prev) { rc = drain(prev, prev_lo); lb2_batch_destroy(prev); prev = nullptr; }
+        if (rc) { lb2_batch_destroy(b); break; }
+        prev = b; prev_lo = lo;
+    }
+    if (prev) { if (!rc) rc = drain(prev, prev_lo); lb2_batch_destroy(prev); }
+    if (rc) { free(pool); return 1; }
+    if (cigar_pool) *cigar_pool = pool ? pool : (cigar32_t*)malloc(sizeof(cigar32_t));
+    if (cigar_pool_n) *cigar_pool_n = pool_n;
+    return 0;
+}
+
+extern "C" int lb2_ctx_last_run_stats(const lb2_ctx* ctx, int64_t* h2d, int64_t* d2h, int64_t* launches) {
+    if (!ctx) return fail("ctx is NULL");
+    if (h2d) *h2d = ctx->run_h2d;
+    if (d2h) *d2h = ctx->run_d2h;
+    if (launches) *launches = ctx->run_launches;
+    return 0;
 }
 
 extern "C" int lb2_int_peak(lb2_ctx* ctx, double* gops_s16x2, double* gops_s32, int* sm_count, int* clock_khz) {

@@ -10,6 +10,7 @@ Two ways in, both going through the C ABI of ``liblamsa_b200.so``:
 There is no CPU implementation here; without the library or a GPU these raise.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -60,14 +61,29 @@ class Context:
         return {"gops_s16x2": a.value, "gops_s32": b.value, "sm_count": sm.value, "clock_khz": khz.value}
 
     def run(self, tasks, keep=()):
-        """One-shot lb2_dp_run: tasks (TASK_DTYPE array) -> (results, cigar_pool)."""
-        b = Batch(self, tasks, keep)
-        try:
-            b.upload()
-            b.compute()
-            return b.download()
-        finally:
-            b.close()
+        """One-shot lb2_dp_run (host task records in, host results out; large batches are
+        chunked and pipelined inside the library) -> (results, cigar_pool)."""
+        tasks = np.ascontiguousarray(tasks, dtype=TASK_DTYPE)
+        res = np.zeros(len(tasks), dtype=RESULT_DTYPE)
+        pool, pn = C.c_void_p(), C.c_int64()
+        if self.lib.lb2_dp_run(self.handle, len(tasks), tasks.ctypes.data, res.ctypes.data, C.byref(pool), C.byref(pn)):
+            raise _err(self.lib, "lb2_dp_run")
+        if not pn.value:
+            self.lib.lb2_free(pool)
+            return res, np.zeros(0, dtype=np.int32)
+        # wrap the malloc'd pool without copying; it is freed when the array goes away
+        cig = np.ctypeslib.as_array(C.cast(pool, C.POINTER(C.c_int32)), shape=(pn.value,))
+        weakref.finalize(cig, self.lib.lb2_free, pool.value)
+        return res, cig
+
+    def set_chunk_tasks(self, n):
+        if self.lib.lb2_ctx_set_chunk_tasks(self.handle, int(n)):
+            raise _err(self.lib, "lb2_ctx_set_chunk_tasks")
+
+    def last_run_stats(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.lib.lb2_ctx_last_run_stats(self.handle, C.byref(a), C.byref(b), C.byref(c))
+        return {"h2d_bytes": a.value, "d2h_bytes": b.value, "launches": c.value}
 
     def close(self):
         if self.handle:

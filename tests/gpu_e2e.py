@@ -17,3 +17,7 @@ for it in range(3):
     cells = int(res["cells"].sum())
     print(f"iter {it}: create(pack) {t1-t0:.3f}  upload(async) {t2-t1:.3f}  compute {t3-t2:.3f} (kernels {ms/1e3:.3f})  "
           f"download {t4-t3:.3f}  close {t5-t4:.3f}  total {t5-t0:.3f} s -> {cells/(t5-t0)/1e9:.1f} GCUPS e2e; cigar words {len(cig)}", flush=True)
+
+for it in range(3):
+    t0 = time.perf_counter(); res, cig = ctx.run(tasks, keep); dt = time.perf_counter() - t0
+    print(f"lb2_dp_run (pipelined) iter {it}: {dt:.3f} s -> {int(res['cells'].sum())/dt/1e9:.1f} GCUPS e2e; {ctx.last_run_stats()}", flush=True)

@@ -165,3 +165,17 @@ def test_gpu_reference_windows_from_resident_pac(ctx):
     assert not bad, "\n".join(bad)
     with pytest.raises(RuntimeError):          # windows need a resident reference
         ctx.run(bypac[:4], keep)
+
+
+def test_gpu_pipelined_run_equals_oracle():
+    """lb2_dp_run cuts large batches into chunks (pack / H2D / kernels overlapped): results and
+    CIGAR offsets must be stitched back in task order."""
+    c2 = lamsa_b200.Context(0)
+    c2.set_chunk_tasks(1500)
+    tasks, keep = workload.gen_microbench(20000, seed=206, qmax=300)
+    res, cig = c2.run(tasks, keep)
+    assert c2.last_run_stats()["launches"] > 30          # really ran as many chunks
+    c2.close()
+    ores, ocig, _ = _oracle.oracle_run(tasks)
+    bad = _oracle.compare(tasks, res, cig, ores, ocig, what="pipelined", check_cells=True)
+    assert not bad, "\n".join(bad)
