@@ -16,6 +16,7 @@
 #include "../../include/lamsa_b200.h"
 #include "dp_fill.cuh"
 #include "dp_fill16.cuh"
+#include "dp_fill16s.cuh"
 #include "dp_trace.cuh"
 #include "int_peak.cuh"
 
@@ -38,10 +39,11 @@ extern "C" void lb2_free(void* p) { free(p); }
 // ----------------------------------------------------------------- context --
 // A launch class = (kind, variant, S = window slots).
 // variants: 0..2 int32 lanes with G = 1,2,4 columns per lane; 3,4 packed int16 with NP = 2,4 pairs
-// per lane; 5 = int32 G=4 with the window in global memory (does not fit shared memory).
+// per lane; 5 = int32 G=4 with the window in global memory (does not fit shared memory);
+// 6,7 = packed NP=2 in sub-warp bundles of L = 16 / 8 lanes per task (dp_fill16s.cuh).
 constexpr int kMinLogS = 6, kMaxLogS = 18;          // 64 .. 262144 slots per warp
 constexpr int kNumLogS = kMaxLogS - kMinLogS + 1;
-constexpr int kNumVar = 6;
+constexpr int kNumVar = 8;
 constexpr int kVarGmem = 5;
 constexpr int kNumClass = 2 * kNumVar * kNumLogS;
 constexpr size_t kMaxDynSmem = 200 * 1024;
@@ -49,8 +51,12 @@ static inline int class_id(int kind, int var, int logS) { return (kind * kNumVar
 static inline int class_kind(int c) { return c / (kNumVar * kNumLogS); }
 static inline int class_var(int c) { return (c / kNumLogS) % kNumVar; }
 static inline int class_logS(int c) { return c % kNumLogS + kMinLogS; }
-static inline int var_gshift(int var) { return var == kVarGmem ? 2 : var < 3 ? var : var - 1; }     // log2(columns per lane)
-static inline size_t var_warp_smem(int var, int S) { return var == 3 || var == 4 ? warp_smem_bytes16(S) : warp_smem_bytes(S); }
+static inline int var_gshift(int var) { return var == kVarGmem || var >= 6 ? 2 : var < 3 ? var : var - 1; }     // log2(columns per lane)
+static inline bool var_packed(int var) { return var == 3 || var == 4 || var >= 6; }
+static inline int var_tasks_per_warp(int var) { return var == 6 ? 2 : var == 7 ? 4 : 1; }
+static inline size_t var_warp_smem(int var, int S) {
+    return var_packed(var) ? warp_smem_bytes16(S) * var_tasks_per_warp(var) : warp_smem_bytes(S);
+}
 static inline int class_warps(int var, int logS) {   // warps per block
     if (var == kVarGmem) return 4;
     int wpb = 8;
@@ -116,13 +122,15 @@ static fill_fn fill_table(int kind, int var) {
         switch (var) {
             case 0: return fill_kernel<1, kKindGlobal, false>;   case 1: return fill_kernel<2, kKindGlobal, false>;
             case 2: return fill_kernel<4, kKindGlobal, false>;   case 3: return fill16_kernel<2, kKindGlobal>;
-            case 4: return fill16_kernel<4, kKindGlobal>;        default: return fill_kernel<4, kKindGlobal, true>;
+            case 4: return fill16_kernel<4, kKindGlobal>;        case 5: return fill_kernel<4, kKindGlobal, true>;
+            case 6: return fill16s_kernel<2, kKindGlobal, 16>;   default: return fill16s_kernel<2, kKindGlobal, 8>;
         }
     }
     switch (var) {
         case 0: return fill_kernel<1, kKindExtend, false>;   case 1: return fill_kernel<2, kKindExtend, false>;
         case 2: return fill_kernel<4, kKindExtend, false>;   case 3: return fill16_kernel<2, kKindExtend>;
-        case 4: return fill16_kernel<4, kKindExtend>;        default: return fill_kernel<4, kKindExtend, true>;
+        case 4: return fill16_kernel<4, kKindExtend>;        case 5: return fill_kernel<4, kKindExtend, true>;
+        case 6: return fill16s_kernel<2, kKindExtend, 16>;   default: return fill16s_kernel<2, kKindExtend, 8>;
     }
 }
 
@@ -274,8 +282,15 @@ static int pick_variant(const lb2_task& t, int w, long ncol, int logS) {
     if (force_gmem || warp_smem_bytes16(S_) > kMaxDynSmem) return kVarGmem;   // window beyond shared memory
     static const int use16 = env_int("LB2_P16", 1), p16_min = env_int("LB2_P16_MIN", 37),
                      np4_min = env_int("LB2_NP4_MIN", 200), np4_min_ext = env_int("LB2_NP4_MIN_EXT", 1000000);
-    if (use16 && ncol >= p16_min && fits_int16(t, w))
-        return ncol >= (t.kind == LB2_KIND_EXTEND ? np4_min_ext : np4_min) ? 4 : 3;
+    // narrow bands (the short interval fills of real reads) run 4 tasks per warp
+    static const int sub_l = env_int("LB2_SUBWARP", 8), sub_max_ext = env_int("LB2_SUBWARP_MAX_EXT", 73),
+                     sub_max_glb = env_int("LB2_SUBWARP_MAX_GLB", 73);
+    if (use16 && fits_int16(t, w)) {
+        const bool wide = ncol >= (t.kind == LB2_KIND_EXTEND ? np4_min_ext : np4_min);
+        const int sub_max = t.kind == LB2_KIND_EXTEND ? sub_max_ext : sub_max_glb;
+        if (sub_l && ncol < sub_max && warp_smem_bytes16(S_) * (32 / sub_l) * 2 <= kMaxDynSmem) return sub_l == 16 ? 6 : 7;
+        if (ncol >= p16_min) return wide ? 4 : 3;
+    }
     if (warp_smem_bytes(S_) > kMaxDynSmem) return kVarGmem;
     return ncol <= 36 ? 0 : ncol <= 72 ? 1 : 2;
 }
@@ -509,7 +524,7 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
             d.mat_id = (uint8_t)matid[i]; d.cshift = (uint8_t)cshift[i];
             const long ncol = std::min<long>(t.qlen, 2L * wfin[i] + 1);
             d.row_chunks = row_tiles_for(ncol, 1 << cshift[i]);
-            d.dir_fmt = (variant[i] == 3 || variant[i] == 4) ? 1 : 0;
+            d.dir_fmt = var_packed(variant[i]) ? 1 : 0;
             uint8_t* q = hp + qoff[i];
             const uint64_t qp = ((uint64_t)t.qlen + 1 + 31) & ~uint64_t(31);
             if (t.qlen) memcpy(q, t.query, t.qlen);
@@ -633,7 +648,8 @@ static int compute_enqueue(lb2_batch* b) {
                 CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fill_table(kind, var), wpb * 32, smem));
                 c->occ[k] = nb > 0 ? nb : 1;
             }
-            int grid = (cnt + wpb - 1) / wpb;
+            const int tpb = wpb * var_tasks_per_warp(var);
+            int grid = (cnt + tpb - 1) / tpb;
             const int cap = c->sm_count * c->occ[k];
             if (grid > cap) grid = cap;
             if (var == kVarGmem) {                    // per-warp windows in global scratch (one class at a time)

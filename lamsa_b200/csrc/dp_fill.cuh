@@ -131,7 +131,6 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool, cons
     int beg = 0, end = qlen;
     int mx = h0, mx_i = -1, mx_j = -1, mx_ie = -1, gscore = -1, max_off = 0;
     long long cells = 0;
-    const int tpad = (tlen + 31) & ~31;
     uint32_t tcur = tsrc.at(lane);
     uint32_t tnext = tsrc.at(32 + lane);
     __syncwarp();

@@ -119,7 +119,6 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
     const size_t zrow_bytes = (size_t)T.row_chunks * 32 * (G / 2);
     const uint2* __restrict__ mrows = smat + (int)T.mat_id * 8;
     const int qpad = (qlen + 1 + 31) & ~31;
-    const int tpad = (tlen + 31) & ~31;
 
     // packed constants
     const uint32_t NEGP = dup2(kNeg16);
