@@ -55,6 +55,12 @@ __device__ __forceinline__ uint32_t blend(uint32_t a, uint32_t b, uint32_t m) {
     return r;
 }
 
+// d += bit when the predicate holds: one predicated integer add per stored direction bit
+// (written as PTX so that ptxas keeps the chain instead of building a SEL + IADD3 tree)
+__device__ __forceinline__ void add_flag(uint32_t& d, bool p, uint32_t bit) {
+    asm("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q mad.lo.u32 %0, %2, 1, %0; }" : "+r"(d) : "r"((uint32_t)p), "r"(bit));
+}
+
 // selector pair for two adjacent query codes: {row[c0], sign, row[c1], sign}
 __device__ __forceinline__ uint32_t sel_for_pair(uint32_t c0, uint32_t c1) {
     c0 &= 7u; c1 &= 7u;
@@ -272,8 +278,10 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
                 const uint32_t En = __vibmax_s16x2(tD, __vadd2(E[p], N_E_DEL), &c_hi, &c_lo);
                 (void)__vibmax_s16x2(tI[p], __vadd2(F, N_E_INS), &d_hi, &d_lo);
                 E[p] = EXT ? blend(En, E[p], am[p]) : En;
-                dirw |= ((a_lo ? 1u : 0u) | (b_lo ? 2u : 0u) | (c_lo ? 4u : 0u) | (d_lo ? 8u : 0u) |
-                         (a_hi ? 16u : 0u) | (b_hi ? 32u : 0u) | (c_hi ? 64u : 0u) | (d_hi ? 128u : 0u)) << (8 * p);
+                add_flag(dirw, a_lo, 1u << (8 * p));  add_flag(dirw, b_lo, 2u << (8 * p));
+                add_flag(dirw, c_lo, 4u << (8 * p));  add_flag(dirw, d_lo, 8u << (8 * p));
+                add_flag(dirw, a_hi, 16u << (8 * p)); add_flag(dirw, b_hi, 32u << (8 * p));
+                add_flag(dirw, c_hi, 64u << (8 * p)); add_flag(dirw, d_hi, 128u << (8 * p));
                 if (EXT) {
                     bool m_hi, m_lo;
                     const uint32_t hm = h | ~am[p];              // inactive columns read -1: never >= max

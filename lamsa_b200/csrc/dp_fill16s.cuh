@@ -207,8 +207,10 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
                 const uint32_t En = __vibmax_s16x2(tD, __vadd2(E[p], N_E_DEL), &c_hi, &c_lo);
                 (void)__vibmax_s16x2(tI[p], __vadd2(F, N_E_INS), &d_hi, &d_lo);
                 E[p] = EXT ? blend(En, E[p], am[p]) : En;
-                dirw |= ((a_lo ? 1u : 0u) | (b_lo ? 2u : 0u) | (c_lo ? 4u : 0u) | (d_lo ? 8u : 0u) |
-                         (a_hi ? 16u : 0u) | (b_hi ? 32u : 0u) | (c_hi ? 64u : 0u) | (d_hi ? 128u : 0u)) << (8 * p);
+                add_flag(dirw, a_lo, 1u << (8 * p));  add_flag(dirw, b_lo, 2u << (8 * p));
+                add_flag(dirw, c_lo, 4u << (8 * p));  add_flag(dirw, d_lo, 8u << (8 * p));
+                add_flag(dirw, a_hi, 16u << (8 * p)); add_flag(dirw, b_hi, 32u << (8 * p));
+                add_flag(dirw, c_hi, 64u << (8 * p)); add_flag(dirw, d_hi, 128u << (8 * p));
                 if (EXT) {
                     bool m_hi, m_lo;
                     const uint32_t hm = h | ~am[p];
