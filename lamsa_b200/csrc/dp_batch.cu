@@ -271,8 +271,10 @@ static bool fits_int16(const lb2_task& t, int w) {
         const long maxh = (long)t.h0 + (long)t.qlen * maxs;
         return maxh <= 16000 && maxh + scan <= 32000;
     }
+    // global fill, hat domain (values carry + column*e_ins): s + e_ins must stay an int8
+    if (maxs + t.e_ins > 127) return false;
     const long lower = (long)(-mins) * std::min(t.qlen, t.tlen) + 2 * maxo + maxe * ((long)t.qlen + t.tlen + 2) + (maxo + maxe) + 64;
-    return lower <= 30000 && (long)t.qlen * maxs + scan <= 32000;
+    return lower <= 30000 && (long)t.qlen * (maxs + t.e_ins) + 64 <= 32000;
 }
 
 // kernel variant from the widest band a row can have

@@ -67,14 +67,37 @@ __device__ __forceinline__ uint32_t sel_for_pair(uint32_t c0, uint32_t c1) {
     return c0 | ((c0 | 8u) << 4) | (c1 << 8) | ((c1 | 8u) << 12);
 }
 
+// "row -1" value of slot j in the packed domain.  The GLOBAL fill works in the "hat" domain
+// X^(i,j) = X(i,j) + j*e_ins (slot j holds H(i-1,j-1) + (j-1)*e_ins): there F^ is a plain prefix
+// maximum of u^_k = M^_k - o_ins, so the row-relative scan offsets disappear; every comparison
+// of the reference is between quantities of the same column and is unchanged by the offset.
 template <int KIND>
 __device__ __forceinline__ int init_h16(int j, int qlen, int w, int h0, int o_ins, int e_ins) {
-    const int v = init_h<KIND>(j, qlen, w, h0, o_ins, e_ins);
-    return (KIND == kKindGlobal && v == kNegInf) ? kNeg16 : v;
+    if (KIND == kKindGlobal) {
+        if (j == 0) return -e_ins;                                   // H(-1,-1) = 0, column -1
+        return (j <= qlen && j <= w) ? -(o_ins + e_ins) : kNeg16;    // -(o+e*j) + (j-1)*e
+    }
+    return init_h<KIND>(j, qlen, w, h0, o_ins, e_ins);
+}
+
+// per-task copy of the scoring-matrix rows: global fill adds e_ins to every byte (s^ = s + e_ins)
+__device__ __forceinline__ uint32_t add_bytes(uint32_t x, uint32_t e4) {
+    return ((x & 0x7f7f7f7fu) + (e4 & 0x7f7f7f7fu)) ^ ((x ^ e4) & 0x80808080u);
+}
+template <int KIND>
+__device__ __forceinline__ void stage_matrix(uint2* __restrict__ mrw, const uint2* __restrict__ rows, int e_ins, int gl) {
+    if (gl < 8) {
+        uint2 v = rows[gl];
+        if (KIND == kKindGlobal) {
+            const uint32_t e4 = (uint32_t)(e_ins & 0xff) * 0x01010101u;
+            v.x = add_bytes(v.x, e4); v.y = add_bytes(v.y, e4);
+        }
+        mrw[gl] = v;
+    }
 }
 
 // shared-memory bytes one warp needs for a window of S slots (h16, e16, one selector per pair)
-__host__ __device__ constexpr size_t warp_smem_bytes16(int S) { return (size_t)S * 5; }
+__host__ __device__ constexpr size_t warp_smem_bytes16(int S) { return (size_t)S * 5 + 64; }   // + 8 staged matrix rows
 // per-block table of half masks: entry [lo*(G+1)+hi][p] = mask of columns c in [lo,hi) of pair p
 template <int NP> __host__ __device__ constexpr int mask_table_words() { return (2 * NP + 1) * (2 * NP + 1) * NP; }
 
@@ -106,7 +129,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
                             uint8_t* __restrict__ zbase, DResult* __restrict__ res,
                             const uint2* __restrict__ smat, const uint32_t* __restrict__ mtab,
                             int16_t* __restrict__ hb, int16_t* __restrict__ eb, uint16_t* __restrict__ qb,
-                            const int S, const int lane)
+                            uint2* __restrict__ mrw, const int S, const int lane)
 {
     constexpr int G = 2 * NP;
     constexpr int GS = (NP == 2 ? 2 : 3);
@@ -129,7 +152,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
     // packed constants
     const uint32_t NEGP = dup2(kNeg16);
     const uint32_t N_OE_INS = dup2(-(o_ins + e_ins)), N_OE_DEL = dup2(-(o_del + e_del));
-    const uint32_t N_E_INS = dup2(-e_ins), N_E_DEL = dup2(-e_del);
+    const uint32_t N_E_INS = dup2(-e_ins), N_E_DEL = dup2(-e_del), N_O_INS = dup2(-o_ins);
     const uint32_t TILE_STEP = dup2(32 * G * e_ins), N_TILE_STEP = dup2(-32 * G * e_ins);
     // row-relative scan offsets of my pairs in tile 0: RO1 = ((r+1)e,(r+2)e), NRO = (-r e, -(r+1)e)
     uint32_t RO1_0[NP], NRO_0[NP];
@@ -140,6 +163,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
         NRO_0[p] = pk2(-r * e_ins, -(r + 1) * e_ins);
     }
 
+    stage_matrix<KIND>(mrw, mrows, e_ins, lane);
     // ---- window initialisation: slots [0, send_0]; selectors for columns [0, w+66)
     int slot_hi = (w + 1 < qlen) ? w + 1 : qlen;        // slots [0, slot_hi] are initialised
     for (int j = lane; j <= slot_hi; j += 32) {
@@ -195,17 +219,17 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
         if (lane < G - 1 && base + lane < beg) hb[(base + lane) & SM] = (int16_t)POISON;
         __syncwarp();
 
-        const uint2 mrow = mrows[tb];
+        const uint2 mrow = mrw[tb];
         int h1init;
         if (EXT) {
             h1init = 0;
             if (beg == 0) { h1init = h0 - (o_del + e_del * (i + 1)); if (h1init < 0) h1init = 0; }
         } else {
-            h1init = beg == 0 ? -(o_del + e_del * (i + 1)) : kNeg16;
+            h1init = beg == 0 ? -(o_del + e_del * (i + 1)) - e_ins : kNeg16;    // hat: column -1
         }
         const int rb = beg - base, re = end - base;            // live columns, row-relative [rb, re)
         const int ntile = end >= base ? ((end - base) >> (5 + GS)) + 1 : 0;
-        uint32_t carryF = dup2(FINIT + rb * e_ins);            // seeded with F(i,beg) in the u-domain
+        uint32_t carryF = dup2(EXT ? FINIT + rb * e_ins : kNeg16);            // seeded with F(i,beg) in the u-domain
         uint32_t carryH = 0;                                   // left neighbour's last pair, previous tile
         uint32_t RO1[NP], NRO[NP];
 #pragma unroll
@@ -240,10 +264,10 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
                     M[p] = __viaddmin_s16x2(H[p], s, __vadd2(H[p], H[p]));
                     tI[p] = __viaddmax_s16x2_relu(M[p], N_OE_INS, 0u);
                 } else {
-                    M[p] = __vadd2(H[p], s);
-                    tI[p] = __vadd2(M[p], N_OE_INS);
+                    M[p] = __vadd2(H[p], s);                     // hat domain: s already holds s + e_ins
+                    tI[p] = __vadd2(M[p], N_O_INS);              // u^ = M^ - o_ins
                 }
-                const uint32_t u = __vadd2(tI[p], RO1[p]);
+                const uint32_t u = EXT ? __vadd2(tI[p], RO1[p]) : tI[p];
                 // exclusive prefix inside the lane: (run, max(run, u.lo))
                 pre[p] = __vmaxs2(run, prmt(u, NEGP, 0x1054));
                 run = __vimax3_s16x2(run, u, prmt(u, 0u, 0x1032));
@@ -261,7 +285,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
             uint32_t Hn[NP];
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-                const uint32_t F = __vadd2(__vmaxs2(pin, pre[p]), NRO[p]);
+                const uint32_t F = EXT ? __vadd2(__vmaxs2(pin, pre[p]), NRO[p]) : __vmaxs2(pin, pre[p]);
                 bool a_hi, a_lo, b_hi, b_lo, c_hi, c_lo, d_hi, d_lo;
                 uint32_t h;
                 if (EXT) {                           // ties: E over M, F over both (src/ksw.c:738-741)
@@ -276,7 +300,8 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
                 if (EXT) tD = __viaddmax_s16x2_relu(M[p], N_OE_DEL, 0u);
                 else tD = __vadd2(M[p], N_OE_DEL);
                 const uint32_t En = __vibmax_s16x2(tD, __vadd2(E[p], N_E_DEL), &c_hi, &c_lo);
-                (void)__vibmax_s16x2(tI[p], __vadd2(F, N_E_INS), &d_hi, &d_lo);
+                // F' opened?  tI >= F - e_ins; in the hat domain that is u^ >= F^
+                (void)__vibmax_s16x2(tI[p], EXT ? __vadd2(F, N_E_INS) : F, &d_hi, &d_lo);
                 E[p] = EXT ? blend(En, E[p], am[p]) : En;
                 add_flag(dirw, a_lo, 1u << (8 * p));  add_flag(dirw, b_lo, 2u << (8 * p));
                 add_flag(dirw, c_lo, 4u << (8 * p));  add_flag(dirw, d_lo, 8u << (8 * p));
@@ -289,8 +314,10 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
                     if (m_lo) mt_lo[p] = tile;
                     if (m_hi) mt_hi[p] = tile;
                 }
-                RO1[p] = __vadd2(RO1[p], TILE_STEP);
-                NRO[p] = __vadd2(NRO[p], N_TILE_STEP);
+                if (EXT) {
+                    RO1[p] = __vadd2(RO1[p], TILE_STEP);
+                    NRO[p] = __vadd2(NRO[p], N_TILE_STEP);
+                }
             }
             // shifted H row: slot j <- H(i, j-1); my first slot takes the left neighbour's last column
             uint32_t left = __shfl_up_sync(kFull, Hn[NP - 1], 1);
@@ -385,7 +412,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
     // ---- results
     int score = 0, ti = -1, tk = -1;
     if (!EXT) {
-        score = (int)hb[qlen & SM];                          // eh[qlen].h (src/ksw.c:634)
+        score = (int)hb[qlen & SM] - (qlen - 1) * e_ins;     // eh[qlen].h (src/ksw.c:634), out of the hat domain
         ti = tlen - 1;
         tk = (ti + w + 1 < qlen ? ti + w + 1 : qlen) - 1;     // :638
     } else {
@@ -426,13 +453,14 @@ fill16_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order
     int16_t* hb = reinterpret_cast<int16_t*>(mine);
     int16_t* eb = hb + S;
     uint16_t* qb = reinterpret_cast<uint16_t*>(eb + S);
+    uint2* mrw = reinterpret_cast<uint2*>(qb + (S >> 1));
     for (;;) {
         unsigned int t = 0;
         if (lane == 0) t = atomicAdd(counter, 1u);
         t = __shfl_sync(kFull, t, 0);
         if (t >= (unsigned)n) break;
         const int idx = order[t];
-        fill_task16<NP, KIND>(tasks[idx], pool, pac, zbase, results + idx, smat, mtab, hb, eb, qb, S, lane);
+        fill_task16<NP, KIND>(tasks[idx], pool, pac, zbase, results + idx, smat, mtab, hb, eb, qb, mrw, S, lane);
     }
 }
 

@@ -43,6 +43,7 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
     int16_t* __restrict__ hb = reinterpret_cast<int16_t*>(warp_smem + (size_t)g * warp_smem_bytes16(S));
     int16_t* __restrict__ eb = hb + S;
     uint16_t* __restrict__ qb = reinterpret_cast<uint16_t*>(eb + S);
+    uint2* __restrict__ mrw = reinterpret_cast<uint2*>(qb + (S >> 1));
     const int qlen = T.qlen, tlen = T.tlen, w = T.w, h0 = T.h0;
     const int o_del = T.o_del, e_del = T.e_del, o_ins = T.o_ins, e_ins = T.e_ins;
     const uint8_t* __restrict__ qseq = pool + (size_t)T.q_off32 * 32;
@@ -56,7 +57,7 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
 
     const uint32_t NEGP = dup2(kNeg16);
     const uint32_t N_OE_INS = dup2(-(o_ins + e_ins)), N_OE_DEL = dup2(-(o_del + e_del));
-    const uint32_t N_E_INS = dup2(-e_ins), N_E_DEL = dup2(-e_del);
+    const uint32_t N_E_INS = dup2(-e_ins), N_E_DEL = dup2(-e_del), N_O_INS = dup2(-o_ins);
     const uint32_t TILE_STEP = dup2(L * G * e_ins), N_TILE_STEP = dup2(-L * G * e_ins);
     uint32_t RO1_0[NP], NRO_0[NP];
 #pragma unroll
@@ -66,6 +67,7 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
         NRO_0[p] = pk2(-r * e_ins, -(r + 1) * e_ins);
     }
 
+    stage_matrix<KIND>(mrw, mrows, e_ins, gl);
     // ---- window initialisation: slots [0, send_0]; selectors for columns [0, w+66)
     int slot_hi = (w + 1 < qlen) ? w + 1 : qlen;
     for (int j = gl; j <= slot_hi; j += L) {
@@ -126,18 +128,18 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
         }
         __syncwarp();
 
-        const uint2 mrow = mrows[tb];
+        const uint2 mrow = mrw[tb];
         int h1init;
         if (EXT) {
             h1init = 0;
             if (beg == 0) { h1init = h0 - (o_del + e_del * (i + 1)); if (h1init < 0) h1init = 0; }
         } else {
-            h1init = beg == 0 ? -(o_del + e_del * (i + 1)) : kNeg16;
+            h1init = beg == 0 ? -(o_del + e_del * (i + 1)) - e_ins : kNeg16;    // hat: column -1
         }
         const int rb = beg - base, re = end - base;
         const int ntile = (lr && end >= base) ? ((end - base) >> (LS + GS)) + 1 : 0;
         const int ntile_max = __reduce_max_sync(kFull, ntile);
-        uint32_t carryF = dup2(FINIT + rb * e_ins);
+        uint32_t carryF = dup2(EXT ? FINIT + rb * e_ins : kNeg16);
         uint32_t carryH = 0;
         uint32_t RO1[NP], NRO[NP];
 #pragma unroll
@@ -171,10 +173,10 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
                     M[p] = __viaddmin_s16x2(H[p], s, __vadd2(H[p], H[p]));
                     tI[p] = __viaddmax_s16x2_relu(M[p], N_OE_INS, 0u);
                 } else {
-                    M[p] = __vadd2(H[p], s);
-                    tI[p] = __vadd2(M[p], N_OE_INS);
+                    M[p] = __vadd2(H[p], s);                     // hat domain: s already holds s + e_ins
+                    tI[p] = __vadd2(M[p], N_O_INS);              // u^ = M^ - o_ins
                 }
-                const uint32_t u = __vadd2(tI[p], RO1[p]);
+                const uint32_t u = EXT ? __vadd2(tI[p], RO1[p]) : tI[p];
                 pre[p] = __vmaxs2(run, prmt(u, NEGP, 0x1054));
                 run = __vimax3_s16x2(run, u, prmt(u, 0u, 0x1032));
             }
@@ -190,7 +192,7 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
             uint32_t Hn[NP];
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-                const uint32_t F = __vadd2(__vmaxs2(pin, pre[p]), NRO[p]);
+                const uint32_t F = EXT ? __vadd2(__vmaxs2(pin, pre[p]), NRO[p]) : __vmaxs2(pin, pre[p]);
                 bool a_hi, a_lo, b_hi, b_lo, c_hi, c_lo, d_hi, d_lo;
                 uint32_t h;
                 if (EXT) {
@@ -205,7 +207,8 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
                 if (EXT) tD = __viaddmax_s16x2_relu(M[p], N_OE_DEL, 0u);
                 else tD = __vadd2(M[p], N_OE_DEL);
                 const uint32_t En = __vibmax_s16x2(tD, __vadd2(E[p], N_E_DEL), &c_hi, &c_lo);
-                (void)__vibmax_s16x2(tI[p], __vadd2(F, N_E_INS), &d_hi, &d_lo);
+                // F' opened?  tI >= F - e_ins; in the hat domain that is u^ >= F^
+                (void)__vibmax_s16x2(tI[p], EXT ? __vadd2(F, N_E_INS) : F, &d_hi, &d_lo);
                 E[p] = EXT ? blend(En, E[p], am[p]) : En;
                 add_flag(dirw, a_lo, 1u << (8 * p));  add_flag(dirw, b_lo, 2u << (8 * p));
                 add_flag(dirw, c_lo, 4u << (8 * p));  add_flag(dirw, d_lo, 8u << (8 * p));
@@ -221,8 +224,10 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
                         if (m_hi) mt_hi[p] = tile;
                     }
                 }
-                RO1[p] = __vadd2(RO1[p], TILE_STEP);
-                NRO[p] = __vadd2(NRO[p], N_TILE_STEP);
+                if (EXT) {
+                    RO1[p] = __vadd2(RO1[p], TILE_STEP);
+                    NRO[p] = __vadd2(NRO[p], N_TILE_STEP);
+                }
             }
             uint32_t left = __shfl_up_sync(kFull, Hn[NP - 1], 1, L);
             if (gl == 0) left = carryH;
@@ -319,7 +324,7 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
     if (have) {
         int score, ti, tk;
         if (!EXT) {
-            score = (int)hb[qlen & SM];
+            score = (int)hb[qlen & SM] - (qlen - 1) * e_ins;     // out of the hat domain
             ti = tlen - 1;
             tk = (ti + w + 1 < qlen ? ti + w + 1 : qlen) - 1;
         } else {
