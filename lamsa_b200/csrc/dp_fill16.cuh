@@ -55,10 +55,12 @@ __device__ __forceinline__ uint32_t blend(uint32_t a, uint32_t b, uint32_t m) {
     return r;
 }
 
-// d += bit when the predicate holds: one predicated integer add per stored direction bit
-// (written as PTX so that ptxas keeps the chain instead of building a SEL + IADD3 tree)
-__device__ __forceinline__ void add_flag(uint32_t& d, bool p, uint32_t bit) {
-    asm("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q mad.lo.u32 %0, %2, 1, %0; }" : "+r"(d) : "r"((uint32_t)p), "r"(bit));
+// d += bit when the predicate holds.  The integer ALU pipe is what bounds these kernels while the
+// FMA pipe idles, so the add is written as a guarded multiply-add by a value ptxas cannot prove to
+// be 1: it issues as `@P IMAD` on the FMA pipe (a plain guarded add would go to the ALU pipe, and
+// the C expression becomes a SEL + IADD3 tree there).
+__device__ __forceinline__ void add_flag(uint32_t& d, bool p, uint32_t bit, uint32_t one) {
+    asm("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q mad.lo.u32 %0, %2, %3, %0; }" : "+r"(d) : "r"((uint32_t)p), "r"(one), "r"(bit));
 }
 
 // selector pair for two adjacent query codes: {row[c0], sign, row[c1], sign}
@@ -138,6 +140,8 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
     constexpr int FINIT = EXT ? 0 : kNeg16;
     constexpr int POISON = EXT ? 0 : kNeg16;           // H of dead slots left of the band (see below)
     const int SM = S - 1, SMQ = SM >> 1;
+    // the value 1, opaque to ptxas (S is a power of two): lets add_flag issue on the FMA pipe
+    const uint32_t one = (uint32_t)S >> (31 - __clz(S));
     const int qlen = T.qlen, tlen = T.tlen, w = T.w, h0 = T.h0;
     const int o_del = T.o_del, e_del = T.e_del, o_ins = T.o_ins, e_ins = T.e_ins;
     const uint8_t* __restrict__ qseq = pool + (size_t)T.q_off32 * 32;
@@ -303,10 +307,10 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
                 // F' opened?  tI >= F - e_ins; in the hat domain that is u^ >= F^
                 (void)__vibmax_s16x2(tI[p], EXT ? __vadd2(F, N_E_INS) : F, &d_hi, &d_lo);
                 E[p] = EXT ? blend(En, E[p], am[p]) : En;
-                add_flag(dirw, a_lo, 1u << (8 * p));  add_flag(dirw, b_lo, 2u << (8 * p));
-                add_flag(dirw, c_lo, 4u << (8 * p));  add_flag(dirw, d_lo, 8u << (8 * p));
-                add_flag(dirw, a_hi, 16u << (8 * p)); add_flag(dirw, b_hi, 32u << (8 * p));
-                add_flag(dirw, c_hi, 64u << (8 * p)); add_flag(dirw, d_hi, 128u << (8 * p));
+                add_flag(dirw, a_lo, 1u << (8 * p), one);  add_flag(dirw, b_lo, 2u << (8 * p), one);
+                add_flag(dirw, c_lo, 4u << (8 * p), one);  add_flag(dirw, d_lo, 8u << (8 * p), one);
+                add_flag(dirw, a_hi, 16u << (8 * p), one); add_flag(dirw, b_hi, 32u << (8 * p), one);
+                add_flag(dirw, c_hi, 64u << (8 * p), one); add_flag(dirw, d_hi, 128u << (8 * p), one);
                 if (EXT) {
                     bool m_hi, m_lo;
                     const uint32_t hm = h | ~am[p];              // inactive columns read -1: never >= max
@@ -431,7 +435,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
 }
 
 template <int NP, int KIND>
-__global__ void __launch_bounds__(256, LB2_FILL16_MIN_BLOCKS)
+__global__ void __launch_bounds__(256, (NP == 4 && KIND == kKindGlobal) ? 3 : LB2_FILL16_MIN_BLOCKS)   // measured per kernel
 fill16_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order, int n,
               const uint8_t* __restrict__ pool, const uint8_t* __restrict__ pac, uint8_t* __restrict__ zbase,
               DResult* __restrict__ results, const uint2* __restrict__ gmat,

@@ -35,6 +35,8 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
     const int g = lane >> LS, gl = lane & (L - 1);
     const unsigned gmask = (L == 32) ? kFull : (((1u << L) - 1u) << (g * L));
     const int SM = S - 1, SMQ = SM >> 1;
+    // the value 1, opaque to ptxas (S is a power of two): lets add_flag issue on the FMA pipe
+    const uint32_t one = (uint32_t)S >> (31 - __clz(S));
 
     // ---- my group's task
     const bool have = first + (unsigned)g < (unsigned)n;
@@ -210,10 +212,10 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
                 // F' opened?  tI >= F - e_ins; in the hat domain that is u^ >= F^
                 (void)__vibmax_s16x2(tI[p], EXT ? __vadd2(F, N_E_INS) : F, &d_hi, &d_lo);
                 E[p] = EXT ? blend(En, E[p], am[p]) : En;
-                add_flag(dirw, a_lo, 1u << (8 * p));  add_flag(dirw, b_lo, 2u << (8 * p));
-                add_flag(dirw, c_lo, 4u << (8 * p));  add_flag(dirw, d_lo, 8u << (8 * p));
-                add_flag(dirw, a_hi, 16u << (8 * p)); add_flag(dirw, b_hi, 32u << (8 * p));
-                add_flag(dirw, c_hi, 64u << (8 * p)); add_flag(dirw, d_hi, 128u << (8 * p));
+                add_flag(dirw, a_lo, 1u << (8 * p), one);  add_flag(dirw, b_lo, 2u << (8 * p), one);
+                add_flag(dirw, c_lo, 4u << (8 * p), one);  add_flag(dirw, d_lo, 8u << (8 * p), one);
+                add_flag(dirw, a_hi, 16u << (8 * p), one); add_flag(dirw, b_hi, 32u << (8 * p), one);
+                add_flag(dirw, c_hi, 64u << (8 * p), one); add_flag(dirw, d_hi, 128u << (8 * p), one);
                 if (EXT) {
                     bool m_hi, m_lo;
                     const uint32_t hm = h | ~am[p];
