@@ -207,6 +207,78 @@ void lb2_free(void *p);
  * for the s16x2 DPX max/add chain the fill kernels are built from. */
 int  lb2_int_peak(lb2_ctx *ctx, double *gops_s16x2, double *gops_s32, int *sm_count, int *clock_khz);
 
+/* ------------------------------------------- 3. sparse-DP anchor chaining -- */
+/*
+ * SDP = the skeleton search of src/lamsa_dp_con.c: frag_line_BCC (:1305, round 1
+ * over all seed hits of a read) and frag_line_remain (:1252, round 2 inside the
+ * read regions round 1 left unaligned).  A read is described by its seeds that
+ * have hits (src/lamsa_aln.c:943-951: seed_out of seed_all), each with map_n
+ * hits; a hit is the part of map_t (src/lamsa_aln.h:230-239) the chaining reads.
+ * One warp per read; the predecessor scans of frag_dp_update (:713-751) run across
+ * the lanes, node order and every tie rule of the reference are kept.
+ */
+typedef struct {
+    int64_t offset;      /* map_t.offset: 1-based reference coordinate of the hit      */
+    int32_t nchr;        /* map_t.nchr                                                 */
+    int32_t NM;          /* map_t.NM                                                   */
+    int32_t len_dif;     /* map_t.len_dif                                              */
+    int32_t nstrand;     /* map_t.nstrand: +1 / -1                                     */
+} lb2_sdp_hit;           /* 24 bytes */
+
+/* the fields of lamsa_aln_para the chaining reads */
+typedef struct {
+    int32_t seed_len, seed_step, seed_inv;
+    int32_t per_aln_m, first_loci_thd, SV_len_thd, ske_max;
+    float   ovlp_rat;
+    int32_t split_len, match_dis, mismatch_thd, aln_mode, bwt_seed_len;
+    int32_t frag_score_table[10];   /* src/lamsa_aln.c:177-188 */
+} lb2_sdp_para;
+
+/* one aligned record of round 1 = one push_reg_res entry (src/lamsa_aln.c:580-606) */
+typedef struct {
+    int32_t beg, end;           /* read interval, 1-based inclusive */
+    int32_t chr, is_rev;
+    int64_t ref_beg, ref_end;
+} lb2_sdp_reg;           /* 32 bytes */
+
+typedef struct {
+    int32_t seed_out;    /* seeds with hits (lamsa_aln_per_para.seed_out)              */
+    int32_t seed_all;    /* all seeds of the read (lamsa_aln_per_para.seed_all)        */
+    int32_t read_len;
+    int32_t n_reg;       /* aligned records handed to the remain stage                 */
+    int64_t seed_first;  /* first entry in seed_id[] / map_n[]                         */
+    int64_t hit_first;   /* first entry in hits[]; hits of a read are seed-major       */
+    int64_t reg_first;   /* first entry in regs[]                                      */
+} lb2_sdp_read;          /* 40 bytes */
+
+/*
+ * Result of one stage for one read = the chosen skeletons as an int32 stream
+ * (what frag_dp_path, src/lamsa_dp_con.c:1152-1250, turns into frag_msg):
+ *   n_lines, then per line:  line_score, frag_num,
+ *                            then per fragment: seed_num, seed_num x (seed_i, aln_i)
+ * fragments and seeds in the order frag_set_msg (src/frag_check.c:55) receives them;
+ * frag_left_bound is 0 and frag_right_bound is seed_all+1 for every line (:1191,:1228).
+ */
+typedef struct lb2_sdp_batch lb2_sdp_batch;
+
+/* Packs and uploads the reads (hits stay resident for both stages). */
+int  lb2_sdp_create(lb2_ctx *ctx, const lb2_sdp_para *para, int64_t n_reads, const lb2_sdp_read *reads,
+                    const int32_t *seed_id, const int32_t *map_n, const lb2_sdp_hit *hits,
+                    lb2_sdp_batch **out);
+/* Stage 1 (frag_line_BCC) for every read.  stream/offsets are owned by the batch and stay
+ * valid until the next stage call or lb2_sdp_destroy; read r owns words
+ * [off[r], off[r+1]). */
+int  lb2_sdp_run_bcc(lb2_sdp_batch *b, const int32_t **stream, const int64_t **off, float *kernel_ms);
+/* Stage 2 (frag_line_remain): regs = the aligned records of stage 1 per read
+ * (reads[r].reg_first / n_reg of the `reads` passed here, which may differ from create's
+ * only in those two fields). */
+int  lb2_sdp_run_remain(lb2_sdp_batch *b, const lb2_sdp_read *reads, const lb2_sdp_reg *regs,
+                        const int32_t **stream, const int64_t **off, float *kernel_ms);
+/* predecessor pairs evaluated by get_fseed_dis inside frag_dp_update in the last stage
+ * (the unit of work of the chaining) */
+int  lb2_sdp_stats(const lb2_sdp_batch *b, int64_t *pairs, int64_t *h2d_bytes, int64_t *d2h_bytes);
+void lb2_sdp_destroy(lb2_sdp_batch *b);
+
 #ifdef __cplusplus
 }
 #endif
