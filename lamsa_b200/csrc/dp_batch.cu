@@ -19,6 +19,7 @@
 #include "dp_fill16s.cuh"
 #include "dp_trace.cuh"
 #include "int_peak.cuh"
+#include "ctx_internal.h"
 
 using namespace lb2;
 
@@ -902,4 +903,17 @@ extern "C" int lb2_int_peak(lb2_ctx* ctx, double* gops_s16x2, double* gops_s32, 
     if (gops_s16x2) *gops_s16x2 = a;
     if (gops_s32) *gops_s32 = c;
     return 0;
+}
+
+// ---- internal accessors for the other translation units (ctx_internal.h) ----
+namespace lb2 {
+cudaStream_t ctx_stream(lb2_ctx* c) { return c->stream; }
+int ctx_device(lb2_ctx* c) { return c->device; }
+int ctx_sm_count(lb2_ctx* c) { return c->sm_count; }
+int set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return 1;
+}
 }

@@ -1,0 +1,286 @@
+// sdp_batch.cu -- host side of the sparse-DP chaining interface (include/lamsa_b200.h, section 3):
+// lays the reads out for the kernel (per-read hit prefix, seed-of-hit, scan order, scratch),
+// derives the unaligned read regions for stage 2 (the reference does that on the host too:
+// get_remain_reg, src/lamsa_aln.c:548-572), launches sdp_kernel and gathers the skeleton streams.
+// No chaining decision is taken here.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../include/lamsa_b200.h"
+#include "ctx_internal.h"
+#include "sdp_kernel.cuh"
+
+using namespace lb2;
+using namespace lb2::sdp;
+
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
+    return set_error("%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); } while (0)
+
+namespace {
+template <class T> struct DevBuf {
+    T* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = std::max<size_t>(n, 1);
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+}  // namespace
+
+struct lb2_sdp_batch {
+    lb2_ctx* ctx = nullptr;
+    lb2_sdp_para para{};
+    int64_t n = 0, n_hits = 0, n_seeds = 0;
+    std::vector<DRead> reads;
+    std::vector<int32_t> order;
+    DevBuf<DRead> d_reads; DevBuf<int32_t> d_order, d_seed_id, d_map_n, d_hoff, d_hseed, d_rflat;
+    DevBuf<lb2_sdp_hit> d_hits;
+    DevBuf<int> d_scratch, d_dense; DevBuf<DOut> d_outs; DevBuf<unsigned int> d_counter; DevBuf<long long> d_off;
+    DevBuf<DRegion> d_regions; DevBuf<DPoint> d_pts;
+    std::vector<int32_t> stream; std::vector<int64_t> off; std::vector<DOut> outs;
+    int64_t pairs = 0, h2d = 0, d2h = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+extern "C" void lb2_sdp_destroy(lb2_sdp_batch* b) {
+    if (!b) return;
+    cudaSetDevice(ctx_device(b->ctx));
+    b->d_reads.release(); b->d_order.release(); b->d_seed_id.release(); b->d_map_n.release(); b->d_hoff.release();
+    b->d_hseed.release(); b->d_rflat.release(); b->d_hits.release(); b->d_scratch.release(); b->d_dense.release();
+    b->d_outs.release(); b->d_counter.release(); b->d_off.release(); b->d_regions.release(); b->d_pts.release();
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    delete b;
+}
+
+extern "C" int lb2_sdp_create(lb2_ctx* ctx, const lb2_sdp_para* para, int64_t n_reads, const lb2_sdp_read* reads,
+                              const int32_t* seed_id, const int32_t* map_n, const lb2_sdp_hit* hits,
+                              lb2_sdp_batch** out) {
+    if (!ctx || !para || !out || n_reads < 0 || (n_reads > 0 && (!reads || !seed_id || !map_n)))
+        return set_error("lb2_sdp_create: bad arguments");
+    if (para->seed_step <= 0 || para->ske_max < 1 || para->per_aln_m < 1)
+        return set_error("lb2_sdp_create: seed_step, ske_max and per_aln_m must be positive");
+    if (n_reads > INT32_MAX) return set_error("lb2_sdp_create: too many reads");
+    CU(cudaSetDevice(ctx_device(ctx)));
+    lb2_sdp_batch* b = new lb2_sdp_batch();
+    b->ctx = ctx; b->para = *para; b->n = n_reads;
+    b->reads.resize(n_reads);
+    int64_t n_seeds = 0, n_hits = 0, scratch = 0;
+    for (int64_t r = 0; r < n_reads; ++r) {
+        const lb2_sdp_read& rd = reads[r];
+        if (rd.seed_out < 0 || rd.seed_first < 0 || rd.hit_first < 0) { delete b; return set_error("lb2_sdp_create: read %lld: negative field", (long long)r); }
+        int64_t H = 0;
+        for (int i = 0; i < rd.seed_out; ++i) {
+            const int m = map_n[rd.seed_first + i];
+            if (m < 0 || m > para->per_aln_m) { delete b; return set_error("lb2_sdp_create: read %lld seed %d: map_n %d outside [0, per_aln_m]", (long long)r, i, m); }
+            if (i > 0 && seed_id[rd.seed_first + i] <= seed_id[rd.seed_first + i - 1]) { delete b; return set_error("lb2_sdp_create: read %lld: seed ids must increase", (long long)r); }
+            H += m;
+        }
+        if (H > (1 << 26)) { delete b; return set_error("lb2_sdp_create: read %lld has %lld hits", (long long)r, (long long)H); }
+        DRead& d = b->reads[r];
+        d.seed_out = rd.seed_out; d.seed_all = rd.seed_all; d.read_len = rd.read_len; d.n_hits = (int32_t)H;
+        d.n_region = 0; d.pad = 0; d.region_first = 0;
+        d.seed_base = n_seeds; d.hoff_base = n_seeds + r; d.hit_base = n_hits; d.scratch = scratch;
+        n_seeds += rd.seed_out; n_hits += H;
+        scratch += make_layout((int)H, rd.seed_out, para->ske_max).total;
+    }
+    b->n_seeds = n_seeds; b->n_hits = n_hits;
+    // packed copies: seeds / hits of the reads in batch order, plus the derived index arrays
+    std::vector<int32_t> h_sid(n_seeds), h_mn(n_seeds), h_hoff(n_seeds + n_reads), h_hseed(n_hits), h_rflat(n_hits);
+    std::vector<lb2_sdp_hit> h_hits(n_hits);
+    for (int64_t r = 0; r < n_reads; ++r) {
+        const lb2_sdp_read& rd = reads[r];
+        const DRead& d = b->reads[r];
+        int32_t* hoff = h_hoff.data() + d.hoff_base;
+        int acc = 0;
+        for (int i = 0; i < rd.seed_out; ++i) {
+            h_sid[d.seed_base + i] = seed_id[rd.seed_first + i];
+            const int m = map_n[rd.seed_first + i];
+            h_mn[d.seed_base + i] = m;
+            hoff[i] = acc;
+            for (int j = 0; j < m; ++j) h_hseed[d.hit_base + acc + j] = i;
+            acc += m;
+        }
+        hoff[rd.seed_out] = acc;
+        if (acc) memcpy(h_hits.data() + d.hit_base, hits + rd.hit_first, (size_t)acc * sizeof(lb2_sdp_hit));
+        // scan order of the predecessor loops (src/lamsa_dp_con.c:713-714): seeds descending, hits ascending
+        int q = 0;
+        for (int i = rd.seed_out - 1; i >= 0; --i)
+            for (int p = hoff[i]; p < hoff[i + 1]; ++p) h_rflat[d.hit_base + q++] = p;
+    }
+    b->order.resize(n_reads);
+    std::iota(b->order.begin(), b->order.end(), 0);
+    std::stable_sort(b->order.begin(), b->order.end(), [&](int32_t x, int32_t y) { return b->reads[x].n_hits > b->reads[y].n_hits; });
+
+    cudaStream_t st = ctx_stream(ctx);
+#define UP(dst, src, cnt) do { auto e1_ = (dst).reserve(cnt); if (e1_ != cudaSuccess) { lb2_sdp_destroy(b); return set_error("lb2_sdp_create: cudaMalloc: %s", cudaGetErrorString(e1_)); } \
+        if ((cnt) > 0) { auto e2_ = cudaMemcpyAsync((dst).p, (src), (size_t)(cnt) * sizeof(*(dst).p), cudaMemcpyHostToDevice, st); \
+        if (e2_ != cudaSuccess) { lb2_sdp_destroy(b); return set_error("lb2_sdp_create: H2D: %s", cudaGetErrorString(e2_)); } \
+        b->h2d += (int64_t)(cnt) * sizeof(*(dst).p); } } while (0)
+    UP(b->d_reads, b->reads.data(), n_reads);
+    UP(b->d_order, b->order.data(), n_reads);
+    UP(b->d_seed_id, h_sid.data(), n_seeds);
+    UP(b->d_map_n, h_mn.data(), n_seeds);
+    UP(b->d_hoff, h_hoff.data(), n_seeds + n_reads);
+    UP(b->d_hseed, h_hseed.data(), n_hits);
+    UP(b->d_rflat, h_rflat.data(), n_hits);
+    UP(b->d_hits, h_hits.data(), n_hits);
+#undef UP
+    cudaError_t e = b->d_scratch.reserve((size_t)scratch);
+    if (e == cudaSuccess) e = b->d_outs.reserve(n_reads);
+    if (e == cudaSuccess) e = b->d_counter.reserve(1);
+    if (e == cudaSuccess) e = b->d_off.reserve(n_reads + 1);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // the host vectors above go out of scope
+    if (e != cudaSuccess) { lb2_sdp_destroy(b); return set_error("lb2_sdp_create: %s", cudaGetErrorString(e)); }
+    *out = b;
+    return 0;
+}
+
+static const char* err_name(int e) {
+    switch (e) {
+        case ERR_PATH: return "inconsistent chain (the reference aborts with a BUG message here)";
+        case ERR_STREAM: return "skeleton stream overflow";
+        case ERR_EDGE: return "unknown edge kind on a skeleton";
+        case ERR_STACK: return "path list overflow";
+        default: return "unknown";
+    }
+}
+
+// launch one stage and bring the ordered streams back
+static int run_stage(lb2_sdp_batch* b, int stage, const int32_t** stream, const int64_t** off, float* kernel_ms) {
+    cudaStream_t st = ctx_stream(b->ctx);
+    CU(cudaSetDevice(ctx_device(b->ctx)));
+    const int n = (int)b->n;
+    b->off.assign(n + 1, 0);
+    b->stream.clear();
+    b->pairs = 0;
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (n > 0) {
+        CU(cudaMemsetAsync(b->d_counter.p, 0, sizeof(unsigned int), st));
+        const int warps_per_block = 4;
+        const int grid = std::max(1, std::min((n + warps_per_block - 1) / warps_per_block, ctx_sm_count(b->ctx) * 8));
+        CU(cudaEventRecord(b->ev0, st));
+        sdp_kernel<<<grid, warps_per_block * 32, 0, st>>>(stage, b->para, n, b->d_reads.p, b->d_order.p, b->d_seed_id.p, b->d_map_n.p,
+                                                          b->d_hoff.p, b->d_hits.p, b->d_hseed.p, b->d_rflat.p, b->d_regions.p,
+                                                          b->d_pts.p, b->d_scratch.p, b->d_outs.p, b->d_counter.p);
+        CU(cudaGetLastError());
+        sdp_scan_kernel<<<1, 1024, 0, st>>>(b->d_outs.p, n, b->d_off.p);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(b->ev1, st));
+        b->outs.resize(n);
+        std::vector<long long> h_off(n + 1);
+        CU(cudaMemcpyAsync(b->outs.data(), b->d_outs.p, (size_t)n * sizeof(DOut), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_off.data(), b->d_off.p, (size_t)(n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        b->d2h += (int64_t)n * sizeof(DOut) + (int64_t)(n + 1) * 8;
+        for (int r = 0; r < n; ++r) {
+            if (b->outs[r].err) return set_error("lb2_sdp: read %d: %s", r, err_name(b->outs[r].err));
+            b->pairs += b->outs[r].pairs;
+        }
+        const long long total = h_off[n];
+        CU(b->d_dense.reserve((size_t)total));
+        b->stream.resize((size_t)total);
+        if (total > 0) {
+            const int threads = 256, blocks = (int)(((long long)n * 32 + threads - 1) / threads);
+            sdp_gather_kernel<<<blocks, threads, 0, st>>>(b->d_reads.p, b->d_outs.p, n, b->para.ske_max, b->d_scratch.p, b->d_off.p, b->d_dense.p);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(b->stream.data(), b->d_dense.p, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            b->d2h += total * 4;
+        }
+        for (int r = 0; r <= n; ++r) b->off[r] = h_off[r];
+        if (kernel_ms) CU(cudaEventElapsedTime(kernel_ms, b->ev0, b->ev1));
+    }
+    if (stream) *stream = b->stream.data();
+    if (off) *off = b->off.data();
+    return 0;
+}
+
+extern "C" int lb2_sdp_run_bcc(lb2_sdp_batch* b, const int32_t** stream, const int64_t** off, float* kernel_ms) {
+    if (!b) return set_error("lb2_sdp_run_bcc: batch is NULL");
+    return run_stage(b, 1, stream, off, kernel_ms);
+}
+
+// The read intervals stage 1 left unaligned, each with the reference ends of its flanks:
+// get_remain_reg (src/lamsa_aln.c:548-572) with aln_sort_reg (:477, stable like glibc's merge sort)
+// and aln_merg_reg (:498-519, neighbours closer than bwt_seed_len are merged).
+namespace {
+struct Aligned { int beg, end; std::vector<DPoint> rb, re; };
+void remaining_regions(const lb2_sdp_para& P, int read_len, const lb2_sdp_reg* regs, int n_reg,
+                       std::vector<DRegion>& out, std::vector<DPoint>& pts) {
+    const int lo = P.seed_len, hi = read_len;
+    auto emit = [&](int beg, int end, const std::vector<DPoint>* b, const std::vector<DPoint>* e) {
+        DRegion r; r.beg = beg; r.end = end; r.bn = b ? (int)b->size() : 0; r.en = e ? (int)e->size() : 0;
+        r.pt_first = (int64_t)pts.size();
+        if (b) pts.insert(pts.end(), b->begin(), b->end());
+        if (e) pts.insert(pts.end(), e->begin(), e->end());
+        out.push_back(r);
+    };
+    if (n_reg == 0) {
+        if (lo < read_len && read_len <= hi) emit(1, read_len, nullptr, nullptr);
+        return;
+    }
+    std::vector<int> ord(n_reg);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return regs[a].beg < regs[b].beg; });
+    std::vector<Aligned> A;
+    for (int k = 0; k < n_reg; ++k) {
+        const lb2_sdp_reg& g = regs[ord[k]];
+        const DPoint pb{g.ref_beg, g.chr, 0}, pe{g.ref_end, g.chr, 0};
+        if (!A.empty() && g.beg - A.back().end - 1 < P.bwt_seed_len) {
+            Aligned& c = A.back();
+            if (g.end > c.end) c.end = g.end;
+            c.rb.push_back(pb); c.re.push_back(pe);
+        } else {
+            A.push_back(Aligned{g.beg, g.end, {pb}, {pe}});
+        }
+    }
+    const int n = (int)A.size();
+    if (A[0].beg > lo && A[0].beg - 1 <= hi) emit(1, A[0].beg - 1, nullptr, &A[0].rb);
+    for (int i = 1; i < n; ++i)
+        if (A[i].beg - A[i - 1].end > lo && A[i].beg - 1 - A[i - 1].end <= hi)
+            emit(A[i - 1].end + 1, A[i].beg - 1, &A[i - 1].re, &A[i].rb);
+    if (read_len - A[n - 1].end > lo && read_len - A[n - 1].end <= hi) emit(A[n - 1].end + 1, read_len, &A[n - 1].re, nullptr);
+}
+}  // namespace
+
+extern "C" int lb2_sdp_run_remain(lb2_sdp_batch* b, const lb2_sdp_read* reads, const lb2_sdp_reg* regs,
+                                  const int32_t** stream, const int64_t** off, float* kernel_ms) {
+    if (!b || (b->n > 0 && !reads)) return set_error("lb2_sdp_run_remain: bad arguments");
+    CU(cudaSetDevice(ctx_device(b->ctx)));
+    std::vector<DRegion> h_regions; std::vector<DPoint> h_pts;
+    for (int64_t r = 0; r < b->n; ++r) {
+        if (reads[r].n_reg < 0 || (reads[r].n_reg > 0 && !regs)) return set_error("lb2_sdp_run_remain: read %lld: bad region list", (long long)r);
+        DRead& d = b->reads[r];
+        d.region_first = (int64_t)h_regions.size();
+        remaining_regions(b->para, d.read_len, regs ? regs + reads[r].reg_first : nullptr, reads[r].n_reg, h_regions, h_pts);
+        d.n_region = (int32_t)(h_regions.size() - d.region_first);
+    }
+    cudaStream_t st = ctx_stream(b->ctx);
+    CU(b->d_regions.reserve(h_regions.size()));
+    CU(b->d_pts.reserve(h_pts.size()));
+    if (!h_regions.empty()) CU(cudaMemcpyAsync(b->d_regions.p, h_regions.data(), h_regions.size() * sizeof(DRegion), cudaMemcpyHostToDevice, st));
+    if (!h_pts.empty()) CU(cudaMemcpyAsync(b->d_pts.p, h_pts.data(), h_pts.size() * sizeof(DPoint), cudaMemcpyHostToDevice, st));
+    if (b->n > 0) CU(cudaMemcpyAsync(b->d_reads.p, b->reads.data(), (size_t)b->n * sizeof(DRead), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    b->h2d += (int64_t)(h_regions.size() * sizeof(DRegion) + h_pts.size() * sizeof(DPoint) + (size_t)b->n * sizeof(DRead));
+    return run_stage(b, 2, stream, off, kernel_ms);
+}
+
+extern "C" int lb2_sdp_stats(const lb2_sdp_batch* b, int64_t* pairs, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    if (!b) return set_error("lb2_sdp_stats: batch is NULL");
+    if (pairs) *pairs = b->pairs;
+    if (h2d_bytes) *h2d_bytes = b->h2d;
+    if (d2h_bytes) *d2h_bytes = b->d2h;
+    return 0;
+}
