@@ -124,6 +124,47 @@ void sw_mid_fix(cigar32_t **cigar, int *cigar_n, int *cigar_m,
                 const uint8_t *target, int tlen, int lte, int rte,
                 lamsa_aln_para *AP, int m, const int8_t *mat);
 
+/* ---- sparse-DP chaining entry points (src/lamsa_dp_con.h:8-15).  The struct types are the
+ * reference's (src/lamsa_aln.h:230-245 map_msg, :368-377 lamsa_aln_per_para, :282-295 aln_reg,
+ * :300-303 line_node, :345-366 frag_dp_node; src/frag_check.h:13-43 frag_msg; kseq_t); this
+ * header only names them -- lamsa_b200/csrc/ref_abi.h holds the layout-identical restatements,
+ * checked against the reference headers by tests/test_abi.py.  The scratch arguments (line,
+ * line_start_len, line_rank, ..., f_node) are accepted and not touched: no caller reads them
+ * (only lamsa_dp_con.c itself did); f_node serves as the per-worker key that ties a read's
+ * frag_line_remain call to its frag_line_BCC call.  *f_msg is malloc'd exactly like
+ * frag_init_msg/frag_set_msg would (src/frag_check.c:19-93) and freed by frag_check's
+ * frag_free_msg (:959); frag_line_remain sorts and merges a_reg in place like get_remain_reg
+ * does (src/lamsa_aln.c:558). */
+#ifndef LAMSA_B200_NO_PARA_TYPE   /* with the reference's headers in scope its own prototypes stand */
+struct lb2_ref_map_msg; struct lb2_ref_frag_msg; struct lb2_ref_per_para; struct lb2_ref_aln_reg;
+struct lb2_ref_line_node; struct lb2_ref_kseq;
+/* replaces src/lamsa_dp_con.h:12 / src/lamsa_dp_con.c:1305 */
+int frag_line_BCC(struct lb2_ref_map_msg *m_msg, struct lb2_ref_frag_msg **f_msg,
+                  struct lb2_ref_per_para *APP, lamsa_aln_para *AP, struct lb2_ref_kseq *seqs,
+                  struct lb2_ref_line_node *line, int *line_start_len, int *line_rank, int *line_select_rank,
+                  void ***f_node, struct lb2_ref_line_node *_line, int line_n_max);
+/* replaces src/lamsa_dp_con.h:8 / src/lamsa_dp_con.c:1252 */
+int frag_line_remain(struct lb2_ref_aln_reg *a_reg, struct lb2_ref_map_msg *m_msg, struct lb2_ref_frag_msg **f_msg,
+                     struct lb2_ref_per_para *APP, lamsa_aln_para *AP, struct lb2_ref_kseq *seqs,
+                     struct lb2_ref_line_node *line, int *line_start_len, int *line_rank, int *line_select_rank,
+                     void ***f_node, struct lb2_ref_line_node *_line, int *_line_start_len, int *_line_rank,
+                     int line_n_max);
+/* helpers of the same translation units that other reference files bind by `extern`
+ * (src/bwt_aln.c:103-105,148; src/lamsa_aln.c:609) or through src/lamsa_heap.h:5-17.
+ * node_score = src/lamsa_aln.h:325-332 (restated in ref_abi.h as lb2_ref_node_score). */
+struct lb2_ref_node_score;
+struct lb2_ref_node_score *node_init_score(int n);                          /* src/lamsa_dp_con.c:29  */
+void  node_free_score(struct lb2_ref_node_score *ns);                       /* src/lamsa_dp_con.c:39  */
+float cover_rate(int s1, int e1, int s2, int e2);                           /* src/lamsa_dp_con.c:61  */
+void  build_node_max_heap(struct lb2_ref_node_score *ns);                   /* src/lamsa_heap.c:35    */
+void  build_node_min_heap(struct lb2_ref_node_score *ns);                   /* src/lamsa_heap.c:171   */
+void  build_node_minpos_heap(struct lb2_ref_node_score *ns);                /* src/lamsa_heap.c:121   */
+#endif
+/* heap_add_node (src/lamsa_dp_con.c:44), node_pop (src/lamsa_heap.c:5), node_heap_extract_max (:42),
+ * node_heap_extract_minpos (:128) and node_heap_update_min (:191) pass or return a line_node BY VALUE
+ * ({int x, y}, 8 bytes, in one integer register on x86-64); they are exported with that calling
+ * convention and declared in ref_abi.h. */
+
 /* ------------------------------------------------------ 2. batch interface -- */
 
 typedef struct lb2_ctx lb2_ctx;        /* one per (process, GPU) */
@@ -265,6 +306,9 @@ typedef struct lb2_sdp_batch lb2_sdp_batch;
 int  lb2_sdp_create(lb2_ctx *ctx, const lb2_sdp_para *para, int64_t n_reads, const lb2_sdp_read *reads,
                     const int32_t *seed_id, const int32_t *map_n, const lb2_sdp_hit *hits,
                     lb2_sdp_batch **out);
+/* Re-load an existing batch object with another set of reads (device buffers are grow-only). */
+int  lb2_sdp_reset(lb2_sdp_batch *b, const lb2_sdp_para *para, int64_t n_reads, const lb2_sdp_read *reads,
+                   const int32_t *seed_id, const int32_t *map_n, const lb2_sdp_hit *hits);
 /* Stage 1 (frag_line_BCC) for every read.  stream/offsets are owned by the batch and stay
  * valid until the next stage call or lb2_sdp_destroy; read r owns words
  * [off[r], off[r+1]). */
@@ -278,6 +322,10 @@ int  lb2_sdp_run_remain(lb2_sdp_batch *b, const lb2_sdp_read *reads, const lb2_s
  * (the unit of work of the chaining) */
 int  lb2_sdp_stats(const lb2_sdp_batch *b, int64_t *pairs, int64_t *h2d_bytes, int64_t *d2h_bytes);
 void lb2_sdp_destroy(lb2_sdp_batch *b);
+/* field offsets / sizes of the library's restatements of the reference structs (ref_abi.h), in the
+ * order of oracle/sdp_ref_shim.c:ref_sdp_offsets / ref_sdp_sizes; returns the count */
+int  lb2_ref_abi_offsets(int *out);
+int  lb2_ref_abi_sizes(int *out);
 
 #ifdef __cplusplus
 }

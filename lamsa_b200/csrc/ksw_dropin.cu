@@ -35,6 +35,10 @@ lb2_ctx* default_ctx() {
     return g_ctx;
 }
 
+}  // namespace
+namespace lb2 { lb2_ctx* dropin_ctx() { return default_ctx(); } }   // shared with sdp_dropin.cu
+namespace {
+
 // ---- combining submitter ----------------------------------------------------
 // The reference calls ksw_* from n_thread pthreads, one read per thread
 // (src/lamsa_aln.c:838-842), each call blocking.  Instead of one launch per

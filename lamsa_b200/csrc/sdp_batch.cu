@@ -61,30 +61,50 @@ extern "C" void lb2_sdp_destroy(lb2_sdp_batch* b) {
     delete b;
 }
 
+extern "C" int lb2_sdp_reset(lb2_sdp_batch* b, const lb2_sdp_para* para, int64_t n_reads, const lb2_sdp_read* reads,
+                             const int32_t* seed_id, const int32_t* map_n, const lb2_sdp_hit* hits);
+
 extern "C" int lb2_sdp_create(lb2_ctx* ctx, const lb2_sdp_para* para, int64_t n_reads, const lb2_sdp_read* reads,
                               const int32_t* seed_id, const int32_t* map_n, const lb2_sdp_hit* hits,
                               lb2_sdp_batch** out) {
-    if (!ctx || !para || !out || n_reads < 0 || (n_reads > 0 && (!reads || !seed_id || !map_n)))
-        return set_error("lb2_sdp_create: bad arguments");
-    if (para->seed_step <= 0 || para->ske_max < 1 || para->per_aln_m < 1)
-        return set_error("lb2_sdp_create: seed_step, ske_max and per_aln_m must be positive");
-    if (n_reads > INT32_MAX) return set_error("lb2_sdp_create: too many reads");
+    if (!ctx || !out) return set_error("lb2_sdp_create: bad arguments");
     CU(cudaSetDevice(ctx_device(ctx)));
     lb2_sdp_batch* b = new lb2_sdp_batch();
-    b->ctx = ctx; b->para = *para; b->n = n_reads;
+    b->ctx = ctx;
+    cudaError_t e = cudaEventCreate(&b->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+    if (e != cudaSuccess) { lb2_sdp_destroy(b); return set_error("lb2_sdp_create: %s", cudaGetErrorString(e)); }
+    if (lb2_sdp_reset(b, para, n_reads, reads, seed_id, map_n, hits)) { lb2_sdp_destroy(b); return 1; }
+    *out = b;
+    return 0;
+}
+
+// (re)load a batch object with a new set of reads; device buffers are grow-only, so a producer
+// that keeps one object per worker (the drop-in entry points do) stops allocating after warm-up
+extern "C" int lb2_sdp_reset(lb2_sdp_batch* b, const lb2_sdp_para* para, int64_t n_reads, const lb2_sdp_read* reads,
+                             const int32_t* seed_id, const int32_t* map_n, const lb2_sdp_hit* hits) {
+    if (!b || !para || n_reads < 0 || (n_reads > 0 && (!reads || !seed_id || !map_n)))
+        return set_error("lb2_sdp_reset: bad arguments");
+    if (para->seed_step <= 0 || para->ske_max < 1 || para->per_aln_m < 1)
+        return set_error("lb2_sdp_reset: seed_step, ske_max and per_aln_m must be positive");
+    if (n_reads > INT32_MAX) return set_error("lb2_sdp_reset: too many reads");
+    lb2_ctx* ctx = b->ctx;
+    CU(cudaSetDevice(ctx_device(ctx)));
+    b->para = *para; b->n = n_reads;
+    b->h2d = b->d2h = b->pairs = 0;
     b->reads.resize(n_reads);
     int64_t n_seeds = 0, n_hits = 0, scratch = 0;
     for (int64_t r = 0; r < n_reads; ++r) {
         const lb2_sdp_read& rd = reads[r];
-        if (rd.seed_out < 0 || rd.seed_first < 0 || rd.hit_first < 0) { delete b; return set_error("lb2_sdp_create: read %lld: negative field", (long long)r); }
+        if (rd.seed_out < 0 || rd.seed_first < 0 || rd.hit_first < 0) return set_error("lb2_sdp_reset: read %lld: negative field", (long long)r);
         int64_t H = 0;
         for (int i = 0; i < rd.seed_out; ++i) {
             const int m = map_n[rd.seed_first + i];
-            if (m < 0 || m > para->per_aln_m) { delete b; return set_error("lb2_sdp_create: read %lld seed %d: map_n %d outside [0, per_aln_m]", (long long)r, i, m); }
-            if (i > 0 && seed_id[rd.seed_first + i] <= seed_id[rd.seed_first + i - 1]) { delete b; return set_error("lb2_sdp_create: read %lld: seed ids must increase", (long long)r); }
+            if (m < 0 || m > para->per_aln_m) return set_error("lb2_sdp_reset: read %lld seed %d: map_n %d outside [0, per_aln_m]", (long long)r, i, m);
+            if (i > 0 && seed_id[rd.seed_first + i] <= seed_id[rd.seed_first + i - 1]) return set_error("lb2_sdp_reset: read %lld: seed ids must increase", (long long)r);
             H += m;
         }
-        if (H > (1 << 26)) { delete b; return set_error("lb2_sdp_create: read %lld has %lld hits", (long long)r, (long long)H); }
+        if (H > (1 << 26)) return set_error("lb2_sdp_reset: read %lld has %lld hits", (long long)r, (long long)H);
         DRead& d = b->reads[r];
         d.seed_out = rd.seed_out; d.seed_all = rd.seed_all; d.read_len = rd.read_len; d.n_hits = (int32_t)H;
         d.n_region = 0; d.pad = 0; d.region_first = 0;
@@ -121,9 +141,9 @@ extern "C" int lb2_sdp_create(lb2_ctx* ctx, const lb2_sdp_para* para, int64_t n_
     std::stable_sort(b->order.begin(), b->order.end(), [&](int32_t x, int32_t y) { return b->reads[x].n_hits > b->reads[y].n_hits; });
 
     cudaStream_t st = ctx_stream(ctx);
-#define UP(dst, src, cnt) do { auto e1_ = (dst).reserve(cnt); if (e1_ != cudaSuccess) { lb2_sdp_destroy(b); return set_error("lb2_sdp_create: cudaMalloc: %s", cudaGetErrorString(e1_)); } \
+#define UP(dst, src, cnt) do { auto e1_ = (dst).reserve(cnt); if (e1_ != cudaSuccess) return set_error("lb2_sdp_reset: cudaMalloc: %s", cudaGetErrorString(e1_)); \
         if ((cnt) > 0) { auto e2_ = cudaMemcpyAsync((dst).p, (src), (size_t)(cnt) * sizeof(*(dst).p), cudaMemcpyHostToDevice, st); \
-        if (e2_ != cudaSuccess) { lb2_sdp_destroy(b); return set_error("lb2_sdp_create: H2D: %s", cudaGetErrorString(e2_)); } \
+        if (e2_ != cudaSuccess) return set_error("lb2_sdp_reset: H2D: %s", cudaGetErrorString(e2_)); \
         b->h2d += (int64_t)(cnt) * sizeof(*(dst).p); } } while (0)
     UP(b->d_reads, b->reads.data(), n_reads);
     UP(b->d_order, b->order.data(), n_reads);
@@ -138,11 +158,8 @@ extern "C" int lb2_sdp_create(lb2_ctx* ctx, const lb2_sdp_para* para, int64_t n_
     if (e == cudaSuccess) e = b->d_outs.reserve(n_reads);
     if (e == cudaSuccess) e = b->d_counter.reserve(1);
     if (e == cudaSuccess) e = b->d_off.reserve(n_reads + 1);
-    if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
-    if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // the host vectors above go out of scope
-    if (e != cudaSuccess) { lb2_sdp_destroy(b); return set_error("lb2_sdp_create: %s", cudaGetErrorString(e)); }
-    *out = b;
+    if (e != cudaSuccess) return set_error("lb2_sdp_reset: %s", cudaGetErrorString(e));
     return 0;
 }
 

@@ -69,6 +69,33 @@ int ref_sdp_sizes(int *o)
 	return n;
 }
 
+/* field offsets the product's layout restatements (lamsa_b200/csrc/ref_abi.h) are checked against;
+ * order must match tests/test_abi.py:SDP_OFFSETS */
+#include <stddef.h>
+int ref_sdp_offsets(int *o)
+{
+	int n = 0;
+	o[n++] = offsetof(map_t, nstrand); o[n++] = offsetof(map_t, nchr); o[n++] = offsetof(map_t, offset);
+	o[n++] = offsetof(map_t, NM); o[n++] = offsetof(map_t, len_dif);
+	o[n++] = offsetof(map_msg, map); o[n++] = offsetof(map_msg, map_n); o[n++] = offsetof(map_msg, seed_id);
+	o[n++] = offsetof(frag_msg, frag_max); o[n++] = offsetof(frag_msg, frag_num); o[n++] = offsetof(frag_msg, fa_msg);
+	o[n++] = offsetof(frag_msg, line_score); o[n++] = offsetof(frag_msg, frag_left_bound); o[n++] = offsetof(frag_msg, frag_right_bound);
+	o[n++] = offsetof(frag_aln_msg, chr); o[n++] = offsetof(frag_aln_msg, strand); o[n++] = offsetof(frag_aln_msg, cigar);
+	o[n++] = offsetof(frag_aln_msg, cigar_len); o[n++] = offsetof(frag_aln_msg, cigar_max); o[n++] = offsetof(frag_aln_msg, flag);
+	o[n++] = offsetof(frag_aln_msg, seed_max); o[n++] = offsetof(frag_aln_msg, seed_num); o[n++] = offsetof(frag_aln_msg, seed_i);
+	o[n++] = offsetof(frag_aln_msg, seed_aln_i);
+	o[n++] = offsetof(lamsa_aln_per_para, seed_all); o[n++] = offsetof(lamsa_aln_per_para, seed_out);
+	o[n++] = offsetof(aln_reg, reg); o[n++] = offsetof(aln_reg, reg_n); o[n++] = offsetof(aln_reg, reg_m); o[n++] = offsetof(aln_reg, read_len);
+	o[n++] = offsetof(reg_t, ref_beg); o[n++] = offsetof(reg_t, ref_end); o[n++] = offsetof(reg_t, beg_n); o[n++] = offsetof(reg_t, end_n);
+	o[n++] = offsetof(reg_t, beg_m); o[n++] = offsetof(reg_t, end_m); o[n++] = offsetof(reg_t, beg); o[n++] = offsetof(reg_t, end);
+	o[n++] = offsetof(reg_b, is_rev); o[n++] = offsetof(reg_b, chr); o[n++] = offsetof(reg_b, ref_pos);
+	o[n++] = offsetof(kseq_t, seq) + offsetof(kstring_t, l);
+	o[n++] = offsetof(node_score, node); o[n++] = offsetof(node_score, score); o[n++] = offsetof(node_score, NM);
+	o[n++] = offsetof(node_score, min_score_thd); o[n++] = offsetof(node_score, max_n); o[n++] = offsetof(node_score, node_n);
+	o[n++] = CIGAR_LEN_M; o[n++] = UNCOVERED;
+	return n;
+}
+
 /* stages: bit 0 = frag_line_BCC, bit 1 = frag_line_remain (needs bit 0).  off1/off2 have
  * n_reads+1 entries.  Returns 0, or -1 when an output buffer was too small. */
 int ref_sdp_run_batch(const lb2_sdp_para *P, int64_t n_reads, const lb2_sdp_read *reads,

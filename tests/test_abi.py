@@ -35,10 +35,101 @@ def lib():
 def test_exports_every_declared_symbol(lib):
     hdr = open(os.path.join(ROOT, "include", "lamsa_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b((?:ksw|lb2|sw)_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b((?:ksw|lb2|sw|frag_line|node|build_node)_[A-Za-z0-9_]+|cover_rate)\s*\(", hdr))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    for name in declared:
+    abi = open(os.path.join(ROOT, "lamsa_b200", "csrc", "ref_abi.h")).read()
+    declared_abi = set(re.findall(r"\b((?:heap|node)_[a-z_]+)\s*\(lb2_ref_node_score", abi))
+    assert declared_abi == set(_lib.EXPORTS_REF_ABI), declared_abi ^ set(_lib.EXPORTS_REF_ABI)
+    for name in declared | declared_abi:
         assert hasattr(lib, name), name
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "liblamsa_ref.so")),
+                    reason="oracle/_ref/liblamsa_ref.so not built (needs /root/reference)")
+def test_sdp_struct_layouts_match_reference_headers(lib):
+    """map_t/map_msg/frag_msg/frag_aln_msg/aln_reg/reg_t/kseq_t/node_score as restated in ref_abi.h"""
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "liblamsa_ref.so"))
+    a, b = (C.c_int * 64)(), (C.c_int * 64)()
+    na, nb = ref.ref_sdp_offsets(a), lib.lb2_ref_abi_offsets(b)
+    assert na == nb and list(a[:na]) == list(b[:nb])
+    na, nb = ref.ref_sdp_sizes(a), lib.lb2_ref_abi_sizes(b)
+    assert na == nb and list(a[:na]) == list(b[:nb])
+
+
+def test_sdp_struct_layouts_match_survey_appendix_b(lib):
+    b = (C.c_int * 64)()
+    n = lib.lb2_ref_abi_sizes(b)
+    # map_t, map_msg, frag_dp_node, frag_msg, frag_aln_msg, lamsa_aln_per_para, aln_reg, reg_t (SURVEY.md appendix B)
+    assert list(b[:8]) == [1064, 32, 80, 32, 88, 12, 24, 40] and b[10] == 8 and b[11] == 40
+
+
+class LineNode(C.Structure):
+    _fields_ = [("x", C.c_int), ("y", C.c_int)]
+
+
+class NodeScore(C.Structure):
+    _fields_ = [("node", C.POINTER(LineNode)), ("score", C.POINTER(C.c_int)), ("NM", C.POINTER(C.c_int)),
+                ("min_score_thd", C.c_int), ("max_n", C.c_int), ("node_n", C.c_int)]
+
+
+def _bind_heap(l):
+    l.node_init_score.restype = C.POINTER(NodeScore); l.node_init_score.argtypes = [C.c_int]
+    l.node_free_score.argtypes = [C.POINTER(NodeScore)]; l.node_free_score.restype = None
+    l.heap_add_node.argtypes = [C.POINTER(NodeScore), LineNode, C.c_int, C.c_int]
+    l.node_heap_update_min.argtypes = [C.POINTER(NodeScore), LineNode, C.c_int, C.c_int]
+    l.node_pop.argtypes = [C.POINTER(NodeScore), C.POINTER(C.c_int), C.POINTER(C.c_int)]; l.node_pop.restype = LineNode
+    l.node_heap_extract_max.argtypes = [C.POINTER(NodeScore), C.POINTER(C.c_int)]; l.node_heap_extract_max.restype = LineNode
+    l.node_heap_extract_minpos.argtypes = [C.POINTER(NodeScore)]; l.node_heap_extract_minpos.restype = LineNode
+    for f in ("build_node_max_heap", "build_node_min_heap", "build_node_minpos_heap"):
+        getattr(l, f).argtypes = [C.POINTER(NodeScore)]; getattr(l, f).restype = None
+    l.cover_rate.argtypes = [C.c_int] * 4; l.cover_rate.restype = C.c_float
+    return l
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "liblamsa_ref.so")),
+                    reason="oracle/_ref/liblamsa_ref.so not built (needs /root/reference)")
+def test_node_score_helpers_match_reference(lib):
+    """the host-side node_score helpers other reference files bind (bwt_aln.c, lamsa_aln.c): same
+    array contents and return values as src/lamsa_heap.c / src/lamsa_dp_con.c:29-67 on random traces"""
+    ref = _bind_heap(C.CDLL(os.path.join(ROOT, "oracle", "_ref", "liblamsa_ref.so")))
+    mine = _bind_heap(lib)
+    rng = np.random.default_rng(5)
+
+    def state(ns):
+        n = ns.contents.node_n
+        return [(ns.contents.node[i].x, ns.contents.node[i].y, ns.contents.score[i], ns.contents.NM[i]) for i in range(n)]
+
+    for trial in range(200):
+        cap = int(rng.integers(1, 12))
+        a, b = ref.node_init_score(cap), mine.node_init_score(cap)
+        ops = rng.integers(0, 100, size=int(rng.integers(1, 40)))
+        for op in ops:
+            x, y, sc, nm = (int(v) for v in rng.integers(0, 8, size=4))
+            if op < 60:
+                ra, rb = ref.heap_add_node(a, LineNode(x, y), sc, nm), mine.heap_add_node(b, LineNode(x, y), sc, nm)
+            elif op < 70:
+                s1, s2, n1, n2 = C.c_int(-9), C.c_int(-9), C.c_int(-9), C.c_int(-9)
+                pa, pb = ref.node_pop(a, C.byref(s1), C.byref(n1)), mine.node_pop(b, C.byref(s2), C.byref(n2))
+                ra, rb = (pa.x, pa.y, s1.value, n1.value), (pb.x, pb.y, s2.value, n2.value)
+            elif op < 80:
+                ref.build_node_minpos_heap(a); mine.build_node_minpos_heap(b)
+                pa, pb = ref.node_heap_extract_minpos(a), mine.node_heap_extract_minpos(b)
+                ra, rb = (pa.x, pa.y), (pb.x, pb.y)
+            elif op < 90:
+                ref.build_node_max_heap(a); mine.build_node_max_heap(b)
+                s1, s2 = C.c_int(-9), C.c_int(-9)
+                pa, pb = ref.node_heap_extract_max(a, C.byref(s1)), mine.node_heap_extract_max(b, C.byref(s2))
+                ra, rb = (pa.x, pa.y, s1.value), (pb.x, pb.y, s2.value)
+            else:
+                ref.build_node_min_heap(a); mine.build_node_min_heap(b)
+                ra = rb = 0
+            assert ra == rb, (trial, op)
+            assert state(a) == state(b), (trial, op)
+        ref.node_free_score(a); mine.node_free_score(b)
+    for _ in range(200):
+        v = [int(t) for t in rng.integers(1, 300, size=4)]
+        s1, e1, s2, e2 = v[0], v[0] + v[1], v[2], v[2] + v[3]
+        assert ref.cover_rate(s1, e1, s2, e2) == mine.cover_rate(s1, e1, s2, e2)
 
 
 def test_para_layout_matches_survey_offsets():

@@ -14,7 +14,10 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EXE = os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin")
+# lamsa_dropin: only ksw.c replaced; lamsa_dropin_sdp: ksw.c, lamsa_dp_con.c and lamsa_heap.c replaced
+# (banded DP and sparse-DP chaining both on the GPU; `make -C oracle dropin_sdp`)
+EXES = {"dp": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin"),
+        "dp+sdp": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin_sdp")}
 FIXTURES = [
     ("small", os.path.join(ROOT, "tests", "golden", "sam_small")),
     ("c1", os.path.join(ROOT, "oracle", "_ref", "sam_c1")),
@@ -36,9 +39,11 @@ def stage(src, dst):
 
 @pytest.mark.parametrize("name,src", FIXTURES, ids=[f[0] for f in FIXTURES])
 @pytest.mark.parametrize("threads", [1, 4])
-def test_dropin_sam_identical_to_reference(tmp_path, name, src, threads):
+@pytest.mark.parametrize("link", ["dp", "dp+sdp"])
+def test_dropin_sam_identical_to_reference(tmp_path, name, src, threads, link):
+    EXE = EXES[link]
     if not os.path.exists(EXE):
-        pytest.skip("oracle/_ref/lamsa_dropin not built (needs the reference tree at build time)")
+        pytest.skip(f"{EXE} not built (needs the reference tree at build time)")
     if not os.path.isdir(src):
         pytest.skip(f"fixture {src} not present")
     if threads != 1 and name not in ("small", "c1"):
