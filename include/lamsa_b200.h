@@ -26,6 +26,7 @@
 
 #include <stdint.h>
 #include <stdio.h>
+#include <pthread.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -318,10 +319,31 @@ int  lb2_sdp_run_bcc(lb2_sdp_batch *b, const int32_t **stream, const int64_t **o
  * only in those two fields). */
 int  lb2_sdp_run_remain(lb2_sdp_batch *b, const lb2_sdp_read *reads, const lb2_sdp_reg *regs,
                         const int32_t **stream, const int64_t **off, float *kernel_ms);
+/* The state stage 2 needs from stage 1 is one flag per hit: "on a stage-1 skeleton" (TRACKED_FLAG,
+ * src/lamsa_dp_con.c:948).  get_tracked after lb2_sdp_run_bcc copies the flags out (one byte per hit,
+ * hits in batch order); set_tracked loads them into a batch object that never ran stage 1, so that
+ * a producer may regroup reads between the stages (reads reach stage 2 at different times). */
+int  lb2_sdp_get_tracked(lb2_sdp_batch *b, uint8_t *flags);
+int  lb2_sdp_set_tracked(lb2_sdp_batch *b, const uint8_t *flags);
 /* predecessor pairs evaluated by get_fseed_dis inside frag_dp_update in the last stage
  * (the unit of work of the chaining) */
 int  lb2_sdp_stats(const lb2_sdp_batch *b, int64_t *pairs, int64_t *h2d_bytes, int64_t *d2h_bytes);
 void lb2_sdp_destroy(lb2_sdp_batch *b);
+/* ------------------------------------------------------ 4. batch producer -- */
+/*
+ * The reference aligns reads on `-t N` pthreads, one read per thread at a time, every DP call
+ * blocking (src/lamsa_aln.c:825-891, :1151-1162).  These two functions have the signatures of
+ * pthread_create / pthread_join and run the same worker functions as user-level fibers on
+ * LB2_HOST_THREADS OS threads instead: a worker that reaches one of the drop-in entry points above
+ * parks its request and yields, and when all workers of an OS thread are parked their requests go
+ * to the GPU as ONE batch (fiber_sched.cu).  `lamsa aln -t 4096` then keeps 4096 reads in flight and
+ * a launch carries thousands of DP tasks.  Redirecting the two pthread names when compiling the
+ * reference's lamsa_aln.c is the whole integration (oracle/fiber_wrapper.c).
+ * Workers start when the first of them is joined; results and output order are unchanged.
+ */
+int lb2_worker_spawn(pthread_t *id, const pthread_attr_t *attr, void *(*fn)(void *), void *arg);
+int lb2_worker_join(pthread_t id, void **ret);
+
 /* field offsets / sizes of the library's restatements of the reference structs (ref_abi.h), in the
  * order of oracle/sdp_ref_shim.c:ref_sdp_offsets / ref_sdp_sizes; returns the count */
 int  lb2_ref_abi_offsets(int *out);

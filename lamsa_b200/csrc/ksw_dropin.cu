@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/lamsa_b200.h"
+#include "dropin_internal.h"
 
 namespace {
 
@@ -47,12 +48,7 @@ namespace {
 // the results back.  With `lamsa aln -t 128` a launch carries up to 128 tasks
 // without touching the reference's sources.  A lone caller (or -t 1) degrades to
 // a batch of one after an empty gather window, so nothing can deadlock.
-struct Pending {
-    lb2_task task;
-    lb2_result* res;
-    cigar32_t** cig;        // NULL: caller wants no CIGAR
-    bool done;
-};
+using Pending = lb2::DpRequest;
 
 std::mutex q_mu;
 std::condition_variable q_cv;
@@ -97,6 +93,7 @@ void submit_batch(std::vector<Pending*>& batch) {
 // run one task; returns malloc'd CIGAR (or NULL) through *cig
 void run_one(const lb2_task& t, lb2_result* r, cigar32_t** cig) {
     Pending me{t, r, cig, false};
+    if (lb2::fiber_active()) { lb2::fiber_wait_dp(&me); return; }      // worker fiber: park and let the scheduler batch it
     std::unique_lock<std::mutex> lk(q_mu);
     q_wait.push_back(&me);
     for (;;) {
@@ -127,6 +124,10 @@ void run_one(const lb2_task& t, lb2_result* r, cigar32_t** cig) {
     lk.unlock();
     q_cv.notify_all();
 }
+
+}  // namespace
+namespace lb2 { void dropin_submit_dp(std::vector<DpRequest*>& batch) { submit_batch(batch); } }
+namespace {
 
 // ---- CIGAR list helpers (src/frag_check.h:139-188) -------------------------
 void list_add(cigar32_t** c, int* n, int* cap, cigar32_t op) {            // _push_cigar0

@@ -44,7 +44,7 @@ struct lb2_sdp_batch {
     DevBuf<DRead> d_reads; DevBuf<int32_t> d_order, d_seed_id, d_map_n, d_hoff, d_hseed, d_rflat;
     DevBuf<lb2_sdp_hit> d_hits;
     DevBuf<int> d_scratch, d_dense; DevBuf<DOut> d_outs; DevBuf<unsigned int> d_counter; DevBuf<long long> d_off;
-    DevBuf<DRegion> d_regions; DevBuf<DPoint> d_pts;
+    DevBuf<DRegion> d_regions; DevBuf<DPoint> d_pts; DevBuf<uint8_t> d_flags;
     std::vector<int32_t> stream; std::vector<int64_t> off; std::vector<DOut> outs;
     int64_t pairs = 0, h2d = 0, d2h = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -55,7 +55,7 @@ extern "C" void lb2_sdp_destroy(lb2_sdp_batch* b) {
     cudaSetDevice(ctx_device(b->ctx));
     b->d_reads.release(); b->d_order.release(); b->d_seed_id.release(); b->d_map_n.release(); b->d_hoff.release();
     b->d_hseed.release(); b->d_rflat.release(); b->d_hits.release(); b->d_scratch.release(); b->d_dense.release();
-    b->d_outs.release(); b->d_counter.release(); b->d_off.release(); b->d_regions.release(); b->d_pts.release();
+    b->d_outs.release(); b->d_counter.release(); b->d_off.release(); b->d_regions.release(); b->d_pts.release(); b->d_flags.release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     delete b;
@@ -301,3 +301,20 @@ extern "C" int lb2_sdp_stats(const lb2_sdp_batch* b, int64_t* pairs, int64_t* h2
     if (d2h_bytes) *d2h_bytes = b->d2h;
     return 0;
 }
+
+static int tracked_io(lb2_sdp_batch* b, uint8_t* flags, int set) {
+    if (!b || (b->n_hits > 0 && !flags)) return set_error("lb2_sdp_%s_tracked: bad arguments", set ? "set" : "get");
+    if (b->n == 0 || b->n_hits == 0) return 0;
+    CU(cudaSetDevice(ctx_device(b->ctx)));
+    cudaStream_t st = ctx_stream(b->ctx);
+    CU(b->d_flags.reserve((size_t)b->n_hits));
+    if (set) { CU(cudaMemcpyAsync(b->d_flags.p, flags, (size_t)b->n_hits, cudaMemcpyHostToDevice, st)); b->h2d += b->n_hits; }
+    const int threads = 256, blocks = (int)((b->n * 32 + threads - 1) / threads);
+    sdp_tracked_kernel<<<blocks, threads, 0, st>>>(b->d_reads.p, (int)b->n, b->para.ske_max, b->d_scratch.p, b->d_flags.p, set);
+    CU(cudaGetLastError());
+    if (!set) { CU(cudaMemcpyAsync(flags, b->d_flags.p, (size_t)b->n_hits, cudaMemcpyDeviceToHost, st)); b->d2h += b->n_hits; }
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+extern "C" int lb2_sdp_get_tracked(lb2_sdp_batch* b, uint8_t* flags) { return tracked_io(b, flags, 0); }
+extern "C" int lb2_sdp_set_tracked(lb2_sdp_batch* b, const uint8_t* flags) { return tracked_io(b, const_cast<uint8_t*>(flags), 1); }

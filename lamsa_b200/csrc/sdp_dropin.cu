@@ -15,8 +15,7 @@
 
 #include "../../include/lamsa_b200.h"
 #include "ref_abi.h"
-
-namespace lb2 { lb2_ctx* dropin_ctx(); }       // ksw_dropin.cu: the process-wide context of the drop-in symbols
+#include "dropin_internal.h"
 
 namespace {
 
@@ -97,13 +96,21 @@ void para_from(const lamsa_aln_para* AP, lb2_sdp_para* P) {
     for (int i = 0; i < 10; ++i) P->frag_score_table[i] = AP->frag_score_table[i];
 }
 
-// one resident batch object per worker, keyed by the worker's f_node scratch pointer
-std::mutex g_mu;
-std::unordered_map<void*, lb2_sdp_batch*> g_live;
-
 [[noreturn]] void die(const char* what) {
     fprintf(stderr, "[lamsa_b200] %s: %s\n", what, lb2_last_error());
     exit(1);
+}
+
+// Per-worker state, keyed by the worker's f_node scratch pointer (one per reference worker,
+// src/lamsa_aln.c:971): the read's flattened hits and the tracked flags stage 1 leaves for stage 2.
+std::mutex g_mu;
+std::unordered_map<void*, lb2::SdpWorkerState*> g_workers;
+lb2::SdpWorkerState* worker_state(void* key, bool create) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_workers.find(key);
+    if (it != g_workers.end()) return it->second;
+    if (!create) return nullptr;
+    return g_workers[key] = new lb2::SdpWorkerState();
 }
 
 // aln_sort_reg + aln_merg_reg on the caller's struct (src/lamsa_aln.c:476-519), the in-place side
@@ -137,50 +144,89 @@ void sort_merge_regions(lb2_ref_aln_reg* a, int thd) {
     a->reg_n = cur + 1;
 }
 
+// serve a request: parked for the fiber scheduler's next batch, or run alone right now
+void serve(lb2::SdpRequest* r) {
+    if (lb2::fiber_active()) { lb2::fiber_wait_sdp(r); return; }
+    std::vector<lb2::SdpRequest*> one{r};
+    lb2::dropin_submit_sdp(one);
+}
+
 }  // namespace
+
+// All requests of `batch` (same stage, same parameters) as ONE GPU batch.  Each OS thread keeps one
+// grow-only batch object, so steady state allocates nothing.
+void lb2::dropin_submit_sdp(std::vector<lb2::SdpRequest*>& batch) {
+    if (batch.empty()) return;
+    thread_local lb2_sdp_batch* tl_batch = nullptr;
+    const int stage = batch[0]->stage;
+    const int64_t n = (int64_t)batch.size();
+    std::vector<lb2_sdp_read> reads((size_t)n);
+    std::vector<int32_t> sid, mn; std::vector<lb2_sdp_hit> hits; std::vector<lb2_sdp_reg> regs; std::vector<uint8_t> flags;
+    for (int64_t i = 0; i < n; ++i) {
+        const lb2::SdpRequest* q = batch[(size_t)i];
+        const lb2::SdpWorkerState* ws = q->ws;
+        if (q->stage != stage || memcmp(&ws->para, &batch[0]->ws->para, sizeof(lb2_sdp_para))) {
+            fprintf(stderr, "[lamsa_b200] chaining requests of one batch must share stage and parameters\n"); exit(1);
+        }
+        lb2_sdp_read rd = ws->read;
+        rd.seed_first = (int64_t)sid.size(); rd.hit_first = (int64_t)hits.size();
+        rd.reg_first = (int64_t)regs.size(); rd.n_reg = (int32_t)q->regs.size();
+        reads[(size_t)i] = rd;
+        sid.insert(sid.end(), ws->seed_id.begin(), ws->seed_id.end());
+        mn.insert(mn.end(), ws->map_n.begin(), ws->map_n.end());
+        hits.insert(hits.end(), ws->hits.begin(), ws->hits.end());
+        regs.insert(regs.end(), q->regs.begin(), q->regs.end());
+        if (stage == 2) flags.insert(flags.end(), ws->tracked.begin(), ws->tracked.end());
+    }
+    const lb2_sdp_para* P = &batch[0]->ws->para;
+    if (!tl_batch) { if (lb2_sdp_create(lb2::dropin_ctx(), P, n, reads.data(), sid.data(), mn.data(), hits.data(), &tl_batch)) die("chaining batch"); }
+    else if (lb2_sdp_reset(tl_batch, P, n, reads.data(), sid.data(), mn.data(), hits.data())) die("chaining batch");
+    const int32_t* w; const int64_t* off;
+    if (stage == 1) {
+        if (lb2_sdp_run_bcc(tl_batch, &w, &off, nullptr)) die("frag_line_BCC");
+        flags.resize(hits.size());
+        if (lb2_sdp_get_tracked(tl_batch, flags.data())) die("frag_line_BCC");
+    } else {
+        if (lb2_sdp_set_tracked(tl_batch, flags.data())) die("frag_line_remain");
+        if (lb2_sdp_run_remain(tl_batch, reads.data(), regs.data(), &w, &off, nullptr)) die("frag_line_remain");
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        lb2::SdpRequest* q = batch[(size_t)i];
+        q->stream.assign(w + off[i], w + off[i + 1]);
+        if (stage == 1) {
+            const size_t h0 = (size_t)reads[(size_t)i].hit_first, hn = q->ws->hits.size();
+            q->ws->tracked.assign(flags.begin() + h0, flags.begin() + h0 + hn);
+        }
+    }
+}
 
 extern "C" int frag_line_BCC(lb2_ref_map_msg* m_msg, lb2_ref_frag_msg** f_msg, lb2_ref_per_para* APP, lamsa_aln_para* AP,
                              lb2_ref_kseq* seqs, lb2_ref_line_node*, int*, int*, int*, void*** f_node, lb2_ref_line_node*, int) {
-    lb2_sdp_para P; para_from(AP, &P);
+    lb2::SdpWorkerState* ws = worker_state((void*)f_node, true);
+    para_from(AP, &ws->para);
     const int S = APP->seed_out;
-    std::vector<int32_t> sid(S), mn(S);
-    std::vector<lb2_sdp_hit> hits;
+    ws->seed_id.resize(S); ws->map_n.resize(S); ws->hits.clear(); ws->tracked.clear();
     for (int i = 0; i < S; ++i) {
-        sid[i] = m_msg[i].seed_id; mn[i] = m_msg[i].map_n;
+        ws->seed_id[i] = m_msg[i].seed_id; ws->map_n[i] = m_msg[i].map_n;
         for (int j = 0; j < m_msg[i].map_n; ++j) {
             const lb2_ref_map& m = m_msg[i].map[j];
-            hits.push_back(lb2_sdp_hit{m.offset, m.nchr, m.NM, m.len_dif, m.nstrand});
+            ws->hits.push_back(lb2_sdp_hit{m.offset, m.nchr, m.NM, m.len_dif, m.nstrand});
         }
     }
-    lb2_sdp_read rd{S, APP->seed_all, (int32_t)seqs->seq.l, 0, 0, 0, 0};
-    lb2_sdp_batch* b = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        auto it = g_live.find((void*)f_node);
-        if (it != g_live.end()) b = it->second;
-    }
-    if (b) { if (lb2_sdp_reset(b, &P, 1, &rd, sid.data(), mn.data(), hits.data())) die("frag_line_BCC"); }
-    else {
-        if (lb2_sdp_create(lb2::dropin_ctx(), &P, 1, &rd, sid.data(), mn.data(), hits.data(), &b)) die("frag_line_BCC");
-        std::lock_guard<std::mutex> lk(g_mu);
-        g_live[(void*)f_node] = b;
-    }
-    const int32_t* w; const int64_t* off;
-    if (lb2_sdp_run_bcc(b, &w, &off, nullptr)) die("frag_line_BCC");
-    return stream_to_fmsg(w + off[0], off[1] - off[0], m_msg, APP->seed_all, f_msg);
+    ws->read = lb2_sdp_read{S, APP->seed_all, (int32_t)seqs->seq.l, 0, 0, 0, 0};
+    lb2::SdpRequest req{1, ws, {}, {}};
+    serve(&req);
+    return stream_to_fmsg(req.stream.data(), (int64_t)req.stream.size(), m_msg, APP->seed_all, f_msg);
 }
 
 extern "C" int frag_line_remain(lb2_ref_aln_reg* a_reg, lb2_ref_map_msg* m_msg, lb2_ref_frag_msg** f_msg, lb2_ref_per_para* APP,
                                 lamsa_aln_para* AP, lb2_ref_kseq* seqs, lb2_ref_line_node*, int*, int*, int*, void*** f_node,
                                 lb2_ref_line_node*, int*, int*, int) {
-    lb2_sdp_batch* b = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        auto it = g_live.find((void*)f_node);
-        if (it != g_live.end()) b = it->second;
+    lb2::SdpWorkerState* ws = worker_state((void*)f_node, false);
+    if (!ws || ws->tracked.size() != ws->hits.size()) {
+        fprintf(stderr, "[lamsa_b200] frag_line_remain without a preceding frag_line_BCC on this worker\n"); exit(1);
     }
-    if (!b) { fprintf(stderr, "[lamsa_b200] frag_line_remain without a preceding frag_line_BCC on this worker\n"); exit(1); }
-    std::vector<lb2_sdp_reg> regs;
+    lb2::SdpRequest req{2, ws, {}, {}};
     for (int k = 0; k < a_reg->reg_n; ++k) {
         const lb2_ref_reg& g = a_reg->reg[k];
         // get_reg (src/lamsa_aln.c:608-616) hands one begin and one end point per record; records that a
@@ -189,14 +235,12 @@ extern "C" int frag_line_remain(lb2_ref_aln_reg* a_reg, lb2_ref_map_msg* m_msg, 
         for (int t = 0; t < n; ++t) {
             const lb2_ref_reg_b& pb = g.ref_beg[std::min(t, g.beg_n - 1)];
             const lb2_ref_reg_b& pe = g.ref_end[std::min(t, g.end_n - 1)];
-            regs.push_back(lb2_sdp_reg{g.beg, g.end, pb.chr, pb.is_rev, pb.ref_pos, pe.ref_pos});
+            req.regs.push_back(lb2_sdp_reg{g.beg, g.end, pb.chr, pb.is_rev, pb.ref_pos, pe.ref_pos});
         }
     }
     if (a_reg->reg_n > 0) sort_merge_regions(a_reg, AP->bwt_seed_len);
-    lb2_sdp_read rd{APP->seed_out, APP->seed_all, (int32_t)seqs->seq.l, (int32_t)regs.size(), 0, 0, 0};
-    const int32_t* w; const int64_t* off;
-    if (lb2_sdp_run_remain(b, &rd, regs.data(), &w, &off, nullptr)) die("frag_line_remain");
-    return stream_to_fmsg(w + off[0], off[1] - off[0], m_msg, APP->seed_all, f_msg);
+    serve(&req);
+    return stream_to_fmsg(req.stream.data(), (int64_t)req.stream.size(), m_msg, APP->seed_all, f_msg);
 }
 
 // ---- node_score helpers (src/lamsa_dp_con.c:29-67, src/lamsa_heap.c) ------------------------

@@ -928,5 +928,21 @@ __global__ void sdp_gather_kernel(const DRead* __restrict__ reads, const DOut* _
     for (int i = lane; i < nw; i += 32) dst[i] = src[i];
 }
 
+// The only node state stage 2 needs from stage 1 is "this hit is on a stage-1 skeleton"
+// (dp_flag == TRACKED_FLAG, tested at src/lamsa_dp_con.c:948).  get: flags[h] = tracked; set: dp_flag of
+// EVERY hit := tracked ? TRACKED : 0, which lets stage 2 run on a batch object that never ran stage 1.
+__global__ void sdp_tracked_kernel(const DRead* __restrict__ reads, int n, int K, int* scratch, uint8_t* flags, int set) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const DRead rd = reads[w];
+    const Layout lay = make_layout(rd.n_hits, rd.seed_out, K);
+    int* dp = scratch + rd.scratch + lay.node + (int64_t)A_DP_FLAG * rd.n_hits;
+    uint8_t* f = flags + rd.hit_base;
+    for (int p = lane; p < rd.n_hits; p += 32) {
+        if (set) dp[p] = f[p] ? ST_TRACKED : 0;
+        else f[p] = dp[p] == ST_TRACKED;
+    }
+}
+
 }  // namespace sdp
 }  // namespace lb2

@@ -17,7 +17,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # lamsa_dropin: only ksw.c replaced; lamsa_dropin_sdp: ksw.c, lamsa_dp_con.c and lamsa_heap.c replaced
 # (banded DP and sparse-DP chaining both on the GPU; `make -C oracle dropin_sdp`)
 EXES = {"dp": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin"),
-        "dp+sdp": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin_sdp")}
+        "dp+sdp": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin_sdp"),
+        # + the worker pool run as fibers whose DP / chaining calls are batched (`make -C oracle dropin_fiber`)
+        "fiber": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin_fiber")}
 FIXTURES = [
     ("small", os.path.join(ROOT, "tests", "golden", "sam_small")),
     ("c1", os.path.join(ROOT, "oracle", "_ref", "sam_c1")),
@@ -39,14 +41,16 @@ def stage(src, dst):
 
 @pytest.mark.parametrize("name,src", FIXTURES, ids=[f[0] for f in FIXTURES])
 @pytest.mark.parametrize("threads", [1, 4])
-@pytest.mark.parametrize("link", ["dp", "dp+sdp"])
+@pytest.mark.parametrize("link", ["dp", "dp+sdp", "fiber"])
 def test_dropin_sam_identical_to_reference(tmp_path, name, src, threads, link):
     EXE = EXES[link]
     if not os.path.exists(EXE):
         pytest.skip(f"{EXE} not built (needs the reference tree at build time)")
     if not os.path.isdir(src):
         pytest.skip(f"fixture {src} not present")
-    if threads != 1 and name not in ("small", "c1"):
+    if link == "fiber":
+        threads = 2048 if threads != 1 else 37        # workers = fibers; 37: fewer workers than reads, odd count
+    elif threads != 1 and name not in ("small", "c1"):
         pytest.skip("multi-thread run only on two fixtures")
     work = str(tmp_path / name)
     stage(src, work)

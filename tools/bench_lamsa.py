@@ -50,17 +50,24 @@ def main():
     ap.add_argument("fixture", nargs="?", default=os.path.join(ROOT, "oracle", "_ref", "sam_c1"))
     ap.add_argument("--threads", default="1,16,128")
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--workers", default="1024,4096", help="worker (fiber) counts of the batch-producer build")
+    ap.add_argument("--skip-dropin", action="store_true", help="skip the thread-per-read drop-in build")
     a = ap.parse_args()
     work = os.path.join(tempfile.mkdtemp(prefix="lamsa_bench_"), "w")
     stage(a.fixture, work)
     opts = open(os.path.join(work, "cmd.txt")).read().split()
     bases = sum(len(l.strip()) for l in open(os.path.join(work, "reads.fa")) if not l.startswith(">"))
     exp = list(open(os.path.join(work, "expected.sam")))
-    for exe, label in ((REFBIN, "reference (CPU ksw.c)"), (DROPIN, "drop-in (liblamsa_b200, B200)")):
+    FIBER = os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin_fiber")
+    impls = [(REFBIN, "reference (CPU ksw.c)", a.threads)]
+    if not a.skip_dropin:
+        impls.append((DROPIN, "drop-in, one blocking call per DP task (liblamsa_b200, B200)", a.threads))
+    impls.append((FIBER, "batch producer: workers as fibers, DP + chaining batched (liblamsa_b200, B200)", a.workers))
+    for exe, label, counts in impls:
         if not os.path.exists(exe):
             print(json.dumps({"impl": label, "unavailable": exe}))
             continue
-        for t in [int(x) for x in a.threads.split(",")]:
+        for t in [int(x) for x in counts.split(",")]:
             best = None
             for _ in range(a.repeat):
                 dt, sam = run(exe, work, t, opts)
