@@ -343,6 +343,9 @@ void lb2_sdp_destroy(lb2_sdp_batch *b);
  */
 int lb2_worker_spawn(pthread_t *id, const pthread_attr_t *attr, void *(*fn)(void *), void *arg);
 int lb2_worker_join(pthread_t id, void **ret);
+/* Opens the process-wide context of the drop-in entry points from a helper thread, so that CUDA
+ * start-up overlaps the caller's own start-up (index loading).  Optional. */
+void lb2_dropin_warmup(void);
 
 /* field offsets / sizes of the library's restatements of the reference structs (ref_abi.h), in the
  * order of oracle/sdp_ref_shim.c:ref_sdp_offsets / ref_sdp_sizes; returns the count */

@@ -38,6 +38,8 @@ lb2_ctx* default_ctx() {
 
 }  // namespace
 namespace lb2 { lb2_ctx* dropin_ctx() { return default_ctx(); } }   // shared with sdp_dropin.cu
+// open the drop-in context from a helper thread (CUDA start-up overlaps the caller's own start-up)
+extern "C" void lb2_dropin_warmup(void) { std::thread([] { default_ctx(); }).detach(); }
 namespace {
 
 // ---- combining submitter ----------------------------------------------------

@@ -11,6 +11,7 @@
  * No reference code is copied.
  */
 #include <pthread.h>            /* before the renames, so the system declarations stay as they are */
+#include <sys/mman.h>
 #include <stdio.h>
 #include <stdint.h>
 #include <zlib.h>
@@ -18,9 +19,60 @@
 #include "lamsa_aln.h"          /* sets the include guard and CHUNK_READ_N 128 */
 #undef CHUNK_READ_N
 #ifndef LAMSA_CHUNK
-#define LAMSA_CHUNK 16384
+#define LAMSA_CHUNK 4096
 #endif
 #define CHUNK_READ_N LAMSA_CHUNK
+
+/* Worker set-up cost.  aux_dp_init (src/lamsa_aln.c:969-982) gives every worker a frag_dp_node table
+ * with one calloc(4, sizeof(line_node)) per node (fnode_alloc, :729-740): 10^4-10^5 small allocations
+ * per worker, which the chaining entry points of liblamsa_b200 never look at (their state is on the
+ * GPU).  With thousands of workers that is seconds of malloc.  Inside this translation unit those
+ * son arrays come from a bump arena instead; free() of an arena pointer is a no-op.  Everything else
+ * allocates as before. */
+#include <stdlib.h>
+#include <string.h>
+static char *lb2w_arena_lo = 0, *lb2w_arena_hi = 0, *lb2w_arena_cur = 0;
+static pthread_mutex_t lb2w_mu = PTHREAD_MUTEX_INITIALIZER;
+static void *lb2w_calloc(size_t n, size_t sz)
+{
+	if (n == 4 && sz == sizeof(line_node)) {
+		pthread_mutex_lock(&lb2w_mu);
+		if (!lb2w_arena_lo) {
+			size_t cap = (size_t)1 << 33;     /* 8 GiB of address space, touched on demand */
+			lb2w_arena_lo = lb2w_arena_cur = (char*)mmap(0, cap, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+			if (lb2w_arena_lo == MAP_FAILED) { lb2w_arena_lo = lb2w_arena_cur = 0; pthread_mutex_unlock(&lb2w_mu); return calloc(n, sz); }
+			lb2w_arena_hi = lb2w_arena_lo + cap;
+		}
+		void *p = 0;
+		if (lb2w_arena_cur + n * sz <= lb2w_arena_hi) { p = lb2w_arena_cur; lb2w_arena_cur += n * sz; }
+		pthread_mutex_unlock(&lb2w_mu);
+		if (p) return p;                      /* fresh anonymous pages are zero */
+	}
+	return calloc(n, sz);
+}
+static void lb2w_free(void *p)
+{
+	if ((char*)p >= lb2w_arena_lo && (char*)p < lb2w_arena_hi) return;
+	free(p);
+}
+static void *lb2w_realloc(void *p, size_t sz)
+{
+	if ((char*)p >= lb2w_arena_lo && (char*)p < lb2w_arena_hi) {      /* grow out of the arena */
+		void *q = malloc(sz);
+		if (q) memcpy(q, p, sz < 4 * sizeof(line_node) ? sz : 4 * sizeof(line_node));
+		return q;
+	}
+	return realloc(p, sz);
+}
+#define calloc lb2w_calloc
+#define free lb2w_free
+#define realloc lb2w_realloc
+
+/* CUDA start-up (about 1.5 s) overlaps index loading: the context is opened from a helper thread as
+ * soon as the program starts. */
+extern void lb2_dropin_warmup(void);
+__attribute__((constructor)) static void lb2w_warm(void) { lb2_dropin_warmup(); }
+
 extern int lb2_worker_spawn(pthread_t *id, const pthread_attr_t *attr, void *(*fn)(void *), void *arg);
 extern int lb2_worker_join(pthread_t id, void **ret);
 #define pthread_create lb2_worker_spawn

@@ -133,3 +133,6 @@ if __name__ == "__main__":
     make(os.path.join(out, "sam_c3s"), 1_000_000, 100, 10000, 0.15, seed=3, aln_opts=("-T", "pacbio"),
          mix=(1.5, 9, 4.5))                                                                      # configs[2], reduced
     make(os.path.join(out, "sam_c4s"), 1_000_000, 100, 20000, 0.05, seed=4, sv=True)             # configs[3], reduced
+    if "--big" in sys.argv:       # throughput fixtures for tools/bench_lamsa.py (minutes of GEM time; xz the members to keep gpurun pushes small)
+        make(os.path.join(out, "sam_c1x8"), 4_000_000, 8000, 5000, 0.05, seed=11)
+        make(os.path.join(out, "sam_c3m"), 4_000_000, 2000, 10000, 0.15, seed=13, aln_opts=("-T", "pacbio"), mix=(1.5, 9, 4.5))

@@ -42,6 +42,8 @@ def run(exe, work, threads, opts):
     dt = time.perf_counter() - t0
     if r.returncode:
         raise RuntimeError(r.stderr.decode()[-1000:])
+    if os.environ.get("LB2_FIBER_STATS"):
+        sys.stderr.write("".join(l + "\n" for l in r.stderr.decode().splitlines() if "[lamsa_b200]" in l))
     return dt, [l for l in open(out) if not l.startswith("@PG")]
 
 
