@@ -8,7 +8,10 @@
 
 namespace lb2 {
 
-lb2_ctx* dropin_ctx();                       // the process-wide context of the drop-in symbols
+lb2_ctx* dropin_ctx();                       // the context of the drop-in symbols: the calling thread's own
+                                             // (dropin_use_thread_ctx) or else the process-wide one
+// give the calling OS thread a context of its own (scheduler thread `index`: GPU index mod #GPUs)
+void dropin_use_thread_ctx(int index);
 
 // one blocked banded-DP call (ksw_dropin.cu)
 struct DpRequest {

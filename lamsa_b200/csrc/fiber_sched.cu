@@ -43,7 +43,9 @@ struct Sched {                       // one per OS thread
     std::vector<Fiber*> fibers, runnable;
     std::vector<lb2::DpRequest*> dp_wait;   std::vector<Fiber*> dp_owner;
     std::vector<lb2::SdpRequest*> sdp_wait; std::vector<Fiber*> sdp_owner;
-    int64_t switches = 0;
+    int index = 0;
+    int64_t switches = 0, flushes = 0, dp_tasks = 0, sdp_reqs = 0, max_dp = 0;
+    double gpu_s = 0;
 };
 thread_local Sched* tl_sched = nullptr;
 
@@ -76,54 +78,23 @@ void yield_to_scheduler() {
     swapcontext(&f->ctx, &s->main);
 }
 
-// ---- global rounds -----------------------------------------------------------------------
-// The OS threads advance in rounds: each runs its workers until all of them are parked, then
-// deposits the parked requests in a shared pool.  The last thread to arrive submits the WHOLE pool
-// (at most one chaining batch per stage and one DP batch) and releases the others.  Host work is
-// parallel across threads, while a launch carries the requests of every worker of the process.
-struct Round {
-    std::mutex mu;
-    std::condition_variable cv;
-    int active = 0, waiting = 0;
-    uint64_t generation = 0;
-    std::vector<lb2::DpRequest*> dp;
-    std::vector<lb2::SdpRequest*> sdp;
-    int64_t flushes = 0, dp_tasks = 0, sdp_reqs = 0, max_dp = 0;
-    double gpu_s = 0;
-};
-Round* g_round = nullptr;
-
-// caller holds r->mu and is the last to arrive: submit everything, then open the next round
-void submit_round(Round* r, std::unique_lock<std::mutex>& lk) {
-    std::vector<lb2::DpRequest*> dp; std::vector<lb2::SdpRequest*> sdp;
-    dp.swap(r->dp); sdp.swap(r->sdp);
-    lk.unlock();
+// ---- rounds ------------------------------------------------------------------------------
+// Each OS thread owns a context (its own streams and scratch; thread k of a process that sees D
+// GPUs uses GPU k mod D) and advances in rounds of its own: it runs its workers until all of them
+// are parked, submits everything parked as one chaining batch per stage and one DP batch, and
+// resumes them.  Threads do not wait for each other, so a long DP task only delays the workers
+// that share its batch, and the batches of different threads overlap on the GPU(s).
+void flush(Sched* s) {
     const auto t0 = std::chrono::steady_clock::now();
     for (int stage = 1; stage <= 2; ++stage) {
         std::vector<lb2::SdpRequest*> grp;
-        for (lb2::SdpRequest* q : sdp) if (q->stage == stage) grp.push_back(q);
+        for (lb2::SdpRequest* q : s->sdp_wait) if (q->stage == stage) grp.push_back(q);
         if (!grp.empty()) lb2::dropin_submit_sdp(grp);
     }
-    if (!dp.empty()) lb2::dropin_submit_dp(dp);
-    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    lk.lock();
-    r->gpu_s += dt; ++r->flushes; r->dp_tasks += (int64_t)dp.size(); r->sdp_reqs += (int64_t)sdp.size();
-    r->max_dp = std::max<int64_t>(r->max_dp, (int64_t)dp.size());
-    r->waiting = 0;
-    ++r->generation;
-    r->cv.notify_all();
-}
-
-// this thread's workers are all parked: join the round
-void flush(Sched* s) {
-    Round* r = g_round;
-    std::unique_lock<std::mutex> lk(r->mu);
-    r->dp.insert(r->dp.end(), s->dp_wait.begin(), s->dp_wait.end());
-    r->sdp.insert(r->sdp.end(), s->sdp_wait.begin(), s->sdp_wait.end());
-    ++r->waiting;
-    if (r->waiting == r->active) submit_round(r, lk);
-    else { const uint64_t g = r->generation; r->cv.wait(lk, [&] { return r->generation != g; }); }
-    lk.unlock();
+    if (!s->dp_wait.empty()) lb2::dropin_submit_dp(s->dp_wait);
+    s->gpu_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    ++s->flushes; s->dp_tasks += (int64_t)s->dp_wait.size(); s->sdp_reqs += (int64_t)s->sdp_wait.size();
+    s->max_dp = std::max<int64_t>(s->max_dp, (int64_t)s->dp_wait.size());
     for (Fiber* f : s->sdp_owner) s->runnable.push_back(f);
     for (Fiber* f : s->dp_owner) s->runnable.push_back(f);
     s->dp_wait.clear(); s->dp_owner.clear(); s->sdp_wait.clear(); s->sdp_owner.clear();
@@ -131,6 +102,7 @@ void flush(Sched* s) {
 
 void run_scheduler(Sched* s) {
     tl_sched = s;
+    lb2::dropin_use_thread_ctx(s->index);
     size_t live = s->fibers.size();
     for (Fiber* f : s->fibers) s->runnable.push_back(f);
     while (live > 0) {
@@ -147,12 +119,6 @@ void run_scheduler(Sched* s) {
         }
         flush(s);
     }
-    {   // leave the rounds; if everybody else is already waiting, their round is complete now
-        Round* r = g_round;
-        std::unique_lock<std::mutex> lk(r->mu);
-        --r->active;
-        if (r->active > 0 && r->waiting == r->active) submit_round(r, lk);
-    }
     tl_sched = nullptr;
 }
 
@@ -163,23 +129,19 @@ void run_all(std::vector<Fiber*>& fibers) {
     for (size_t i = 0; i < fibers.size(); ++i) scheds[i % K].fibers.push_back(fibers[i]);
     // spawn order = worker order; the scheduler pops from the back, so reverse to start worker 0 first
     for (Sched& s : scheds) std::reverse(s.fibers.begin(), s.fibers.end());
-    Round round;
-    round.active = K;
-    g_round = &round;
+    for (int k = 0; k < K; ++k) scheds[(size_t)k].index = k;
     std::vector<std::thread> th;
     for (int k = 1; k < K; ++k) th.emplace_back(run_scheduler, &scheds[(size_t)k]);
     run_scheduler(&scheds[0]);
     for (auto& t : th) t.join();
-    g_round = nullptr;
     if (g_verbose()) {
-        int64_t sw = 0;
-        for (Sched& s : scheds) sw += s.switches;
+        int64_t sw = 0, fl = 0, dp = 0, sd = 0, mx = 0; double g = 0;
+        for (Sched& s : scheds) { sw += s.switches; fl += s.flushes; dp += s.dp_tasks; sd += s.sdp_reqs; mx = std::max(mx, s.max_dp); g = std::max(g, s.gpu_s); }
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        fprintf(stderr, "[lamsa_b200] %zu workers on %d threads: %.3f s, %lld rounds, %lld DP tasks (%.0f per round, max %lld), "
-                        "%lld chaining requests, %lld switches, %.3f s inside GPU submissions\n",
-                fibers.size(), K, wall, (long long)round.flushes, (long long)round.dp_tasks,
-                round.flushes ? (double)round.dp_tasks / round.flushes : 0.0, (long long)round.max_dp,
-                (long long)round.sdp_reqs, (long long)sw, round.gpu_s);
+        fprintf(stderr, "[lamsa_b200] %zu workers on %d threads: %.3f s, %lld rounds (%.0f per thread), %lld DP tasks (%.0f per launch, max %lld), "
+                        "%lld chaining requests, %lld switches, %.3f s inside GPU submissions (slowest thread)\n",
+                fibers.size(), K, wall, (long long)fl, (double)fl / K, (long long)dp, fl ? (double)dp / fl : 0.0, (long long)mx,
+                (long long)sd, (long long)sw, g);
     }
     for (Fiber* f : fibers) delete f;
     fibers.clear();

@@ -23,7 +23,10 @@ namespace {
 std::mutex g_mu;
 lb2_ctx* g_ctx = nullptr;
 
+thread_local lb2_ctx* tl_ctx = nullptr;        // scheduler threads of the batch producer own a context each
+
 lb2_ctx* default_ctx() {
+    if (tl_ctx) return tl_ctx;
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_ctx) {
         int dev = 0;
@@ -38,6 +41,27 @@ lb2_ctx* default_ctx() {
 
 }  // namespace
 namespace lb2 { lb2_ctx* dropin_ctx() { return default_ctx(); } }   // shared with sdp_dropin.cu
+void lb2::dropin_use_thread_ctx(int index) {
+    if (tl_ctx) return;
+    // scheduler threads are re-created per read chunk; their contexts are kept by index
+    static std::mutex mu;
+    static std::vector<lb2_ctx*> table;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((size_t)index < table.size() && table[(size_t)index]) { tl_ctx = table[(size_t)index]; return; }
+    if ((size_t)index >= table.size()) table.resize((size_t)index + 1, nullptr);
+    int ndev = 1;
+    if (const char* e = getenv("LB2_DEVICES")) ndev = atoi(e) > 0 ? atoi(e) : 1;
+    int base = 0;
+    if (const char* e = getenv("LB2_DEVICE")) base = atoi(e);
+    if (lb2_ctx_create(base + index % ndev, &tl_ctx)) {
+        fprintf(stderr, "[lamsa_b200] cannot open GPU %d: %s\n", base + index % ndev, lb2_last_error());
+        exit(1);
+    }
+    uint64_t lim = (uint64_t)4 << 30;              // direction scratch per launch wave of this thread
+    if (const char* e = getenv("LB2_THREAD_SCRATCH_MB")) lim = (uint64_t)atol(e) << 20;
+    lb2_ctx_set_scratch_limit(tl_ctx, lim);
+    table[(size_t)index] = tl_ctx;
+}
 // open the drop-in context from a helper thread (CUDA start-up overlaps the caller's own start-up)
 extern "C" void lb2_dropin_warmup(void) { std::thread([] { default_ctx(); }).detach(); }
 namespace {
@@ -71,7 +95,8 @@ void submit_batch(std::vector<Pending*>& batch) {
     for (int64_t i = 0; i < n; ++i) tasks[(size_t)i] = batch[(size_t)i]->task;
     cigar32_t* pool = nullptr; int64_t pn = 0;
     int rc;
-    {
+    if (tl_ctx) rc = lb2_dp_run(c, n, tasks.data(), results.data(), &pool, &pn);      // this thread's own context
+    else {
         std::lock_guard<std::mutex> lk(g_mu);      // one stream per context
         rc = lb2_dp_run(c, n, tasks.data(), results.data(), &pool, &pn);
     }

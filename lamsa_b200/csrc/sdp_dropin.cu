@@ -157,7 +157,16 @@ void serve(lb2::SdpRequest* r) {
 // grow-only batch object, so steady state allocates nothing.
 void lb2::dropin_submit_sdp(std::vector<lb2::SdpRequest*>& batch) {
     if (batch.empty()) return;
-    thread_local lb2_sdp_batch* tl_batch = nullptr;
+    // one grow-only batch object per context (= per scheduler thread, or the process-wide one)
+    static std::mutex batch_mu;
+    static std::unordered_map<lb2_ctx*, lb2_sdp_batch*> batch_of;
+    lb2_ctx* const my_ctx = lb2::dropin_ctx();
+    lb2_sdp_batch* tl_batch = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(batch_mu);
+        auto it = batch_of.find(my_ctx);
+        if (it != batch_of.end()) tl_batch = it->second;
+    }
     const int stage = batch[0]->stage;
     const int64_t n = (int64_t)batch.size();
     std::vector<lb2_sdp_read> reads((size_t)n);
@@ -179,7 +188,11 @@ void lb2::dropin_submit_sdp(std::vector<lb2::SdpRequest*>& batch) {
         if (stage == 2) flags.insert(flags.end(), ws->tracked.begin(), ws->tracked.end());
     }
     const lb2_sdp_para* P = &batch[0]->ws->para;
-    if (!tl_batch) { if (lb2_sdp_create(lb2::dropin_ctx(), P, n, reads.data(), sid.data(), mn.data(), hits.data(), &tl_batch)) die("chaining batch"); }
+    if (!tl_batch) {
+        if (lb2_sdp_create(my_ctx, P, n, reads.data(), sid.data(), mn.data(), hits.data(), &tl_batch)) die("chaining batch");
+        std::lock_guard<std::mutex> lk(batch_mu);
+        batch_of[my_ctx] = tl_batch;
+    }
     else if (lb2_sdp_reset(tl_batch, P, n, reads.data(), sid.data(), mn.data(), hits.data())) die("chaining batch");
     const int32_t* w; const int64_t* off;
     if (stage == 1) {
