@@ -11,7 +11,6 @@
  * No reference code is copied.
  */
 #include <pthread.h>            /* before the renames, so the system declarations stay as they are */
-#include <sys/mman.h>
 #include <stdio.h>
 #include <stdint.h>
 #include <zlib.h>
@@ -24,49 +23,42 @@
 #define CHUNK_READ_N LAMSA_CHUNK
 
 /* Worker set-up cost.  aux_dp_init (src/lamsa_aln.c:969-982) gives every worker a frag_dp_node table
- * with one calloc(4, sizeof(line_node)) per node (fnode_alloc, :729-740): 10^4-10^5 small allocations
- * per worker, which the chaining entry points of liblamsa_b200 never look at (their state is on the
- * GPU).  With thousands of workers that is seconds of malloc.  Inside this translation unit those
- * son arrays come from a bump arena instead; free() of an arena pointer is a no-op.  Everything else
- * allocates as before. */
+ * (fnode_alloc, :729-740): seed_max+2 rows of per_aln_m nodes of 80 bytes, each node with its own
+ * calloc(4, sizeof(line_node)) -- 10^4-10^5 small allocations and megabytes of touched memory per
+ * worker.  The chaining entry points of liblamsa_b200 never look at that table (their node state is
+ * on the GPU; the f_node pointer only identifies the worker), so with thousands of workers it is
+ * seconds of pure set-up.  Inside fnode_alloc / fnode_free -- selected by __func__, nothing else in
+ * this translation unit is affected -- the node rows and son arrays are served from one shared
+ * scratch block instead (all workers alias it; nobody reads it), and freeing them is a no-op.  The
+ * f_node handle itself stays a real, unique allocation. */
 #include <stdlib.h>
 #include <string.h>
-static char *lb2w_arena_lo = 0, *lb2w_arena_hi = 0, *lb2w_arena_cur = 0;
-static pthread_mutex_t lb2w_mu = PTHREAD_MUTEX_INITIALIZER;
-static void *lb2w_calloc(size_t n, size_t sz)
+#define LB2W_SCRATCH_BYTES ((size_t)4 << 20)
+static char lb2w_scratch[LB2W_SCRATCH_BYTES] __attribute__((aligned(64)));
+static int lb2w_in(const char *fn, const char *name) { return strcmp(fn, name) == 0; }
+static int lb2w_nth;           /* mallocs seen inside the current fnode_alloc call (workers are set up one after the other) */
+static void *lb2w_malloc(size_t sz, const char *fn)
 {
-	if (n == 4 && sz == sizeof(line_node)) {
-		pthread_mutex_lock(&lb2w_mu);
-		if (!lb2w_arena_lo) {
-			size_t cap = (size_t)1 << 33;     /* 8 GiB of address space, touched on demand */
-			lb2w_arena_lo = lb2w_arena_cur = (char*)mmap(0, cap, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-			if (lb2w_arena_lo == MAP_FAILED) { lb2w_arena_lo = lb2w_arena_cur = 0; pthread_mutex_unlock(&lb2w_mu); return calloc(n, sz); }
-			lb2w_arena_hi = lb2w_arena_lo + cap;
-		}
-		void *p = 0;
-		if (lb2w_arena_cur + n * sz <= lb2w_arena_hi) { p = lb2w_arena_cur; lb2w_arena_cur += n * sz; }
-		pthread_mutex_unlock(&lb2w_mu);
-		if (p) return p;                      /* fresh anonymous pages are zero */
+	if (lb2w_in(fn, "fnode_alloc")) {
+		/* :730 the handle (8 bytes, real: it identifies the worker), :731 the row table (real), :733 the rows */
+		if (sz == sizeof(void*)) lb2w_nth = 0;
+		else if (++lb2w_nth >= 2 && sz <= LB2W_SCRATCH_BYTES) return lb2w_scratch;
 	}
+	return malloc(sz);
+}
+static void *lb2w_calloc(size_t n, size_t sz, const char *fn)
+{
+	if (lb2w_in(fn, "fnode_alloc") && n * sz <= LB2W_SCRATCH_BYTES) return lb2w_scratch;
 	return calloc(n, sz);
 }
 static void lb2w_free(void *p)
 {
-	if ((char*)p >= lb2w_arena_lo && (char*)p < lb2w_arena_hi) return;
+	if ((char*)p >= lb2w_scratch && (char*)p < lb2w_scratch + LB2W_SCRATCH_BYTES) return;
 	free(p);
 }
-static void *lb2w_realloc(void *p, size_t sz)
-{
-	if ((char*)p >= lb2w_arena_lo && (char*)p < lb2w_arena_hi) {      /* grow out of the arena */
-		void *q = malloc(sz);
-		if (q) memcpy(q, p, sz < 4 * sizeof(line_node) ? sz : 4 * sizeof(line_node));
-		return q;
-	}
-	return realloc(p, sz);
-}
-#define calloc lb2w_calloc
-#define free lb2w_free
-#define realloc lb2w_realloc
+#define malloc(sz) lb2w_malloc((sz), __func__)
+#define calloc(n, sz) lb2w_calloc((n), (sz), __func__)
+#define free(p) lb2w_free(p)
 
 /* CUDA start-up (about 1.5 s) overlaps index loading: the context is opened from a helper thread as
  * soon as the program starts. */
