@@ -229,11 +229,18 @@ int  lb2_dp_run(lb2_ctx *ctx, int64_t n, const lb2_task *tasks, lb2_result *resu
 int  lb2_ctx_set_chunk_tasks(lb2_ctx *ctx, int64_t tasks);
 /* byte / launch counters of the last lb2_dp_run on this context */
 int  lb2_ctx_last_run_stats(const lb2_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes, int64_t *launches);
+/* CUDA-event time of the fill and traceback kernels of the last lb2_dp_run on this context */
+int  lb2_ctx_last_run_kernel_ms(const lb2_ctx *ctx, float *fill_ms, float *trace_ms);
 
 /* Staged form used by the benchmark and by pipelined producers. */
 int  lb2_batch_create(lb2_ctx *ctx, int64_t n, const lb2_task *tasks, lb2_batch **out); /* pack to pinned host */
 int  lb2_batch_upload(lb2_batch *b);                       /* H2D, async on the ctx stream */
 int  lb2_batch_compute(lb2_batch *b, float *kernel_ms);    /* fill + traceback kernels; CUDA-event ms or NULL */
+/* lb2_batch_compute in two halves: _async enqueues the kernels and returns, _done polls (1 = finished),
+ * _wait blocks and reads the timings.  One batch per context may be between _async and _wait. */
+int  lb2_batch_compute_async(lb2_batch *b);
+int  lb2_batch_compute_done(lb2_batch *b);
+int  lb2_batch_compute_wait(lb2_batch *b, float *kernel_ms);
 int  lb2_batch_download(lb2_batch *b, lb2_result *results,
                         cigar32_t **cigar_pool, int64_t *cigar_pool_n);
 /* as lb2_batch_download, but the CIGAR pool is a view into pinned staging owned by

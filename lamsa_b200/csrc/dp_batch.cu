@@ -100,6 +100,7 @@ struct lb2_ctx {
     Buffers parked[2];                                  // buffers of the last destroyed batches (two: lb2_dp_run pipelines)
     cudaStream_t copy = nullptr;                        // H2D of batch k+1 overlaps the kernels of batch k
     int64_t run_h2d = 0, run_d2h = 0, run_launches = 0; // counters of the last lb2_dp_run
+    float run_fill_ms = 0, run_trace_ms = 0;
     int64_t chunk_tasks = 262144;                       // lb2_dp_run pipelines chunks of about this many tasks
     int sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -745,6 +746,14 @@ extern "C" int lb2_batch_compute(lb2_batch* b, float* kernel_ms) {
     return compute_finish(b, kernel_ms);
 }
 
+// split form of lb2_batch_compute for producers that overlap a batch with other work
+extern "C" int lb2_batch_compute_async(lb2_batch* b) { return compute_enqueue(b); }
+extern "C" int lb2_batch_compute_done(lb2_batch* b) {
+    if (!b || !b->enqueued) return 1;
+    return cudaEventQuery(b->ev[3]) == cudaSuccess ? 1 : 0;
+}
+extern "C" int lb2_batch_compute_wait(lb2_batch* b, float* kernel_ms) { return compute_finish(b, kernel_ms); }
+
 static int cigar_capacity(int n) {      // capacity after the doubling pushes of src/ksw.c:506-516
     if (n == 0) return 0;
     int m = 4; while (m < n) m <<= 1; return m;
@@ -840,6 +849,7 @@ extern "C" int lb2_dp_run(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_re
     int64_t K = chunk_min > 0 ? n / chunk_min : 1;
     K = std::max<int64_t>(1, std::min<int64_t>(K, 16));
     ctx->run_h2d = ctx->run_d2h = ctx->run_launches = 0;
+    ctx->run_fill_ms = ctx->run_trace_ms = 0;
     cigar32_t* pool = nullptr; int64_t pool_n = 0, pool_cap = 0;
     lb2_batch* prev = nullptr; int64_t prev_lo = 0;
     int rc = 0;
@@ -848,6 +858,7 @@ extern "C" int lb2_dp_run(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_re
         const cigar32_t* view = nullptr; int64_t used = 0;
         if (lb2_batch_download_view(b, results + lo, cigar_pool ? &view : nullptr, &used)) return 1;
         ctx->run_h2d += b->h2d_bytes; ctx->run_d2h += b->d2h_bytes; ctx->run_launches += b->launches;
+        ctx->run_fill_ms += b->fill_ms; ctx->run_trace_ms += b->trace_ms;
         if (cigar_pool) {
             if (pool_n + used > pool_cap) {
                 pool_cap = std::max<int64_t>((pool_n + used) * (K > 1 ? 2 : 1), 1024);
@@ -886,6 +897,13 @@ extern "C" int lb2_ctx_last_run_stats(const lb2_ctx* ctx, int64_t* h2d, int64_t*
     if (h2d) *h2d = ctx->run_h2d;
     if (d2h) *d2h = ctx->run_d2h;
     if (launches) *launches = ctx->run_launches;
+    return 0;
+}
+
+extern "C" int lb2_ctx_last_run_kernel_ms(const lb2_ctx* ctx, float* fill_ms, float* trace_ms) {
+    if (!ctx) return fail("ctx is NULL");
+    if (fill_ms) *fill_ms = ctx->run_fill_ms;
+    if (trace_ms) *trace_ms = ctx->run_trace_ms;
     return 0;
 }
 

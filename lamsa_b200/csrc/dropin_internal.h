@@ -23,6 +23,13 @@ struct DpRequest {
 // run requests as ONE GPU batch and hand the results back (ksw_dropin.cu)
 void dropin_submit_dp(std::vector<DpRequest*>& batch);
 
+// The same, overlapped with other work: submit on the calling thread's SECOND context (long tasks
+// must not hold up the rounds of short ones), poll, then finish (waits if needed, delivers results).
+struct DpAsync;
+DpAsync* dropin_dp_async_submit(std::vector<DpRequest*>& batch);
+bool dropin_dp_async_done(DpAsync* a);
+void dropin_dp_async_finish(DpAsync* a);
+
 // one blocked chaining call (sdp_dropin.cu).  The read's flattened seed hits and the tracked
 // flags stage 1 leaves for stage 2 live in the worker's state.
 struct SdpWorkerState {

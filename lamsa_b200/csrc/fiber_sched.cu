@@ -43,8 +43,11 @@ struct Sched {                       // one per OS thread
     std::vector<Fiber*> fibers, runnable;
     std::vector<lb2::DpRequest*> dp_wait;   std::vector<Fiber*> dp_owner;
     std::vector<lb2::SdpRequest*> sdp_wait; std::vector<Fiber*> sdp_owner;
+    // DP tasks too long for a round: parked until the next asynchronous batch, and the batch in flight
+    std::vector<lb2::DpRequest*> slow_wait; std::vector<Fiber*> slow_owner;
+    lb2::DpAsync* slow_inflight = nullptr;  std::vector<Fiber*> slow_inflight_owner;
     int index = 0;
-    int64_t switches = 0, flushes = 0, dp_tasks = 0, sdp_reqs = 0, max_dp = 0;
+    int64_t switches = 0, flushes = 0, dp_tasks = 0, sdp_reqs = 0, max_dp = 0, slow_batches = 0, slow_tasks = 0;
     double gpu_s = 0;
 };
 thread_local Sched* tl_sched = nullptr;
@@ -79,11 +82,34 @@ void yield_to_scheduler() {
 }
 
 // ---- rounds ------------------------------------------------------------------------------
-// Each OS thread owns a context (its own streams and scratch; thread k of a process that sees D
+// Each OS thread owns two contexts (own streams and scratch; thread k of a process that sees D
 // GPUs uses GPU k mod D) and advances in rounds of its own: it runs its workers until all of them
-// are parked, submits everything parked as one chaining batch per stage and one DP batch, and
-// resumes them.  Threads do not wait for each other, so a long DP task only delays the workers
-// that share its batch, and the batches of different threads overlap on the GPU(s).
+// are parked, submits what is parked and resumes the owners.  Threads do not wait for each other.
+//
+// A round lasts as long as its longest DP task (one warp walks the rows of a task: about 1.5 us
+// per row with the traceback), while the median task has 50-150 rows and the longest thousands
+// (SURVEY.md appendix C).  So the parked DP tasks are split: tasks of at most LB2_FAST_ROWS target
+// rows go out at once as the round's batch; longer ones go to the thread's second context as an
+// asynchronous batch that runs beside the following rounds, and their owners resume when it is done.
+int fast_rows() {
+    static const int v = [] { const char* e = getenv("LB2_FAST_ROWS"); return e && *e ? atoi(e) : 512; }();
+    return v;
+}
+
+void start_slow_batch(Sched* s) {
+    if (s->slow_inflight || s->slow_wait.empty()) return;
+    s->slow_inflight = lb2::dropin_dp_async_submit(s->slow_wait);
+    s->slow_inflight_owner.swap(s->slow_owner);
+    ++s->slow_batches; s->slow_tasks += (int64_t)s->slow_wait.size();
+    s->slow_wait.clear();
+}
+void finish_slow_batch(Sched* s) {          // waits if the batch is still running
+    lb2::dropin_dp_async_finish(s->slow_inflight);
+    s->slow_inflight = nullptr;
+    for (Fiber* f : s->slow_inflight_owner) s->runnable.push_back(f);
+    s->slow_inflight_owner.clear();
+}
+
 void flush(Sched* s) {
     const auto t0 = std::chrono::steady_clock::now();
     for (int stage = 1; stage <= 2; ++stage) {
@@ -91,13 +117,29 @@ void flush(Sched* s) {
         for (lb2::SdpRequest* q : s->sdp_wait) if (q->stage == stage) grp.push_back(q);
         if (!grp.empty()) lb2::dropin_submit_sdp(grp);
     }
-    if (!s->dp_wait.empty()) lb2::dropin_submit_dp(s->dp_wait);
-    s->gpu_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    ++s->flushes; s->dp_tasks += (int64_t)s->dp_wait.size(); s->sdp_reqs += (int64_t)s->sdp_wait.size();
-    s->max_dp = std::max<int64_t>(s->max_dp, (int64_t)s->dp_wait.size());
     for (Fiber* f : s->sdp_owner) s->runnable.push_back(f);
-    for (Fiber* f : s->dp_owner) s->runnable.push_back(f);
-    s->dp_wait.clear(); s->dp_owner.clear(); s->sdp_wait.clear(); s->sdp_owner.clear();
+    s->sdp_reqs += (int64_t)s->sdp_wait.size();
+    s->sdp_wait.clear(); s->sdp_owner.clear();
+
+    std::vector<lb2::DpRequest*> fast; std::vector<Fiber*> fast_owner;
+    const int lim = fast_rows();
+    for (size_t i = 0; i < s->dp_wait.size(); ++i) {
+        if (lim > 0 && s->dp_wait[i]->task.tlen > lim) { s->slow_wait.push_back(s->dp_wait[i]); s->slow_owner.push_back(s->dp_owner[i]); }
+        else { fast.push_back(s->dp_wait[i]); fast_owner.push_back(s->dp_owner[i]); }
+    }
+    s->dp_wait.clear(); s->dp_owner.clear();
+    start_slow_batch(s);                       // runs beside the fast batch below and the next rounds
+    if (!fast.empty()) {
+        lb2::dropin_submit_dp(fast);
+        ++s->flushes; s->dp_tasks += (int64_t)fast.size();
+        s->max_dp = std::max<int64_t>(s->max_dp, (int64_t)fast.size());
+        for (Fiber* f : fast_owner) s->runnable.push_back(f);
+    }
+    if (s->slow_inflight && (s->runnable.empty() || lb2::dropin_dp_async_done(s->slow_inflight))) {
+        finish_slow_batch(s);                  // nothing else to do, or it is ready anyway
+        start_slow_batch(s);
+    }
+    s->gpu_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 void run_scheduler(Sched* s) {
@@ -114,7 +156,7 @@ void run_scheduler(Sched* s) {
             if (f->done) { --live; munmap(f->stack, f->stack_bytes); f->stack = nullptr; }
         }
         if (live == 0) break;
-        if (s->dp_wait.empty() && s->sdp_wait.empty()) {
+        if (s->dp_wait.empty() && s->sdp_wait.empty() && s->slow_wait.empty() && !s->slow_inflight) {
             fprintf(stderr, "[lamsa_b200] fiber scheduler: %zu workers alive but nothing parked\n", live); exit(1);
         }
         flush(s);
@@ -135,13 +177,14 @@ void run_all(std::vector<Fiber*>& fibers) {
     run_scheduler(&scheds[0]);
     for (auto& t : th) t.join();
     if (g_verbose()) {
-        int64_t sw = 0, fl = 0, dp = 0, sd = 0, mx = 0; double g = 0;
-        for (Sched& s : scheds) { sw += s.switches; fl += s.flushes; dp += s.dp_tasks; sd += s.sdp_reqs; mx = std::max(mx, s.max_dp); g = std::max(g, s.gpu_s); }
+        int64_t sw = 0, fl = 0, dp = 0, sd = 0, mx = 0, sb = 0, stt = 0; double g = 0;
+        for (Sched& s : scheds) { sw += s.switches; fl += s.flushes; dp += s.dp_tasks; sd += s.sdp_reqs; mx = std::max(mx, s.max_dp); g = std::max(g, s.gpu_s);
+                                  sb += s.slow_batches; stt += s.slow_tasks; }
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         fprintf(stderr, "[lamsa_b200] %zu workers on %d threads: %.3f s, %lld rounds (%.0f per thread), %lld DP tasks (%.0f per launch, max %lld), "
-                        "%lld chaining requests, %lld switches, %.3f s inside GPU submissions (slowest thread)\n",
+                        "%lld long DP tasks in %lld side batches, %lld chaining requests, %lld switches, %.3f s inside GPU submissions (slowest thread)\n",
                 fibers.size(), K, wall, (long long)fl, (double)fl / K, (long long)dp, fl ? (double)dp / fl : 0.0, (long long)mx,
-                (long long)sd, (long long)sw, g);
+                (long long)stt, (long long)sb, (long long)sd, (long long)sw, g);
     }
     for (Fiber* f : fibers) delete f;
     fibers.clear();

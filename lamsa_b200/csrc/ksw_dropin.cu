@@ -24,6 +24,7 @@ std::mutex g_mu;
 lb2_ctx* g_ctx = nullptr;
 
 thread_local lb2_ctx* tl_ctx = nullptr;        // scheduler threads of the batch producer own a context each
+thread_local lb2_ctx* tl_slow_ctx = nullptr;   // ... and a second one for batches that run beside their rounds
 
 lb2_ctx* default_ctx() {
     if (tl_ctx) return tl_ctx;
@@ -45,10 +46,10 @@ void lb2::dropin_use_thread_ctx(int index) {
     if (tl_ctx) return;
     // scheduler threads are re-created per read chunk; their contexts are kept by index
     static std::mutex mu;
-    static std::vector<lb2_ctx*> table;
+    static std::vector<lb2_ctx*> table, slow_table;
     std::lock_guard<std::mutex> lk(mu);
-    if ((size_t)index < table.size() && table[(size_t)index]) { tl_ctx = table[(size_t)index]; return; }
-    if ((size_t)index >= table.size()) table.resize((size_t)index + 1, nullptr);
+    if ((size_t)index < table.size() && table[(size_t)index]) { tl_ctx = table[(size_t)index]; tl_slow_ctx = slow_table[(size_t)index]; return; }
+    if ((size_t)index >= table.size()) { table.resize((size_t)index + 1, nullptr); slow_table.resize((size_t)index + 1, nullptr); }
     int ndev = 1;
     if (const char* e = getenv("LB2_DEVICES")) ndev = atoi(e) > 0 ? atoi(e) : 1;
     int base = 0;
@@ -61,6 +62,37 @@ void lb2::dropin_use_thread_ctx(int index) {
     if (const char* e = getenv("LB2_THREAD_SCRATCH_MB")) lim = (uint64_t)atol(e) << 20;
     lb2_ctx_set_scratch_limit(tl_ctx, lim);
     table[(size_t)index] = tl_ctx;
+    if (lb2_ctx_create(base + index % ndev, &tl_slow_ctx)) { fprintf(stderr, "[lamsa_b200] %s\n", lb2_last_error()); exit(1); }
+    lb2_ctx_set_scratch_limit(tl_slow_ctx, lim);
+    slow_table[(size_t)index] = tl_slow_ctx;
+}
+
+namespace { void deliver(std::vector<lb2::DpRequest*>& batch, const lb2_result* results, const cigar32_t* pool); }
+struct lb2::DpAsync {
+    lb2_batch* b = nullptr;
+    std::vector<DpRequest*> reqs;
+};
+lb2::DpAsync* lb2::dropin_dp_async_submit(std::vector<DpRequest*>& batch) {
+    if (!tl_slow_ctx) { fprintf(stderr, "[lamsa_b200] asynchronous DP batch outside a scheduler thread\n"); exit(1); }
+    DpAsync* a = new DpAsync();
+    a->reqs = batch;
+    std::vector<lb2_task> tasks(batch.size());
+    for (size_t i = 0; i < batch.size(); ++i) tasks[i] = batch[i]->task;
+    if (lb2_batch_create(tl_slow_ctx, (int64_t)tasks.size(), tasks.data(), &a->b) || lb2_batch_upload(a->b) || lb2_batch_compute_async(a->b)) {
+        fprintf(stderr, "[lamsa_b200] DP launch failed: %s\n", lb2_last_error()); exit(1);
+    }
+    return a;
+}
+bool lb2::dropin_dp_async_done(DpAsync* a) { return lb2_batch_compute_done(a->b) != 0; }
+void lb2::dropin_dp_async_finish(DpAsync* a) {
+    std::vector<lb2_result> results(a->reqs.size());
+    const cigar32_t* pool = nullptr; int64_t pn = 0;
+    if (lb2_batch_compute_wait(a->b, nullptr) || lb2_batch_download_view(a->b, results.data(), &pool, &pn)) {
+        fprintf(stderr, "[lamsa_b200] DP batch failed: %s\n", lb2_last_error()); exit(1);
+    }
+    deliver(a->reqs, results.data(), pool);
+    lb2_batch_destroy(a->b);
+    delete a;
 }
 // open the drop-in context from a helper thread (CUDA start-up overlaps the caller's own start-up)
 extern "C" void lb2_dropin_warmup(void) { std::thread([] { default_ctx(); }).detach(); }
@@ -87,6 +119,22 @@ int gather_us() {
     return v;
 }
 
+// hand results (and malloc'd CIGARs with the capacity the reference would have grown to) back
+void deliver(std::vector<Pending*>& batch, const lb2_result* results, const cigar32_t* pool) {
+    for (size_t i = 0; i < batch.size(); ++i) {
+        Pending* p = batch[i];
+        const lb2_result& r = results[i];
+        *p->res = r;
+        if (p->cig) {
+            if (r.n_cigar > 0) {
+                cigar32_t* out = (cigar32_t*)malloc(sizeof(cigar32_t) * (size_t)r.reserved);
+                memcpy(out, pool + r.cigar_off, sizeof(cigar32_t) * (size_t)r.n_cigar);
+                *p->cig = out;
+            } else *p->cig = nullptr;
+        }
+    }
+}
+
 void submit_batch(std::vector<Pending*>& batch) {
     lb2_ctx* c = default_ctx();
     const int64_t n = (int64_t)batch.size();
@@ -95,25 +143,28 @@ void submit_batch(std::vector<Pending*>& batch) {
     for (int64_t i = 0; i < n; ++i) tasks[(size_t)i] = batch[(size_t)i]->task;
     cigar32_t* pool = nullptr; int64_t pn = 0;
     int rc;
+    static FILE* round_log = [] { const char* e = getenv("LB2_ROUND_LOG"); return e && *e ? fopen(e, "w") : (FILE*)nullptr; }();
+    const auto t0 = std::chrono::steady_clock::now();
     if (tl_ctx) rc = lb2_dp_run(c, n, tasks.data(), results.data(), &pool, &pn);      // this thread's own context
     else {
         std::lock_guard<std::mutex> lk(g_mu);      // one stream per context
         rc = lb2_dp_run(c, n, tasks.data(), results.data(), &pool, &pn);
     }
     if (rc) { fprintf(stderr, "[lamsa_b200] DP launch failed: %s\n", lb2_last_error()); exit(1); }
-    for (int64_t i = 0; i < n; ++i) {
-        Pending* p = batch[(size_t)i];
-        const lb2_result& r = results[(size_t)i];
-        *p->res = r;
-        if (p->cig) {
-            if (r.n_cigar > 0) {
-                // hand back exactly the capacity the reference would have grown to
-                cigar32_t* out = (cigar32_t*)malloc(sizeof(cigar32_t) * (size_t)r.reserved);
-                memcpy(out, pool + r.cigar_off, sizeof(cigar32_t) * (size_t)r.n_cigar);
-                *p->cig = out;
-            } else *p->cig = nullptr;
+    if (round_log) {        // one line per submitted batch: tasks, longest task, cells, wall and kernel time
+        const double us = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e6;
+        int max_t = 0, max_q = 0, max_w = 0; int64_t cells = 0, launches = 0; float fm = 0, tm = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            if (tasks[(size_t)i].tlen > max_t) { max_t = tasks[(size_t)i].tlen; max_q = tasks[(size_t)i].qlen; max_w = tasks[(size_t)i].w; }
+            cells += results[(size_t)i].cells;
         }
+        lb2_ctx_last_run_stats(c, nullptr, nullptr, &launches);
+        lb2_ctx_last_run_kernel_ms(c, &fm, &tm);
+        static std::mutex log_mu;
+        std::lock_guard<std::mutex> lk(log_mu);
+        fprintf(round_log, "%lld %d %d %d %lld %.1f %.3f %.3f %lld\n", (long long)n, max_t, max_q, max_w, (long long)cells, us, fm, tm, (long long)launches);
     }
+    deliver(batch, results.data(), pool);
     lb2_free(pool);
 }
 
