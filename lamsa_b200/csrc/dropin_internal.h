@@ -23,10 +23,12 @@ struct DpRequest {
 // run requests as ONE GPU batch and hand the results back (ksw_dropin.cu)
 void dropin_submit_dp(std::vector<DpRequest*>& batch);
 
-// The same, overlapped with other work: submit on the calling thread's SECOND context (long tasks
-// must not hold up the rounds of short ones), poll, then finish (waits if needed, delivers results).
+// The same, overlapped with other work: submit on one of the calling scheduler thread's side
+// contexts (slot 0..kAsyncSlots-1, one batch in flight per slot), poll, then finish (waits if
+// needed, delivers results).
+constexpr int kAsyncSlots = 3;
 struct DpAsync;
-DpAsync* dropin_dp_async_submit(std::vector<DpRequest*>& batch);
+DpAsync* dropin_dp_async_submit(std::vector<DpRequest*>& batch, int slot);
 bool dropin_dp_async_done(DpAsync* a);
 void dropin_dp_async_finish(DpAsync* a);
 

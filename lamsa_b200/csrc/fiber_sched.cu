@@ -37,15 +37,19 @@ struct Fiber {
     bool done = false;
 };
 
+struct InFlight { lb2::DpAsync* a = nullptr; std::vector<Fiber*> owners; int slot = 0; };
+
 struct Sched {                       // one per OS thread
     ucontext_t main;
     Fiber* cur = nullptr;
     std::vector<Fiber*> fibers, runnable;
     std::vector<lb2::DpRequest*> dp_wait;   std::vector<Fiber*> dp_owner;
     std::vector<lb2::SdpRequest*> sdp_wait; std::vector<Fiber*> sdp_owner;
-    // DP tasks too long for a round: parked until the next asynchronous batch, and the batch in flight
-    std::vector<lb2::DpRequest*> slow_wait; std::vector<Fiber*> slow_owner;
-    lb2::DpAsync* slow_inflight = nullptr;  std::vector<Fiber*> slow_inflight_owner;
+    // parked DP requests by class (short / long tasks), batches in flight, workers not yet started
+    std::vector<lb2::DpRequest*> fast_wait, slow_wait; std::vector<Fiber*> fast_owner, slow_owner;
+    std::vector<InFlight> inflight;
+    bool slot_busy[lb2::kAsyncSlots] = {false};
+    std::vector<Fiber*> staged;
     int index = 0;
     int64_t switches = 0, flushes = 0, dp_tasks = 0, sdp_reqs = 0, max_dp = 0, slow_batches = 0, slow_tasks = 0;
     double gpu_s = 0;
@@ -82,63 +86,71 @@ void yield_to_scheduler() {
 }
 
 // ---- rounds ------------------------------------------------------------------------------
-// Each OS thread owns two contexts (own streams and scratch; thread k of a process that sees D
-// GPUs uses GPU k mod D) and advances in rounds of its own: it runs its workers until all of them
-// are parked, submits what is parked and resumes the owners.  Threads do not wait for each other.
-//
-// A round lasts as long as its longest DP task (one warp walks the rows of a task: about 1.5 us
-// per row with the traceback), while the median task has 50-150 rows and the longest thousands
-// (SURVEY.md appendix C).  So the parked DP tasks are split: tasks of at most LB2_FAST_ROWS target
-// rows go out at once as the round's batch; longer ones go to the thread's second context as an
-// asynchronous batch that runs beside the following rounds, and their owners resume when it is done.
+// Each OS thread owns its contexts (own streams and scratch; thread k of a process that sees D GPUs
+// uses GPU k mod D) and is never synchronised with the other threads.  Whenever none of its workers
+// can run, it submits what they have parked as ASYNCHRONOUS batches (up to kAsyncSlots in flight)
+// and, if still nothing can run, waits for the oldest batch and resumes its owners.
+//  * The workers are started in two halves, so that while one half's batch is on the GPU the other
+//    half does its host work: submission, kernels and host control flow overlap.
+//  * A batch lasts as long as its longest DP task (one warp walks the rows of a task: about 1.5 us
+//    per row with the traceback), while the median task has 50-150 rows and the longest thousands
+//    (SURVEY.md appendix C).  Parked tasks are therefore split: tasks of more than LB2_FAST_ROWS
+//    target rows travel in a batch of their own, so the owners of short tasks resume early.
 int fast_rows() {
     static const int v = [] { const char* e = getenv("LB2_FAST_ROWS"); return e && *e ? atoi(e) : 512; }();
     return v;
 }
 
-void start_slow_batch(Sched* s) {
-    if (s->slow_inflight || s->slow_wait.empty()) return;
-    s->slow_inflight = lb2::dropin_dp_async_submit(s->slow_wait);
-    s->slow_inflight_owner.swap(s->slow_owner);
-    ++s->slow_batches; s->slow_tasks += (int64_t)s->slow_wait.size();
-    s->slow_wait.clear();
+bool submit_group(Sched* s, std::vector<lb2::DpRequest*>& reqs, std::vector<Fiber*>& owners, bool slow) {
+    if (reqs.empty()) return true;
+    int slot = -1;
+    for (int k = 0; k < lb2::kAsyncSlots; ++k) if (!s->slot_busy[k]) { slot = k; break; }
+    if (slot < 0) return false;
+    InFlight f;
+    f.a = lb2::dropin_dp_async_submit(reqs, slot);
+    f.owners.swap(owners);
+    f.slot = slot;
+    s->slot_busy[slot] = true;
+    s->inflight.push_back(std::move(f));
+    if (slow) { ++s->slow_batches; s->slow_tasks += (int64_t)reqs.size(); }
+    else { ++s->flushes; s->dp_tasks += (int64_t)reqs.size(); s->max_dp = std::max<int64_t>(s->max_dp, (int64_t)reqs.size()); }
+    reqs.clear();
+    return true;
 }
-void finish_slow_batch(Sched* s) {          // waits if the batch is still running
-    lb2::dropin_dp_async_finish(s->slow_inflight);
-    s->slow_inflight = nullptr;
-    for (Fiber* f : s->slow_inflight_owner) s->runnable.push_back(f);
-    s->slow_inflight_owner.clear();
+void finish_at(Sched* s, size_t i) {                 // waits if the batch is still running
+    InFlight f = std::move(s->inflight[i]);
+    s->inflight.erase(s->inflight.begin() + (long)i);
+    lb2::dropin_dp_async_finish(f.a);
+    s->slot_busy[f.slot] = false;
+    for (Fiber* w : f.owners) s->runnable.push_back(w);
 }
 
+// nothing can run: submit, reap, wait
 void flush(Sched* s) {
     const auto t0 = std::chrono::steady_clock::now();
-    for (int stage = 1; stage <= 2; ++stage) {
-        std::vector<lb2::SdpRequest*> grp;
-        for (lb2::SdpRequest* q : s->sdp_wait) if (q->stage == stage) grp.push_back(q);
-        if (!grp.empty()) lb2::dropin_submit_sdp(grp);
+    if (!s->sdp_wait.empty()) {                      // chaining: two calls per read, served at once
+        for (int stage = 1; stage <= 2; ++stage) {
+            std::vector<lb2::SdpRequest*> grp;
+            for (lb2::SdpRequest* q : s->sdp_wait) if (q->stage == stage) grp.push_back(q);
+            if (!grp.empty()) lb2::dropin_submit_sdp(grp);
+        }
+        for (Fiber* f : s->sdp_owner) s->runnable.push_back(f);
+        s->sdp_reqs += (int64_t)s->sdp_wait.size();
+        s->sdp_wait.clear(); s->sdp_owner.clear();
     }
-    for (Fiber* f : s->sdp_owner) s->runnable.push_back(f);
-    s->sdp_reqs += (int64_t)s->sdp_wait.size();
-    s->sdp_wait.clear(); s->sdp_owner.clear();
-
-    std::vector<lb2::DpRequest*> fast; std::vector<Fiber*> fast_owner;
     const int lim = fast_rows();
     for (size_t i = 0; i < s->dp_wait.size(); ++i) {
-        if (lim > 0 && s->dp_wait[i]->task.tlen > lim) { s->slow_wait.push_back(s->dp_wait[i]); s->slow_owner.push_back(s->dp_owner[i]); }
-        else { fast.push_back(s->dp_wait[i]); fast_owner.push_back(s->dp_owner[i]); }
+        const bool slow = lim > 0 && s->dp_wait[i]->task.tlen > lim;
+        (slow ? s->slow_wait : s->fast_wait).push_back(s->dp_wait[i]);
+        (slow ? s->slow_owner : s->fast_owner).push_back(s->dp_owner[i]);
     }
     s->dp_wait.clear(); s->dp_owner.clear();
-    start_slow_batch(s);                       // runs beside the fast batch below and the next rounds
-    if (!fast.empty()) {
-        lb2::dropin_submit_dp(fast);
-        ++s->flushes; s->dp_tasks += (int64_t)fast.size();
-        s->max_dp = std::max<int64_t>(s->max_dp, (int64_t)fast.size());
-        for (Fiber* f : fast_owner) s->runnable.push_back(f);
-    }
-    if (s->slow_inflight && (s->runnable.empty() || lb2::dropin_dp_async_done(s->slow_inflight))) {
-        finish_slow_batch(s);                  // nothing else to do, or it is ready anyway
-        start_slow_batch(s);
-    }
+    submit_group(s, s->fast_wait, s->fast_owner, false);
+    submit_group(s, s->slow_wait, s->slow_owner, true);
+    for (size_t i = 0; i < s->inflight.size();)      // reap what is ready
+        if (lb2::dropin_dp_async_done(s->inflight[i].a)) finish_at(s, i); else ++i;
+    if (s->runnable.empty() && !s->staged.empty()) { s->runnable.swap(s->staged); }   // second half of the workers starts now
+    if (s->runnable.empty() && !s->inflight.empty()) finish_at(s, 0);                  // wait for the oldest batch
     s->gpu_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
@@ -146,7 +158,9 @@ void run_scheduler(Sched* s) {
     tl_sched = s;
     lb2::dropin_use_thread_ctx(s->index);
     size_t live = s->fibers.size();
-    for (Fiber* f : s->fibers) s->runnable.push_back(f);
+    // s->fibers is in reverse worker order (the run queue pops from the back)
+    const size_t half = s->fibers.size() / 2;
+    for (size_t i = 0; i < s->fibers.size(); ++i) (i < half ? s->staged : s->runnable).push_back(s->fibers[i]);
     while (live > 0) {
         while (!s->runnable.empty()) {
             Fiber* f = s->runnable.back(); s->runnable.pop_back();
@@ -156,7 +170,7 @@ void run_scheduler(Sched* s) {
             if (f->done) { --live; munmap(f->stack, f->stack_bytes); f->stack = nullptr; }
         }
         if (live == 0) break;
-        if (s->dp_wait.empty() && s->sdp_wait.empty() && s->slow_wait.empty() && !s->slow_inflight) {
+        if (s->dp_wait.empty() && s->sdp_wait.empty() && s->slow_wait.empty() && s->fast_wait.empty() && s->inflight.empty() && s->staged.empty()) {
             fprintf(stderr, "[lamsa_b200] fiber scheduler: %zu workers alive but nothing parked\n", live); exit(1);
         }
         flush(s);

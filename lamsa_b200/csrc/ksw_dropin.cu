@@ -24,7 +24,7 @@ std::mutex g_mu;
 lb2_ctx* g_ctx = nullptr;
 
 thread_local lb2_ctx* tl_ctx = nullptr;        // scheduler threads of the batch producer own a context each
-thread_local lb2_ctx* tl_slow_ctx = nullptr;   // ... and a second one for batches that run beside their rounds
+thread_local lb2_ctx* tl_side_ctx[lb2::kAsyncSlots] = {nullptr};   // ... and side contexts for batches in flight
 
 lb2_ctx* default_ctx() {
     if (tl_ctx) return tl_ctx;
@@ -46,10 +46,15 @@ void lb2::dropin_use_thread_ctx(int index) {
     if (tl_ctx) return;
     // scheduler threads are re-created per read chunk; their contexts are kept by index
     static std::mutex mu;
-    static std::vector<lb2_ctx*> table, slow_table;
+    static std::vector<lb2_ctx*> table;
+    static std::vector<std::vector<lb2_ctx*>> side_table;
     std::lock_guard<std::mutex> lk(mu);
-    if ((size_t)index < table.size() && table[(size_t)index]) { tl_ctx = table[(size_t)index]; tl_slow_ctx = slow_table[(size_t)index]; return; }
-    if ((size_t)index >= table.size()) { table.resize((size_t)index + 1, nullptr); slow_table.resize((size_t)index + 1, nullptr); }
+    if ((size_t)index < table.size() && table[(size_t)index]) {
+        tl_ctx = table[(size_t)index];
+        for (int k = 0; k < lb2::kAsyncSlots; ++k) tl_side_ctx[k] = side_table[(size_t)index][(size_t)k];
+        return;
+    }
+    if ((size_t)index >= table.size()) { table.resize((size_t)index + 1, nullptr); side_table.resize((size_t)index + 1); }
     int ndev = 1;
     if (const char* e = getenv("LB2_DEVICES")) ndev = atoi(e) > 0 ? atoi(e) : 1;
     int base = 0;
@@ -62,9 +67,11 @@ void lb2::dropin_use_thread_ctx(int index) {
     if (const char* e = getenv("LB2_THREAD_SCRATCH_MB")) lim = (uint64_t)atol(e) << 20;
     lb2_ctx_set_scratch_limit(tl_ctx, lim);
     table[(size_t)index] = tl_ctx;
-    if (lb2_ctx_create(base + index % ndev, &tl_slow_ctx)) { fprintf(stderr, "[lamsa_b200] %s\n", lb2_last_error()); exit(1); }
-    lb2_ctx_set_scratch_limit(tl_slow_ctx, lim);
-    slow_table[(size_t)index] = tl_slow_ctx;
+    for (int k = 0; k < lb2::kAsyncSlots; ++k) {
+        if (lb2_ctx_create(base + index % ndev, &tl_side_ctx[k])) { fprintf(stderr, "[lamsa_b200] %s\n", lb2_last_error()); exit(1); }
+        lb2_ctx_set_scratch_limit(tl_side_ctx[k], lim);
+        side_table[(size_t)index].push_back(tl_side_ctx[k]);
+    }
 }
 
 namespace { void deliver(std::vector<lb2::DpRequest*>& batch, const lb2_result* results, const cigar32_t* pool); }
@@ -72,8 +79,9 @@ struct lb2::DpAsync {
     lb2_batch* b = nullptr;
     std::vector<DpRequest*> reqs;
 };
-lb2::DpAsync* lb2::dropin_dp_async_submit(std::vector<DpRequest*>& batch) {
-    if (!tl_slow_ctx) { fprintf(stderr, "[lamsa_b200] asynchronous DP batch outside a scheduler thread\n"); exit(1); }
+lb2::DpAsync* lb2::dropin_dp_async_submit(std::vector<DpRequest*>& batch, int slot) {
+    if (slot < 0 || slot >= kAsyncSlots || !tl_side_ctx[slot]) { fprintf(stderr, "[lamsa_b200] asynchronous DP batch outside a scheduler thread\n"); exit(1); }
+    lb2_ctx* tl_slow_ctx = tl_side_ctx[slot];
     DpAsync* a = new DpAsync();
     a->reqs = batch;
     std::vector<lb2_task> tasks(batch.size());
@@ -162,7 +170,10 @@ void submit_batch(std::vector<Pending*>& batch) {
         lb2_ctx_last_run_kernel_ms(c, &fm, &tm);
         static std::mutex log_mu;
         std::lock_guard<std::mutex> lk(log_mu);
-        fprintf(round_log, "%lld %d %d %d %lld %.1f %.3f %.3f %lld\n", (long long)n, max_t, max_q, max_w, (long long)cells, us, fm, tm, (long long)launches);
+        static const auto log_t0 = std::chrono::steady_clock::now();
+        const double at = std::chrono::duration<double>(t0 - log_t0).count() * 1e6;
+        fprintf(round_log, "%lld %d %d %d %lld %.1f %.3f %.3f %lld %.0f %p\n", (long long)n, max_t, max_q, max_w, (long long)cells, us, fm, tm,
+                (long long)launches, at, (void*)c);
     }
     deliver(batch, results.data(), pool);
     lb2_free(pool);
