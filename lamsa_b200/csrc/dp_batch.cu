@@ -342,6 +342,13 @@ static void parallel_for(int64_t n, F f) {
     for (auto& t : th) t.join();
 }
 
+// Grow-only buffers grow geometrically with a floor: every cudaMalloc / cudaFree / cudaMallocHost is a
+// device-wide synchronisation, and a producer that submits batch after batch of slightly different size
+// (the fiber scheduler, many contexts at once) must reach a steady state without them.
+static size_t grown(size_t need, size_t old_cap, size_t floor_) {
+    return std::max(std::max(need + need / 4, old_cap * 2), floor_);
+}
+
 extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_batch** out) {
     if (!ctx || !out || (n > 0 && !tasks)) return fail("lb2_batch_create: NULL argument");
     if (n < 0 || n > (int64_t)1 << 30) return fail("lb2_batch_create: n=%lld out of range", (long long)n);
@@ -440,14 +447,14 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     B.valid = true;
     const size_t n1c = (size_t)std::max<int64_t>(n, 1);
     if (B.h_pool_cap < b->pool_bytes) {
+        const size_t cap = grown(b->pool_bytes, B.h_pool_cap, (size_t)1 << 20);
         cudaFreeHost(B.h_pool); B.h_pool = nullptr; B.h_pool_cap = 0;
-        const size_t cap = b->pool_bytes + b->pool_bytes / 8;
         CU(cudaMallocHost(&B.h_pool, cap)); B.h_pool_cap = cap;
     }
     if (B.h_n_cap < n1c) {
+        const size_t cap = grown(n1c, B.h_n_cap, 4096);
         cudaFreeHost(B.h_tasks); cudaFreeHost(B.h_results); cudaFreeHost(B.h_order);
         B.h_tasks = nullptr; B.h_results = nullptr; B.h_order = nullptr; B.h_n_cap = 0;
-        const size_t cap = n1c + n1c / 8;
         CU(cudaMallocHost(&B.h_tasks, sizeof(DTask) * cap));
         CU(cudaMallocHost(&B.h_results, sizeof(DResult) * cap));
         CU(cudaMallocHost(&B.h_order, sizeof(int32_t) * cap));
@@ -544,14 +551,14 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
 
     // ---- device allocations (grow-only, reused across batches)
     if (B.d_pool_cap < b->pool_bytes) {
+        const size_t cap = grown(b->pool_bytes, B.d_pool_cap, (size_t)1 << 20);
         cudaFree(B.d_pool); B.d_pool = nullptr; B.d_pool_cap = 0;
-        const size_t cap = b->pool_bytes + b->pool_bytes / 8;
         CU(cudaMalloc(&B.d_pool, cap)); B.d_pool_cap = cap;
     }
     if (B.d_n_cap < n1c) {
+        const size_t cap = grown(n1c, B.d_n_cap, 4096);
         cudaFree(B.d_tasks); cudaFree(B.d_results); cudaFree(B.d_order);
         B.d_tasks = nullptr; B.d_results = nullptr; B.d_order = nullptr; B.d_n_cap = 0;
-        const size_t cap = n1c + n1c / 8;
         CU(cudaMalloc(&B.d_tasks, sizeof(DTask) * cap));
         CU(cudaMalloc(&B.d_results, sizeof(DResult) * cap));
         CU(cudaMalloc(&B.d_order, sizeof(int32_t) * cap));
@@ -560,8 +567,8 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     if (!B.d_mats) CU(cudaMalloc(&B.d_mats, sizeof(uint2) * kMaxMats * 8));
     b->dense_cap = dense + 16;
     if (B.dense_cap < b->dense_cap) {
+        const size_t cap = grown(b->dense_cap, B.dense_cap, (size_t)1 << 18);
         cudaFree(B.d_cdense); B.d_cdense = nullptr; B.dense_cap = 0;
-        const size_t cap = b->dense_cap + b->dense_cap / 8;
         CU(cudaMalloc(&B.d_cdense, sizeof(int32_t) * cap)); B.dense_cap = cap;
     }
     if (!B.d_cursor) CU(cudaMalloc(&B.d_cursor, sizeof(unsigned long long)));
@@ -580,14 +587,16 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     uint64_t zmax = 16, cmax = 16;
     for (auto& wv : b->waves) { zmax = std::max(zmax, wv.z_bytes); cmax = std::max(cmax, wv.ctmp_words); }
     if (ctx->z_cap < zmax) {
+        const size_t cap = grown(zmax, ctx->z_cap, (size_t)16 << 20);
         if (ctx->d_z) CU(cudaFree(ctx->d_z));
         ctx->d_z = nullptr; ctx->z_cap = 0;
-        CU(cudaMalloc(&ctx->d_z, zmax + 64)); ctx->z_cap = zmax;
+        CU(cudaMalloc(&ctx->d_z, cap + 64)); ctx->z_cap = cap;
     }
     if (ctx->ctmp_cap < cmax) {
+        const size_t cap = grown(cmax, ctx->ctmp_cap, (size_t)1 << 20);
         if (ctx->d_ctmp) CU(cudaFree(ctx->d_ctmp));
         ctx->d_ctmp = nullptr; ctx->ctmp_cap = 0;
-        CU(cudaMalloc(&ctx->d_ctmp, (cmax + 16) * 4)); ctx->ctmp_cap = cmax;
+        CU(cudaMalloc(&ctx->d_ctmp, (cap + 16) * 4)); ctx->ctmp_cap = cap;
     }
     guard.ok = true;
     *out = b;
@@ -772,8 +781,8 @@ static int download_impl(lb2_batch* b, lb2_result* results, bool want_cigar, uns
     if (want_cigar && used) {
         Buffers& B = b->B;
         if (B.h_cigar_cap < used) {
+            const size_t cap = grown(used, B.h_cigar_cap, (size_t)1 << 18);
             cudaFreeHost(B.h_cigar); B.h_cigar = nullptr; B.h_cigar_cap = 0;
-            const size_t cap = used + used / 8 + 1024;
             CU(cudaMallocHost(&B.h_cigar, cap * sizeof(cigar32_t))); B.h_cigar_cap = cap;
         }
         CU(cudaMemcpyAsync(B.h_cigar, b->d_cdense, sizeof(cigar32_t) * used, cudaMemcpyDeviceToHost, s));

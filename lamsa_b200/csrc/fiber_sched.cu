@@ -64,9 +64,12 @@ size_t stack_bytes() {
     static const size_t v = [] { const char* e = getenv("LB2_FIBER_STACK_KB"); return (size_t)(e && *e ? atol(e) : 1024) * 1024; }();
     return v;
 }
+// scheduler threads.  Measured on the 16-thread B200 host (profiles/r01_lamsa_whole_program.jsonl):
+// 4 threads beat 8 and 16 -- the host control flow between two DP calls is a few microseconds per
+// worker, while every additional thread adds small concurrent launches that queue behind each other.
 int host_threads() {
     const char* e = getenv("LB2_HOST_THREADS");
-    int v = e && *e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    int v = e && *e ? atoi(e) : std::min(4, (int)std::thread::hardware_concurrency());
     if (v < 1) v = 1;
     return v > 64 ? 64 : v;
 }

@@ -23,12 +23,15 @@ using namespace lb2::sdp;
 namespace {
 template <class T> struct DevBuf {
     T* p = nullptr; size_t cap = 0;
+    // geometric growth with a floor: cudaMalloc / cudaFree synchronise the device, and a producer that
+    // reloads one batch object again and again must stop allocating after warm-up
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
+        const size_t want = std::max(std::max(n + n / 4, cap * 2), (size_t)4096 / sizeof(T) + 1);
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
-        if (e == cudaSuccess) cap = std::max<size_t>(n, 1);
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
