@@ -145,12 +145,29 @@ extern "C" int lb2_ctx_create(int device, lb2_ctx** out) {
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
     if (device < 0 || device >= ndev) return fail("lb2_ctx_create: device %d of %d", device, ndev);
     CU(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return fail("lb2_ctx_create: device %d is sm_%d%d, need sm_100", device, prop.major, prop.minor);
+    // per-device facts and the one-time kernel attributes are looked up once per process: a batch producer
+    // opens many contexts (fiber_sched.cu), and cudaGetDeviceProperties / cudaFuncSetAttribute are slow
+    static std::mutex dev_mu;
+    static int dev_major[64], dev_minor[64], dev_sms[64];
+    static bool dev_known[64] = {false};
+    {
+        std::lock_guard<std::mutex> lk(dev_mu);
+        if (device >= 64) return fail("lb2_ctx_create: device %d", device);
+        if (!dev_known[device]) {
+            CU(cudaDeviceGetAttribute(&dev_major[device], cudaDevAttrComputeCapabilityMajor, device));
+            CU(cudaDeviceGetAttribute(&dev_minor[device], cudaDevAttrComputeCapabilityMinor, device));
+            CU(cudaDeviceGetAttribute(&dev_sms[device], cudaDevAttrMultiProcessorCount, device));
+            if (dev_major[device] >= 10)
+                for (int kind = 0; kind < 2; ++kind)
+                    for (int var = 0; var < kNumVar; ++var)
+                        CU(cudaFuncSetAttribute(fill_table(kind, var), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+            dev_known[device] = true;
+        }
+    }
+    if (dev_major[device] < 10) return fail("lb2_ctx_create: device %d is sm_%d%d, need sm_100", device, dev_major[device], dev_minor[device]);
     lb2_ctx* c = new lb2_ctx();
     c->device = device;
-    c->sm_count = prop.multiProcessorCount;
+    c->sm_count = dev_sms[device];
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
     for (int k = 0; k < lb2_ctx::kAux; ++k) {
@@ -161,9 +178,6 @@ extern "C" int lb2_ctx_create(int device, lb2_ctx** out) {
     size_t fr = 0, tot = 0;
     CU(cudaMemGetInfo(&fr, &tot));
     c->scratch_limit = (uint64_t)(fr * 0.40);
-    for (int kind = 0; kind < 2; ++kind)
-        for (int var = 0; var < kNumVar; ++var)
-            CU(cudaFuncSetAttribute(fill_table(kind, var), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
     *out = c;
     return 0;
 }

@@ -52,7 +52,7 @@ struct Sched {                       // one per OS thread
     std::vector<Fiber*> staged;
     int index = 0;
     int64_t switches = 0, flushes = 0, dp_tasks = 0, sdp_reqs = 0, max_dp = 0, slow_batches = 0, slow_tasks = 0;
-    double gpu_s = 0;
+    double gpu_s = 0, ctx_s = 0, sdp_s = 0, submit_s = 0, wait_s = 0;
 };
 thread_local Sched* tl_sched = nullptr;
 
@@ -132,6 +132,7 @@ void finish_at(Sched* s, size_t i) {                 // waits if the batch is st
 void flush(Sched* s) {
     const auto t0 = std::chrono::steady_clock::now();
     if (!s->sdp_wait.empty()) {                      // chaining: two calls per read, served at once
+        const auto ts0 = std::chrono::steady_clock::now();
         for (int stage = 1; stage <= 2; ++stage) {
             std::vector<lb2::SdpRequest*> grp;
             for (lb2::SdpRequest* q : s->sdp_wait) if (q->stage == stage) grp.push_back(q);
@@ -140,6 +141,7 @@ void flush(Sched* s) {
         for (Fiber* f : s->sdp_owner) s->runnable.push_back(f);
         s->sdp_reqs += (int64_t)s->sdp_wait.size();
         s->sdp_wait.clear(); s->sdp_owner.clear();
+        s->sdp_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - ts0).count();
     }
     const int lim = fast_rows();
     for (size_t i = 0; i < s->dp_wait.size(); ++i) {
@@ -148,18 +150,24 @@ void flush(Sched* s) {
         (slow ? s->slow_owner : s->fast_owner).push_back(s->dp_owner[i]);
     }
     s->dp_wait.clear(); s->dp_owner.clear();
+    const auto tb0 = std::chrono::steady_clock::now();
     submit_group(s, s->fast_wait, s->fast_owner, false);
     submit_group(s, s->slow_wait, s->slow_owner, true);
+    const auto tb1 = std::chrono::steady_clock::now();
+    s->submit_s += std::chrono::duration<double>(tb1 - tb0).count();
     for (size_t i = 0; i < s->inflight.size();)      // reap what is ready
         if (lb2::dropin_dp_async_done(s->inflight[i].a)) finish_at(s, i); else ++i;
     if (s->runnable.empty() && !s->staged.empty()) { s->runnable.swap(s->staged); }   // second half of the workers starts now
     if (s->runnable.empty() && !s->inflight.empty()) finish_at(s, 0);                  // wait for the oldest batch
+    s->wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - tb1).count();
     s->gpu_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 void run_scheduler(Sched* s) {
     tl_sched = s;
+    const auto tc0 = std::chrono::steady_clock::now();
     lb2::dropin_use_thread_ctx(s->index);
+    s->ctx_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count();
     size_t live = s->fibers.size();
     // s->fibers is in reverse worker order (the run queue pops from the back)
     const size_t half = s->fibers.size() / 2;
@@ -194,14 +202,15 @@ void run_all(std::vector<Fiber*>& fibers) {
     run_scheduler(&scheds[0]);
     for (auto& t : th) t.join();
     if (g_verbose()) {
-        int64_t sw = 0, fl = 0, dp = 0, sd = 0, mx = 0, sb = 0, stt = 0; double g = 0;
-        for (Sched& s : scheds) { sw += s.switches; fl += s.flushes; dp += s.dp_tasks; sd += s.sdp_reqs; mx = std::max(mx, s.max_dp); g = std::max(g, s.gpu_s);
+        int64_t sw = 0, fl = 0, dp = 0, sd = 0, mx = 0, sb = 0, stt = 0; double g = 0, cx = 0, ss = 0, su = 0, wa = 0;
+        for (Sched& s : scheds) { cx = std::max(cx, s.ctx_s); ss = std::max(ss, s.sdp_s); su = std::max(su, s.submit_s); wa = std::max(wa, s.wait_s);
+                                  sw += s.switches; fl += s.flushes; dp += s.dp_tasks; sd += s.sdp_reqs; mx = std::max(mx, s.max_dp); g = std::max(g, s.gpu_s);
                                   sb += s.slow_batches; stt += s.slow_tasks; }
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         fprintf(stderr, "[lamsa_b200] %zu workers on %d threads: %.3f s, %lld rounds (%.0f per thread), %lld DP tasks (%.0f per launch, max %lld), "
-                        "%lld long DP tasks in %lld side batches, %lld chaining requests, %lld switches, %.3f s inside GPU submissions (slowest thread)\n",
+                        "%lld long DP tasks in %lld side batches, %lld chaining requests, %lld switches, %.3f s inside GPU submissions (slowest thread; max per thread: contexts %.3f, chaining %.3f, DP submit %.3f, DP wait %.3f)\n",
                 fibers.size(), K, wall, (long long)fl, (double)fl / K, (long long)dp, fl ? (double)dp / fl : 0.0, (long long)mx,
-                (long long)stt, (long long)sb, (long long)sd, (long long)sw, g);
+                (long long)stt, (long long)sb, (long long)sd, (long long)sw, g, cx, ss, su, wa);
     }
     for (Fiber* f : fibers) delete f;
     fibers.clear();
