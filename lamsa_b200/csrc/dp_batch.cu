@@ -300,8 +300,11 @@ static int pick_variant(const lb2_task& t, int w, long ncol, int logS) {
     if (force_gmem || warp_smem_bytes16(S_) > kMaxDynSmem) return kVarGmem;   // window beyond shared memory
     static const int use16 = env_int("LB2_P16", 1), p16_min = env_int("LB2_P16_MIN", 37),
                      np4_min = env_int("LB2_NP4_MIN", 200), np4_min_ext = env_int("LB2_NP4_MIN_EXT", 1000000);
-    // narrow bands (the short interval fills of real reads) run 4 tasks per warp
-    static const int sub_l = env_int("LB2_SUBWARP", 8), sub_max_ext = env_int("LB2_SUBWARP_MAX_EXT", 73),
+    // narrow bands (the short interval fills of real reads) run 4 tasks per warp; so does every extension
+    // whose static band is below 410 columns: its LIVE band (src/ksw.c:775-778) is a few dozen columns wide,
+    // and the 32-column tiles of an 8-lane group follow it with less idle lanes than 128-column warp tiles
+    // (1 M-task C2: 437 vs 423 GCUPS, tools/kernel_probe.py)
+    static const int sub_l = env_int("LB2_SUBWARP", 8), sub_max_ext = env_int("LB2_SUBWARP_MAX_EXT", 410),
                      sub_max_glb = env_int("LB2_SUBWARP_MAX_GLB", 73);
     if (use16 && fits_int16(t, w)) {
         const bool wide = ncol >= (t.kind == LB2_KIND_EXTEND ? np4_min_ext : np4_min);
