@@ -51,7 +51,7 @@ struct Sched {                       // one per OS thread
     bool slot_busy[lb2::kAsyncSlots] = {false};
     std::vector<Fiber*> staged;
     int index = 0;
-    int64_t switches = 0, flushes = 0, dp_tasks = 0, sdp_reqs = 0, max_dp = 0, slow_batches = 0, slow_tasks = 0;
+    int64_t switches = 0, flushes = 0, dp_tasks = 0, sdp_reqs = 0, max_dp = 0, slow_batches = 0, slow_tasks = 0, sdp_batches = 0;
     double gpu_s = 0, ctx_s = 0, sdp_s = 0, submit_s = 0, wait_s = 0;
 };
 thread_local Sched* tl_sched = nullptr;
@@ -64,12 +64,16 @@ size_t stack_bytes() {
     static const size_t v = [] { const char* e = getenv("LB2_FIBER_STACK_KB"); return (size_t)(e && *e ? atol(e) : 1024) * 1024; }();
     return v;
 }
-// scheduler threads.  Measured on the 16-thread B200 host (profiles/r01_lamsa_whole_program.jsonl):
-// 4 threads beat 8 and 16 -- the host control flow between two DP calls is a few microseconds per
-// worker, while every additional thread adds small concurrent launches that queue behind each other.
+// scheduler threads: two per GPU unless LB2_HOST_THREADS says otherwise.  Measured on a 16-thread B200
+// host, steady-state chunk of 4 096 reads x 5 kbp (profiles/r01_lamsa_whole_program_fibers.jsonl): 1 thread
+// 0.58 s (host control flow of all workers on one core), 2 threads 0.38 s, 3 threads 0.44 s, 4 threads 0.62 s
+// (time moves into waiting for DP batches: many small concurrent launches of one GPU queue behind each
+// other); 4 threads over 2 GPUs 0.27 s.
 int host_threads() {
     const char* e = getenv("LB2_HOST_THREADS");
-    int v = e && *e ? atoi(e) : std::min(4, (int)std::thread::hardware_concurrency());
+    const char* d = getenv("LB2_DEVICES");
+    const int ndev = d && *d && atoi(d) > 0 ? atoi(d) : 1;
+    int v = e && *e ? atoi(e) : std::min(2 * ndev, (int)std::thread::hardware_concurrency());
     if (v < 1) v = 1;
     return v > 64 ? 64 : v;
 }
@@ -131,12 +135,16 @@ void finish_at(Sched* s, size_t i) {                 // waits if the batch is st
 // nothing can run: submit, reap, wait
 void flush(Sched* s) {
     const auto t0 = std::chrono::steady_clock::now();
-    if (!s->sdp_wait.empty()) {                      // chaining: two calls per read, served at once
+    // chaining requests (two per read) are synchronous batches: worth a launch when enough of them have
+    // gathered, or when there is no DP work to overlap with; until then their owners stay parked
+    static const size_t sdp_min = [] { const char* e = getenv("LB2_SDP_MIN_BATCH"); return (size_t)(e && *e ? atoi(e) : 64); }();
+    const bool other_work = !s->dp_wait.empty() || !s->fast_wait.empty() || !s->slow_wait.empty() || !s->inflight.empty() || !s->staged.empty();
+    if (!s->sdp_wait.empty() && (s->sdp_wait.size() >= sdp_min || !other_work)) {
         const auto ts0 = std::chrono::steady_clock::now();
         for (int stage = 1; stage <= 2; ++stage) {
             std::vector<lb2::SdpRequest*> grp;
             for (lb2::SdpRequest* q : s->sdp_wait) if (q->stage == stage) grp.push_back(q);
-            if (!grp.empty()) lb2::dropin_submit_sdp(grp);
+            if (!grp.empty()) { lb2::dropin_submit_sdp(grp); ++s->sdp_batches; }
         }
         for (Fiber* f : s->sdp_owner) s->runnable.push_back(f);
         s->sdp_reqs += (int64_t)s->sdp_wait.size();
@@ -202,15 +210,15 @@ void run_all(std::vector<Fiber*>& fibers) {
     run_scheduler(&scheds[0]);
     for (auto& t : th) t.join();
     if (g_verbose()) {
-        int64_t sw = 0, fl = 0, dp = 0, sd = 0, mx = 0, sb = 0, stt = 0; double g = 0, cx = 0, ss = 0, su = 0, wa = 0;
+        int64_t sw = 0, fl = 0, dp = 0, sd = 0, mx = 0, sb = 0, stt = 0, sdb = 0; double g = 0, cx = 0, ss = 0, su = 0, wa = 0;
         for (Sched& s : scheds) { cx = std::max(cx, s.ctx_s); ss = std::max(ss, s.sdp_s); su = std::max(su, s.submit_s); wa = std::max(wa, s.wait_s);
                                   sw += s.switches; fl += s.flushes; dp += s.dp_tasks; sd += s.sdp_reqs; mx = std::max(mx, s.max_dp); g = std::max(g, s.gpu_s);
-                                  sb += s.slow_batches; stt += s.slow_tasks; }
+                                  sb += s.slow_batches; stt += s.slow_tasks; sdb += s.sdp_batches; }
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         fprintf(stderr, "[lamsa_b200] %zu workers on %d threads: %.3f s, %lld rounds (%.0f per thread), %lld DP tasks (%.0f per launch, max %lld), "
-                        "%lld long DP tasks in %lld side batches, %lld chaining requests, %lld switches, %.3f s inside GPU submissions (slowest thread; max per thread: contexts %.3f, chaining %.3f, DP submit %.3f, DP wait %.3f)\n",
+                        "%lld long DP tasks in %lld side batches, %lld chaining requests in %lld batches, %lld switches, %.3f s inside GPU submissions (slowest thread; max per thread: contexts %.3f, chaining %.3f, DP submit %.3f, DP wait %.3f)\n",
                 fibers.size(), K, wall, (long long)fl, (double)fl / K, (long long)dp, fl ? (double)dp / fl : 0.0, (long long)mx,
-                (long long)stt, (long long)sb, (long long)sd, (long long)sw, g, cx, ss, su, wa);
+                (long long)stt, (long long)sb, (long long)sd, (long long)sdb, (long long)sw, g, cx, ss, su, wa);
     }
     for (Fiber* f : fibers) delete f;
     fibers.clear();
