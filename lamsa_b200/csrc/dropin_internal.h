@@ -12,6 +12,7 @@ lb2_ctx* dropin_ctx();                       // the context of the drop-in symbo
                                              // (dropin_use_thread_ctx) or else the process-wide one
 // give the calling OS thread a context of its own (scheduler thread `index`: GPU index mod #GPUs)
 void dropin_use_thread_ctx(int index);
+bool dropin_has_thread_ctx();                // false: the caller shares the process-wide context with other threads
 
 // one blocked banded-DP call (ksw_dropin.cu)
 struct DpRequest {

@@ -42,6 +42,7 @@ lb2_ctx* default_ctx() {
 
 }  // namespace
 namespace lb2 { lb2_ctx* dropin_ctx() { return default_ctx(); } }   // shared with sdp_dropin.cu
+bool lb2::dropin_has_thread_ctx() { return tl_ctx != nullptr; }
 void lb2::dropin_use_thread_ctx(int index) {
     if (tl_ctx) return;
     // scheduler threads are re-created per read chunk; their contexts are kept by index

@@ -157,7 +157,11 @@ void serve(lb2::SdpRequest* r) {
 // grow-only batch object, so steady state allocates nothing.
 void lb2::dropin_submit_sdp(std::vector<lb2::SdpRequest*>& batch) {
     if (batch.empty()) return;
-    // one grow-only batch object per context (= per scheduler thread, or the process-wide one)
+    // one grow-only batch object per context (= per scheduler thread, or the process-wide one, which the
+    // reference's pthread workers share: those calls are serialised here, like the DP calls in ksw_dropin.cu)
+    static std::mutex shared_ctx_mu;
+    std::unique_lock<std::mutex> serial(shared_ctx_mu, std::defer_lock);
+    if (!lb2::dropin_has_thread_ctx()) serial.lock();
     static std::mutex batch_mu;
     static std::unordered_map<lb2_ctx*, lb2_sdp_batch*> batch_of;
     lb2_ctx* const my_ctx = lb2::dropin_ctx();
