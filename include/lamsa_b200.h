@@ -225,7 +225,7 @@ int  lb2_dp_run(lb2_ctx *ctx, int64_t n, const lb2_task *tasks, lb2_result *resu
                 cigar32_t **cigar_pool, int64_t *cigar_pool_n);
 
 /* lb2_dp_run cuts batches into chunks of about this many tasks and pipelines host packing,
- * H2D and kernels across them (default 262144; at most 16 chunks) */
+ * H2D, kernels and read-backs across them (default 131072; at most 16 chunks) */
 int  lb2_ctx_set_chunk_tasks(lb2_ctx *ctx, int64_t tasks);
 /* byte / launch counters of the last lb2_dp_run on this context */
 int  lb2_ctx_last_run_stats(const lb2_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes, int64_t *launches);

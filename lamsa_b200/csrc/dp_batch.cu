@@ -101,7 +101,7 @@ struct lb2_ctx {
     cudaStream_t copy = nullptr;                        // H2D of batch k+1 overlaps the kernels of batch k
     int64_t run_h2d = 0, run_d2h = 0, run_launches = 0; // counters of the last lb2_dp_run
     float run_fill_ms = 0, run_trace_ms = 0;
-    int64_t chunk_tasks = 262144;                       // lb2_dp_run pipelines chunks of about this many tasks
+    int64_t chunk_tasks = 131072;                       // lb2_dp_run pipelines chunks of about this many tasks
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     uint64_t scratch_limit = 0;
@@ -741,7 +741,6 @@ static int compute_finish(lb2_batch* b, float* kernel_ms) {
     if (!b || !b->enqueued) return fail("lb2_batch_compute: nothing enqueued");
     lb2_ctx* c = b->ctx;
     CU(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
     CU(cudaEventSynchronize(b->ev[3]));
     float total = 0, fill_acc = 0, trace_acc = 0;
     CU(cudaEventElapsedTime(&total, b->ev[0], b->ev[3]));
@@ -758,9 +757,11 @@ static int compute_finish(lb2_batch* b, float* kernel_ms) {
     }
     b->fill_ms = fill_acc; b->trace_ms = trace_acc;
     if (kernel_ms) *kernel_ms = total;
+    // read-backs go through the COPY stream: the compute stream may already hold the kernels of the next
+    // chunk (lb2_dp_run pipelines chunks), and a copy queued behind them would stall the pipeline
     int err = 0;
-    CU(cudaMemcpyAsync(&err, b->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    CU(cudaMemcpyAsync(&err, b->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->copy));
+    CU(cudaStreamSynchronize(c->copy));
     if (err) return fail("traceback kernel reported CIGAR scratch overflow (code %d)", err);
     b->computed = true;
     b->enqueued = false;
@@ -790,7 +791,7 @@ static int download_impl(lb2_batch* b, lb2_result* results, bool want_cigar, uns
     if (!b->computed) return fail("lb2_batch_download before lb2_batch_compute");
     lb2_ctx* c = b->ctx;
     CU(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->copy;                // see compute_finish: never queue read-backs behind the next chunk's kernels
     unsigned long long used = 0;
     CU(cudaMemcpyAsync(&used, b->d_cursor, sizeof used, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(b->h_results, b->d_results, sizeof(DResult) * std::max<int64_t>(b->n, 1), cudaMemcpyDeviceToHost, s));
