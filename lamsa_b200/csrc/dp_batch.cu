@@ -41,10 +41,10 @@ extern "C" void lb2_free(void* p) { free(p); }
 // A launch class = (kind, variant, S = window slots).
 // variants: 0..2 int32 lanes with G = 1,2,4 columns per lane; 3,4 packed int16 with NP = 2,4 pairs
 // per lane; 5 = int32 G=4 with the window in global memory (does not fit shared memory);
-// 6,7 = packed NP=2 in sub-warp bundles of L = 16 / 8 lanes per task (dp_fill16s.cuh).
+// 6,7 = packed NP=2 in sub-warp bundles of L = 16 / 8 lanes per task (dp_fill16s.cuh); 8, 9 = packed NP=4, L = 8 / 16.
 constexpr int kMinLogS = 6, kMaxLogS = 18;          // 64 .. 262144 slots per warp
 constexpr int kNumLogS = kMaxLogS - kMinLogS + 1;
-constexpr int kNumVar = 8;
+constexpr int kNumVar = 10;
 constexpr int kVarGmem = 5;
 constexpr int kNumClass = 2 * kNumVar * kNumLogS;
 constexpr size_t kMaxDynSmem = 200 * 1024;
@@ -52,9 +52,9 @@ static inline int class_id(int kind, int var, int logS) { return (kind * kNumVar
 static inline int class_kind(int c) { return c / (kNumVar * kNumLogS); }
 static inline int class_var(int c) { return (c / kNumLogS) % kNumVar; }
 static inline int class_logS(int c) { return c % kNumLogS + kMinLogS; }
-static inline int var_gshift(int var) { return var == kVarGmem || var >= 6 ? 2 : var < 3 ? var : var - 1; }     // log2(columns per lane)
+static inline int var_gshift(int var) { return var >= 8 ? 3 : var == kVarGmem || var >= 6 ? 2 : var < 3 ? var : var - 1; }     // log2(columns per lane)
 static inline bool var_packed(int var) { return var == 3 || var == 4 || var >= 6; }
-static inline int var_tasks_per_warp(int var) { return var == 6 ? 2 : var == 7 ? 4 : 1; }
+static inline int var_tasks_per_warp(int var) { return var == 6 || var == 9 ? 2 : var >= 7 ? 4 : 1; }
 static inline size_t var_warp_smem(int var, int S) {
     return var_packed(var) ? warp_smem_bytes16(S) * var_tasks_per_warp(var) : warp_smem_bytes(S);
 }
@@ -125,14 +125,16 @@ static fill_fn fill_table(int kind, int var) {
             case 0: return fill_kernel<1, kKindGlobal, false>;   case 1: return fill_kernel<2, kKindGlobal, false>;
             case 2: return fill_kernel<4, kKindGlobal, false>;   case 3: return fill16_kernel<2, kKindGlobal>;
             case 4: return fill16_kernel<4, kKindGlobal>;        case 5: return fill_kernel<4, kKindGlobal, true>;
-            case 6: return fill16s_kernel<2, kKindGlobal, 16>;   default: return fill16s_kernel<2, kKindGlobal, 8>;
+            case 6: return fill16s_kernel<2, kKindGlobal, 16>;   case 7: return fill16s_kernel<2, kKindGlobal, 8>;
+            case 8: return fill16s_kernel<4, kKindGlobal, 8>;    default: return fill16s_kernel<4, kKindGlobal, 16>;
         }
     }
     switch (var) {
         case 0: return fill_kernel<1, kKindExtend, false>;   case 1: return fill_kernel<2, kKindExtend, false>;
         case 2: return fill_kernel<4, kKindExtend, false>;   case 3: return fill16_kernel<2, kKindExtend>;
         case 4: return fill16_kernel<4, kKindExtend>;        case 5: return fill_kernel<4, kKindExtend, true>;
-        case 6: return fill16s_kernel<2, kKindExtend, 16>;   default: return fill16s_kernel<2, kKindExtend, 8>;
+        case 6: return fill16s_kernel<2, kKindExtend, 16>;   case 7: return fill16s_kernel<2, kKindExtend, 8>;
+        case 8: return fill16s_kernel<4, kKindExtend, 8>;    default: return fill16s_kernel<4, kKindExtend, 16>;
     }
 }
 
@@ -309,6 +311,13 @@ static int pick_variant(const lb2_task& t, int w, long ncol, int logS) {
     if (use16 && fits_int16(t, w)) {
         const bool wide = ncol >= (t.kind == LB2_KIND_EXTEND ? np4_min_ext : np4_min);
         const int sub_max = t.kind == LB2_KIND_EXTEND ? sub_max_ext : sub_max_glb;
+        // wide bands in 8-lane groups with 8 columns per lane (64-column tiles): LB2_SUB_NP4_MIN_EXT / _GLB
+        static const int sub4_ext = env_int("LB2_SUB_NP4_MIN_EXT", 160), sub4_glb = env_int("LB2_SUB_NP4_MIN_GLB", 1000000);
+        static const int sub16_ext = env_int("LB2_SUB16_NP4_MIN_EXT", 1000000);     // 16-lane groups, 128-column tiles
+        if (sub_l == 8 && t.kind == LB2_KIND_EXTEND && ncol < sub_max && ncol >= sub16_ext &&
+            warp_smem_bytes16(S_) * 2 * 2 <= kMaxDynSmem) return 9;
+        if (sub_l == 8 && ncol < sub_max && ncol >= (t.kind == LB2_KIND_EXTEND ? sub4_ext : sub4_glb) &&
+            warp_smem_bytes16(S_) * 4 * 2 <= kMaxDynSmem) return 8;
         if (sub_l && ncol < sub_max && warp_smem_bytes16(S_) * (32 / sub_l) * 2 <= kMaxDynSmem) return sub_l == 16 ? 6 : 7;
         if (ncol >= p16_min) return wide ? 4 : 3;
     }
