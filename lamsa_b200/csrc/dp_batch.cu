@@ -307,12 +307,12 @@ static int pick_variant(const lb2_task& t, int w, long ncol, int logS) {
     // and the 32-column tiles of an 8-lane group follow it with less idle lanes than 128-column warp tiles
     // (1 M-task C2: 437 vs 423 GCUPS, tools/kernel_probe.py)
     static const int sub_l = env_int("LB2_SUBWARP", 8), sub_max_ext = env_int("LB2_SUBWARP_MAX_EXT", 410),
-                     sub_max_glb = env_int("LB2_SUBWARP_MAX_GLB", 73);
+                     sub_max_glb = env_int("LB2_SUBWARP_MAX_GLB", 200);
     if (use16 && fits_int16(t, w)) {
         const bool wide = ncol >= (t.kind == LB2_KIND_EXTEND ? np4_min_ext : np4_min);
         const int sub_max = t.kind == LB2_KIND_EXTEND ? sub_max_ext : sub_max_glb;
         // wide bands in 8-lane groups with 8 columns per lane (64-column tiles): LB2_SUB_NP4_MIN_EXT / _GLB
-        static const int sub4_ext = env_int("LB2_SUB_NP4_MIN_EXT", 160), sub4_glb = env_int("LB2_SUB_NP4_MIN_GLB", 1000000);
+        static const int sub4_ext = env_int("LB2_SUB_NP4_MIN_EXT", 160), sub4_glb = env_int("LB2_SUB_NP4_MIN_GLB", 100);
         static const int sub16_ext = env_int("LB2_SUB16_NP4_MIN_EXT", 1000000);     // 16-lane groups, 128-column tiles
         if (sub_l == 8 && t.kind == LB2_KIND_EXTEND && ncol < sub_max && ncol >= sub16_ext &&
             warp_smem_bytes16(S_) * 2 * 2 <= kMaxDynSmem) return 9;
