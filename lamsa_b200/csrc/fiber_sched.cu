@@ -64,16 +64,15 @@ size_t stack_bytes() {
     static const size_t v = [] { const char* e = getenv("LB2_FIBER_STACK_KB"); return (size_t)(e && *e ? atol(e) : 1024) * 1024; }();
     return v;
 }
-// scheduler threads: two per GPU unless LB2_HOST_THREADS says otherwise.  Measured on a 16-thread B200
-// host, steady-state chunk of 4 096 reads x 5 kbp (profiles/r01_lamsa_whole_program_fibers.jsonl): 1 thread
-// 0.58 s (host control flow of all workers on one core), 2 threads 0.38 s, 3 threads 0.44 s, 4 threads 0.62 s
-// (time moves into waiting for DP batches: many small concurrent launches of one GPU queue behind each
-// other); 4 threads over 2 GPUs 0.27 s.
+// scheduler threads: four per GPU unless LB2_HOST_THREADS says otherwise.  Measured on a 16-thread B200 host,
+// steady-state chunk of 4 096 reads x 5 kbp, 16+ hardware queues (see lb2_dropin_warmup): 2 threads 0.38 s
+// (bound by the host control flow of 1 024 workers per thread), 4 threads 0.26 s, 8 threads 0.22 s, 16 threads
+// 0.45 s (small launches of 64 contexts contend again).
 int host_threads() {
     const char* e = getenv("LB2_HOST_THREADS");
     const char* d = getenv("LB2_DEVICES");
     const int ndev = d && *d && atoi(d) > 0 ? atoi(d) : 1;
-    int v = e && *e ? atoi(e) : std::min(2 * ndev, (int)std::thread::hardware_concurrency());
+    int v = e && *e ? atoi(e) : std::min(4 * ndev, (int)std::thread::hardware_concurrency());
     if (v < 1) v = 1;
     return v > 64 ? 64 : v;
 }
@@ -104,7 +103,7 @@ void yield_to_scheduler() {
 //    (SURVEY.md appendix C).  Parked tasks are therefore split: tasks of more than LB2_FAST_ROWS
 //    target rows travel in a batch of their own, so the owners of short tasks resume early.
 int fast_rows() {
-    static const int v = [] { const char* e = getenv("LB2_FAST_ROWS"); return e && *e ? atoi(e) : 512; }();
+    static const int v = [] { const char* e = getenv("LB2_FAST_ROWS"); return e && *e ? atoi(e) : 256; }();
     return v;
 }
 
@@ -242,6 +241,7 @@ void fiber_wait_sdp(SdpRequest* r) {
 
 // pthread_create-shaped: registers a worker; it starts when the first of the workers is joined
 extern "C" int lb2_worker_spawn(pthread_t* id, const pthread_attr_t*, void* (*fn)(void*), void* arg) {
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "16", 0);      // see lb2_dropin_warmup; harmless once CUDA is up
     Fiber* f = new Fiber();
     f->fn = fn; f->arg = arg;
     f->stack_bytes = stack_bytes();

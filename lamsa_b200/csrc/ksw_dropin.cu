@@ -104,7 +104,15 @@ void lb2::dropin_dp_async_finish(DpAsync* a) {
     delete a;
 }
 // open the drop-in context from a helper thread (CUDA start-up overlaps the caller's own start-up)
-extern "C" void lb2_dropin_warmup(void) { std::thread([] { default_ctx(); }).detach(); }
+// The batch producer drives tens of streams (4 contexts x 6 streams per scheduler thread).  With the default
+// of 8 hardware work queues they alias, and independent batches queue behind each other (measured, 4 scheduler
+// threads: 0.60 s per chunk of 4 096 reads with 8 queues, 0.27 s with 16, 0.25 s with 32; CUDA start-up grows
+// with the queue count, about +1.5 s / +2.7 s on a cold box).  The variable only counts before CUDA starts,
+// which is why this is the place to set it; an explicit setting in the environment wins.
+extern "C" void lb2_dropin_warmup(void) {
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "16", 0);
+    std::thread([] { default_ctx(); }).detach();
+}
 namespace {
 
 // ---- combining submitter ----------------------------------------------------
