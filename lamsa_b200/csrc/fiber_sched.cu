@@ -64,15 +64,20 @@ size_t stack_bytes() {
     static const size_t v = [] { const char* e = getenv("LB2_FIBER_STACK_KB"); return (size_t)(e && *e ? atol(e) : 1024) * 1024; }();
     return v;
 }
-// scheduler threads: four per GPU unless LB2_HOST_THREADS says otherwise.  Measured on a 16-thread B200 host,
-// steady-state chunk of 4 096 reads x 5 kbp, 16+ hardware queues (see lb2_dropin_warmup): 2 threads 0.38 s
-// (bound by the host control flow of 1 024 workers per thread), 4 threads 0.26 s, 8 threads 0.22 s, 16 threads
-// 0.45 s (small launches of 64 contexts contend again).
+// scheduler threads per GPU unless LB2_HOST_THREADS says otherwise: two with CUDA's default 8 hardware work
+// queues, four when CUDA_DEVICE_MAX_CONNECTIONS >= 16 (see lb2_dropin_warmup in ksw_dropin.cu).  Measured on a
+// 16-thread B200 host, steady-state chunk of 4 096 reads x 5 kbp:
+//    8 queues: 1 thread 0.58 s, 2 threads 0.38 s, 3 threads 0.44 s, 4 threads 0.60 s
+//   16 queues: 4 threads 0.27 s;   32 queues: 4 threads 0.25 s, 8 threads 0.22 s, 16 threads 0.45 s
+// (with few queues the small launches of many contexts serialise; with few threads the host control flow of
+// 1 024 workers per thread is the bound).
 int host_threads() {
     const char* e = getenv("LB2_HOST_THREADS");
     const char* d = getenv("LB2_DEVICES");
+    const char* q = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
     const int ndev = d && *d && atoi(d) > 0 ? atoi(d) : 1;
-    int v = e && *e ? atoi(e) : std::min(4 * ndev, (int)std::thread::hardware_concurrency());
+    const int per_gpu = q && atoi(q) >= 16 ? 4 : 2;
+    int v = e && *e ? atoi(e) : std::min(per_gpu * ndev, (int)std::thread::hardware_concurrency());
     if (v < 1) v = 1;
     return v > 64 ? 64 : v;
 }
@@ -241,7 +246,6 @@ void fiber_wait_sdp(SdpRequest* r) {
 
 // pthread_create-shaped: registers a worker; it starts when the first of the workers is joined
 extern "C" int lb2_worker_spawn(pthread_t* id, const pthread_attr_t*, void* (*fn)(void*), void* arg) {
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "16", 0);      // see lb2_dropin_warmup; harmless once CUDA is up
     Fiber* f = new Fiber();
     f->fn = fn; f->arg = arg;
     f->stack_bytes = stack_bytes();

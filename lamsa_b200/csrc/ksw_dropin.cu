@@ -104,13 +104,15 @@ void lb2::dropin_dp_async_finish(DpAsync* a) {
     delete a;
 }
 // open the drop-in context from a helper thread (CUDA start-up overlaps the caller's own start-up)
-// The batch producer drives tens of streams (4 contexts x 6 streams per scheduler thread).  With the default
-// of 8 hardware work queues they alias, and independent batches queue behind each other (measured, 4 scheduler
-// threads: 0.60 s per chunk of 4 096 reads with 8 queues, 0.27 s with 16, 0.25 s with 32; CUDA start-up grows
-// with the queue count, about +1.5 s / +2.7 s on a cold box).  The variable only counts before CUDA starts,
-// which is why this is the place to set it; an explicit setting in the environment wins.
+// Hardware work queues.  The batch producer drives tens of streams (4 contexts x 6 streams per scheduler
+// thread); with CUDA's default of 8 hardware queues they alias and independent batches queue behind each other.
+// Measured, chunk of 4 096 reads: 4 scheduler threads need 0.60 s with 8 queues, 0.27 s with 16, 0.25 s with
+// 32 -- but CUDA start-up on a cold box grows from about 2 s (8) to 3-5 s (16) and 4.6 s and more (32).  So the
+// default stays at 8 queues with two scheduler threads per GPU (0.38 s per chunk), and long runs export
+// CUDA_DEVICE_MAX_CONNECTIONS=16 (or 32) before starting: fiber_sched.cu then uses four threads per GPU.
+// LB2_MAX_CONNECTIONS=n sets the variable from here (it only counts before CUDA starts).
 extern "C" void lb2_dropin_warmup(void) {
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "16", 0);
+    if (const char* e = getenv("LB2_MAX_CONNECTIONS")) if (*e) setenv("CUDA_DEVICE_MAX_CONNECTIONS", e, 0);
     std::thread([] { default_ctx(); }).detach();
 }
 namespace {
