@@ -109,6 +109,9 @@ def load_library():
     lib.lb2_batch_create.argtypes = [P, I64, P, C.POINTER(P)]
     lib.lb2_batch_upload.argtypes = [P]
     lib.lb2_batch_compute.argtypes = [P, C.POINTER(C.c_float)]
+    lib.lb2_batch_compute_async.argtypes = [P]
+    lib.lb2_batch_compute_done.argtypes = [P]
+    lib.lb2_batch_compute_wait.argtypes = [P, C.POINTER(C.c_float)]
     lib.lb2_batch_download.argtypes = [P, P, C.POINTER(P), C.POINTER(I64)]
     lib.lb2_batch_download_view.argtypes = [P, P, C.POINTER(P), C.POINTER(I64)]
     lib.lb2_batch_stats.argtypes = [P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64),

@@ -120,6 +120,20 @@ class Batch:
             raise _err(self.lib, "lb2_batch_compute")
         return ms.value
 
+    def compute_async(self):
+        """Enqueue the kernels and return (lb2_batch_compute_async); pair with done() / wait()."""
+        if self.lib.lb2_batch_compute_async(self.handle):
+            raise _err(self.lib, "lb2_batch_compute_async")
+
+    def done(self):
+        return bool(self.lib.lb2_batch_compute_done(self.handle))
+
+    def wait(self):
+        ms = C.c_float()
+        if self.lib.lb2_batch_compute_wait(self.handle, C.byref(ms)):
+            raise _err(self.lib, "lb2_batch_compute_wait")
+        return ms.value
+
     def download(self, want_cigar=True, copy=True):
         """-> (results, cigar words).  copy=False returns a view into the batch's pinned
         staging (valid until close() or the next download)."""

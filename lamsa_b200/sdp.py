@@ -29,6 +29,9 @@ def _bind(lib):
     lib.lb2_sdp_run_bcc.argtypes = [P, C.POINTER(P), C.POINTER(P), C.POINTER(C.c_float)]
     lib.lb2_sdp_run_remain.argtypes = [P, P, P, C.POINTER(P), C.POINTER(P), C.POINTER(C.c_float)]
     lib.lb2_sdp_stats.argtypes = [P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64)]
+    lib.lb2_sdp_get_tracked.argtypes = [P, P]
+    lib.lb2_sdp_set_tracked.argtypes = [P, P]
+    lib.lb2_sdp_reset.argtypes = [P, P, I64, P, P, P, P]
     lib.lb2_sdp_destroy.argtypes = [P]
     lib.lb2_sdp_destroy.restype = None
     lib._sdp_bound = True
@@ -55,6 +58,8 @@ class SdpBatch:
             raise RuntimeError("lb2_sdp_create: " + self.lib.lb2_last_error().decode())
         self.handle = h
         self.kernel_ms = 0.0
+        # hits of the batch, in batch order (the reads may reference the arrays in any order)
+        self._map_n_sum = [int(map_n[int(r["seed_first"]):int(r["seed_first"]) + int(r["seed_out"])].sum()) for r in self.reads]
 
     def _result(self, sp, op):
         n = len(self.reads)
@@ -83,6 +88,20 @@ class SdpBatch:
             raise RuntimeError("lb2_sdp_run_remain: " + self.lib.lb2_last_error().decode())
         self.kernel_ms = ms.value
         return self._result(sp, op)
+
+    def get_tracked(self):
+        """One flag per hit (batch order): on a stage-1 skeleton.  Call after run_bcc()."""
+        n = int(sum(int(m) for m in self._map_n_sum))
+        flags = np.zeros(n, np.uint8)
+        if self.lib.lb2_sdp_get_tracked(self.handle, flags.ctypes.data if n else None):
+            raise RuntimeError("lb2_sdp_get_tracked: " + self.lib.lb2_last_error().decode())
+        return flags
+
+    def set_tracked(self, flags):
+        """Load the stage-1 flags into a batch that did not run stage 1 itself, then run_remain()."""
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        if self.lib.lb2_sdp_set_tracked(self.handle, flags.ctypes.data if len(flags) else None):
+            raise RuntimeError("lb2_sdp_set_tracked: " + self.lib.lb2_last_error().decode())
 
     def stats(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

@@ -69,3 +69,27 @@ def test_gpu_sdp_degenerate(ctx):
     empty = rs.subset(np.zeros(0, np.int64))
     e1, e2, _ = gpu_run(ctx, empty)
     assert len(e1[0]) == 0 and len(e2[0]) == 0
+
+
+def test_gpu_sdp_stage2_on_a_regrouped_batch(ctx):
+    """lb2_sdp_get_tracked / _set_tracked: stage 2 on a batch object that never ran stage 1, holding a
+    permuted subset of the reads (what the batch producer does when reads reach stage 2 at different times)"""
+    from lamsa_b200.sdp import SdpBatch
+    rs = _sdp.gen_reads(300, seed=31, mode="pacbio", repeat_frac=0.3, sv_rate=0.5, miss_frac=0.2, read_len=(500, 9000))
+    o1, o2, _ = _sdp.oracle_run(rs)
+    a = SdpBatch(ctx, rs.para, rs.reads, rs.seed_id, rs.map_n, rs.hits)
+    g1 = a.run_bcc()
+    flags = a.get_tracked()
+    a.close()
+    assert not _sdp.diff_streams(g1, o1, "stage1")
+    hit_first = np.concatenate(([0], np.cumsum([int(rs.map_n[int(r["seed_first"]):int(r["seed_first"]) + int(r["seed_out"])].sum())
+                                                for r in rs.reads])))
+    pick = np.random.default_rng(2).permutation(len(rs))[:173]
+    sub = rs.subset(pick)
+    sub_flags = np.concatenate([flags[hit_first[i]:hit_first[i + 1]] for i in pick])
+    b = SdpBatch(ctx, sub.para, sub.reads, sub.seed_id, sub.map_n, sub.hits)
+    b.set_tracked(sub_flags)
+    s2, f2 = b.run_remain(sub.reads, sub.regs)
+    b.close()
+    for k, i in enumerate(pick):
+        assert np.array_equal(s2[f2[k]:f2[k + 1]], o2[0][o2[1][i]:o2[1][i + 1]]), (k, i)
