@@ -58,6 +58,17 @@ def test_gpu_sdp_matches_oracle_random(ctx, mode, seed, rf, sv, miss, n):
     assert tuple(int(v) for v in opairs) == gpairs        # same number of edge classifications in the scans
 
 
+def test_gpu_sdp_repeat_heavy_reads(ctx):
+    """up to per_aln_m = 200 hits per seed on most seeds (thousands of nodes per read): scratch bounds,
+    long predecessor scans, big son lists, many skeletons per cluster"""
+    rs = _sdp.gen_reads(25, seed=50, mode="default", repeat_frac=0.9, sv_rate=0.5, miss_frac=0.1, max_hits=200, read_len=(2000, 9000))
+    o1, o2, opairs = _sdp.oracle_run(rs)
+    g1, g2, gpairs = gpu_run(ctx, rs)
+    bad = _sdp.diff_streams(g1, o1, "stage1") + _sdp.diff_streams(g2, o2, "stage2")
+    assert not bad, "\n".join(bad)
+    assert tuple(int(v) for v in opairs) == gpairs
+
+
 def test_gpu_sdp_degenerate(ctx):
     para = _sdp.default_para()
     reads = np.array([(0, 20, 2050, 0, 0, 0, 0), (1, 20, 2050, 0, 0, 0, 0), (2, 3, 300, 0, 1, 1, 0)], dtype=_sdp.READ_DTYPE)
