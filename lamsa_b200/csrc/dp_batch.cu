@@ -327,7 +327,10 @@ static int pick_variant(const lb2_task& t, int w, long ncol, int logS) {
         // wide bands in 8-lane groups with 8 columns per lane (64-column tiles): LB2_SUB_NP4_MIN_EXT / _GLB
         static const int sub4_ext = env_int("LB2_SUB_NP4_MIN_EXT", 160), sub4_glb = env_int("LB2_SUB_NP4_MIN_GLB", 100);
         static const int sub16_ext = env_int("LB2_SUB16_NP4_MIN_EXT", 1000000);     // 16-lane groups, 128-column tiles
+        static const int sub16_glb = env_int("LB2_SUB16_NP4_MIN_GLB", 1000000), sub16_glb_max = env_int("LB2_SUB16_NP4_MAX_GLB", 1000000);
         if (sub_l == 8 && t.kind == LB2_KIND_EXTEND && ncol < sub_max && ncol >= sub16_ext &&
+            warp_smem_bytes16(S_) * 2 * 2 <= kMaxDynSmem) return 9;
+        if (sub_l == 8 && t.kind == LB2_KIND_GLOBAL && ncol >= sub16_glb && ncol < sub16_glb_max &&
             warp_smem_bytes16(S_) * 2 * 2 <= kMaxDynSmem) return 9;
         if (sub_l == 8 && ncol < sub_max && ncol >= (t.kind == LB2_KIND_EXTEND ? sub4_ext : sub4_glb) &&
             warp_smem_bytes16(S_) * 4 * 2 <= kMaxDynSmem) return 8;
