@@ -350,6 +350,9 @@ void lb2_sdp_destroy(lb2_sdp_batch *b);
  */
 int lb2_worker_spawn(pthread_t *id, const pthread_attr_t *attr, void *(*fn)(void *), void *arg);
 int lb2_worker_join(pthread_t id, void **ret);
+/* Self test of the worker scheduler and its context switch without a GPU: n workers yielding `yields`
+ * times each on `threads` scheduler threads; returns the number of workers with a wrong result (0 = pass). */
+int lb2_fiber_selftest(int n, int yields, int threads);
 /* Opens the process-wide context of the drop-in entry points from a helper thread, so that CUDA
  * start-up overlaps the caller's own start-up (index loading).  Optional. */
 void lb2_dropin_warmup(void);

@@ -30,8 +30,20 @@
 
 namespace {
 
+#if defined(__x86_64__) && !defined(LB2_FIBER_UCONTEXT)
+#define LB2_FAST_SWITCH 1
+extern "C" void lb2_fiber_swap(void** save_sp, void* load_sp);      // fiber_switch.cpp
+extern "C" void lb2_fiber_entry_thunk(void);
+#else
+#define LB2_FAST_SWITCH 0
+#endif
+
 struct Fiber {
+#if LB2_FAST_SWITCH
+    void* sp = nullptr;                  // saved stack pointer while the fiber is not running
+#else
     ucontext_t ctx;
+#endif
     void* stack = nullptr; size_t stack_bytes = 0;
     void* (*fn)(void*) = nullptr; void* arg = nullptr;
     bool done = false;
@@ -40,7 +52,11 @@ struct Fiber {
 struct InFlight { lb2::DpAsync* a = nullptr; std::vector<Fiber*> owners; int slot = 0; };
 
 struct Sched {                       // one per OS thread
+#if LB2_FAST_SWITCH
+    void* main_sp = nullptr;
+#else
     ucontext_t main;
+#endif
     Fiber* cur = nullptr;
     std::vector<Fiber*> fibers, runnable;
     std::vector<lb2::DpRequest*> dp_wait;   std::vector<Fiber*> dp_owner;
@@ -71,7 +87,10 @@ size_t stack_bytes() {
 //   16 queues: 4 threads 0.27 s;   32 queues: 4 threads 0.25 s, 8 threads 0.22 s, 16 threads 0.45 s
 // (with few queues the small launches of many contexts serialise; with few threads the host control flow of
 // 1 024 workers per thread is the bound).
+bool g_selftest = false;              // lb2_fiber_selftest: no GPU contexts, workers yield through selftest_yield
+int g_selftest_threads = 0;
 int host_threads() {
+    if (g_selftest_threads > 0) return g_selftest_threads;
     const char* e = getenv("LB2_HOST_THREADS");
     const char* d = getenv("LB2_DEVICES");
     const char* q = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
@@ -82,18 +101,25 @@ int host_threads() {
     return v > 64 ? 64 : v;
 }
 
+#if LB2_FAST_SWITCH
+inline void switch_to_fiber(Sched* s, Fiber* f) { lb2_fiber_swap(&s->main_sp, f->sp); }
+inline void switch_to_sched(Sched* s, Fiber* f) { lb2_fiber_swap(&f->sp, s->main_sp); }
+#else
 void trampoline(unsigned lo, unsigned hi) {
     Fiber* f = (Fiber*)(((uintptr_t)hi << 32) | (uintptr_t)lo);
     f->fn(f->arg);
     f->done = true;
     swapcontext(&f->ctx, &tl_sched->main);       // never resumed
 }
+inline void switch_to_fiber(Sched* s, Fiber* f) { swapcontext(&s->main, &f->ctx); }
+inline void switch_to_sched(Sched* s, Fiber* f) { swapcontext(&f->ctx, &s->main); }
+#endif
 
 void yield_to_scheduler() {
     Sched* s = tl_sched;
     Fiber* f = s->cur;
     ++s->switches;
-    swapcontext(&f->ctx, &s->main);
+    switch_to_sched(s, f);
 }
 
 // ---- rounds ------------------------------------------------------------------------------
@@ -178,7 +204,7 @@ void flush(Sched* s) {
 void run_scheduler(Sched* s) {
     tl_sched = s;
     const auto tc0 = std::chrono::steady_clock::now();
-    lb2::dropin_use_thread_ctx(s->index);
+    if (!g_selftest) lb2::dropin_use_thread_ctx(s->index);
     s->ctx_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count();
     size_t live = s->fibers.size();
     // s->fibers is in reverse worker order (the run queue pops from the back)
@@ -188,7 +214,7 @@ void run_scheduler(Sched* s) {
         while (!s->runnable.empty()) {
             Fiber* f = s->runnable.back(); s->runnable.pop_back();
             s->cur = f;
-            swapcontext(&s->main, &f->ctx);
+            switch_to_fiber(s, f);
             s->cur = nullptr;
             if (f->done) { --live; munmap(f->stack, f->stack_bytes); f->stack = nullptr; }
         }
@@ -244,6 +270,57 @@ void fiber_wait_sdp(SdpRequest* r) {
 }
 }  // namespace lb2
 
+#if LB2_FAST_SWITCH
+extern "C" void lb2_fiber_main(void* p) {                 // entered once per fiber from lb2_fiber_entry_thunk
+    Fiber* f = (Fiber*)p;
+    f->fn(f->arg);
+    f->done = true;
+    switch_to_sched(tl_sched, f);                          // never resumed
+    abort();
+}
+#endif
+
+// ---- self test of the scheduler and the context switch (no GPU needed; tests/test_fibers.py) ----------
+namespace {
+struct SelfTestArg { int id, yields; double result; long long sum; };
+void selftest_yield() {               // give the other workers of this thread a turn
+    Sched* s = tl_sched;
+    s->runnable.insert(s->runnable.begin(), s->cur);
+    yield_to_scheduler();
+}
+void* selftest_worker(void* p) {
+    SelfTestArg* a = (SelfTestArg*)p;
+    double acc = (double)a->id;
+    long long sum = 0;
+    volatile int local[64];
+    for (int k = 0; k < 64; ++k) local[k] = a->id * 64 + k;
+    for (int y = 0; y < a->yields; ++y) {
+        acc = acc * 1.0000001 + (double)y * 0.5;          // floating-point state across switches
+        for (int k = 0; k < 64; ++k) sum += local[k] ^ y;  // stack contents across switches
+        selftest_yield();
+    }
+    a->result = acc; a->sum = sum;
+    return nullptr;
+}
+}  // namespace
+// Runs n workers that yield `yields` times each on `threads` scheduler threads; returns the number of workers
+// whose results differ from the same computation done without any switch (0 = pass).
+extern "C" int lb2_fiber_selftest(int n, int yields, int threads) {
+    g_selftest = true; g_selftest_threads = threads > 0 ? threads : 1;
+    std::vector<SelfTestArg> args((size_t)n);
+    std::vector<pthread_t> ids((size_t)n);
+    for (int i = 0; i < n; ++i) { args[(size_t)i] = SelfTestArg{i, yields, 0.0, 0}; lb2_worker_spawn(&ids[(size_t)i], nullptr, selftest_worker, &args[(size_t)i]); }
+    for (int i = 0; i < n; ++i) lb2_worker_join(ids[(size_t)i], nullptr);
+    g_selftest = false; g_selftest_threads = 0;
+    int bad = 0;
+    for (int i = 0; i < n; ++i) {
+        double acc = (double)i; long long sum = 0;
+        for (int y = 0; y < yields; ++y) { acc = acc * 1.0000001 + (double)y * 0.5; for (int k = 0; k < 64; ++k) sum += (i * 64 + k) ^ y; }
+        if (acc != args[(size_t)i].result || sum != args[(size_t)i].sum) ++bad;
+    }
+    return bad;
+}
+
 // pthread_create-shaped: registers a worker; it starts when the first of the workers is joined
 extern "C" int lb2_worker_spawn(pthread_t* id, const pthread_attr_t*, void* (*fn)(void*), void* arg) {
     Fiber* f = new Fiber();
@@ -251,10 +328,24 @@ extern "C" int lb2_worker_spawn(pthread_t* id, const pthread_attr_t*, void* (*fn
     f->stack_bytes = stack_bytes();
     f->stack = mmap(nullptr, f->stack_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE | MAP_STACK, -1, 0);
     if (f->stack == MAP_FAILED) { fprintf(stderr, "[lamsa_b200] cannot map a %zu-byte worker stack\n", f->stack_bytes); exit(1); }
+#if LB2_FAST_SWITCH
+    {   // first switch "returns" into lb2_fiber_entry_thunk with the Fiber* in r12 (frame laid out as lb2_fiber_swap pops it)
+        uintptr_t top = ((uintptr_t)f->stack + f->stack_bytes) & ~(uintptr_t)15;
+        uint64_t* a = (uint64_t*)(top - 8);                 // return address slot: rsp == top (16-aligned) inside the thunk
+        a[0] = (uint64_t)(uintptr_t)&lb2_fiber_entry_thunk;
+        a[-1] = 0;                                          // rbp
+        a[-2] = 0;                                          // rbx
+        a[-3] = (uint64_t)(uintptr_t)f;                     // r12
+        a[-4] = 0; a[-5] = 0; a[-6] = 0;                    // r13, r14, r15
+        a[-7] = (uint64_t)0x1F80u | ((uint64_t)0x037Fu << 32);   // MXCSR and x87 control word defaults
+        f->sp = (void*)(a - 7);
+    }
+#else
     getcontext(&f->ctx);
     f->ctx.uc_stack.ss_sp = f->stack; f->ctx.uc_stack.ss_size = f->stack_bytes; f->ctx.uc_link = nullptr;
     const uintptr_t p = (uintptr_t)f;
     makecontext(&f->ctx, (void (*)())trampoline, 2, (unsigned)(p & 0xffffffffu), (unsigned)(p >> 32));
+#endif
     std::lock_guard<std::mutex> lk(g_spawn_mu);
     g_spawned.push_back(f);
     if (id) *id = (pthread_t)g_spawned.size();
