@@ -148,6 +148,10 @@ def main():
     import lamsa_b200
     dist = None
     if world > 1:
+        # NCCL only carries the timing barrier and the reduction of the reported numbers; keep its version
+        # banner (printed to stdout at NCCL_DEBUG=VERSION/INFO) out of the one-JSON-line output
+        if "LB2_KEEP_NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
