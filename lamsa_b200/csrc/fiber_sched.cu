@@ -87,6 +87,25 @@ size_t stack_bytes() {
 //   16 queues: 4 threads 0.27 s;   32 queues: 4 threads 0.25 s, 8 threads 0.22 s, 16 threads 0.45 s
 // (with few queues the small launches of many contexts serialise; with few threads the host control flow of
 // 1 024 workers per thread is the bound).
+// wall-clock marks for LB2_FIBER_STATS: process start (library load), first spawn, end of the last join, exit
+const std::chrono::steady_clock::time_point g_t_load = std::chrono::steady_clock::now();
+double g_first_spawn_s = -1, g_last_join_s = -1, g_in_chunks_s = 0;
+int g_real_chunks = 0;                 // chunks run with GPU contexts (not the self test)
+double since_load() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t_load).count(); }
+// Runs when the program exits (registered at the first chunk, i.e. after CUDA registered its own handlers, so it
+// runs before them).  A `lamsa aln` process is done at this point: tearing down tens of CUDA contexts and their
+// pinned buffers costs about 0.7 s that the operating system does for free, so after flushing every stdio stream
+// the process leaves with _exit and the status it was given (LB2_FAST_EXIT=0 keeps the ordinary teardown).
+void report_at_exit(int status, void*) {
+    if (g_verbose() && g_first_spawn_s >= 0) {
+        const double t = since_load();
+        fprintf(stderr, "[lamsa_b200] wall clock since library load: first worker spawned at %.3f s, %.3f s inside worker chunks, "
+                        "%.3f s between/after chunks until the last join (%.3f s), exit at %.3f s\n",
+                g_first_spawn_s, g_in_chunks_s, g_last_join_s - g_first_spawn_s - g_in_chunks_s, g_last_join_s, t);
+    }
+    const char* e = getenv("LB2_FAST_EXIT");
+    if (g_real_chunks > 0 && !(e && *e == '0')) { fflush(nullptr); _exit(status); }
+}
 bool g_selftest = false;              // lb2_fiber_selftest: no GPU contexts, workers yield through selftest_yield
 int g_selftest_threads = 0;
 int host_threads() {
@@ -229,6 +248,8 @@ void run_scheduler(Sched* s) {
 
 void run_all(std::vector<Fiber*>& fibers) {
     const auto t0 = std::chrono::steady_clock::now();
+    static const bool hooked = [] { on_exit(report_at_exit, nullptr); return true; }();
+    (void)hooked;
     const int K = std::max(1, std::min(host_threads(), (int)fibers.size()));
     std::vector<Sched> scheds((size_t)K);
     for (size_t i = 0; i < fibers.size(); ++i) scheds[i % K].fibers.push_back(fibers[i]);
@@ -252,6 +273,9 @@ void run_all(std::vector<Fiber*>& fibers) {
     }
     for (Fiber* f : fibers) delete f;
     fibers.clear();
+    g_in_chunks_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    g_last_join_s = since_load();
+    if (!g_selftest) ++g_real_chunks;
 }
 
 }  // namespace
@@ -323,6 +347,7 @@ extern "C" int lb2_fiber_selftest(int n, int yields, int threads) {
 
 // pthread_create-shaped: registers a worker; it starts when the first of the workers is joined
 extern "C" int lb2_worker_spawn(pthread_t* id, const pthread_attr_t*, void* (*fn)(void*), void* arg) {
+    if (g_first_spawn_s < 0) g_first_spawn_s = since_load();
     Fiber* f = new Fiber();
     f->fn = fn; f->arg = arg;
     f->stack_bytes = stack_bytes();
