@@ -857,7 +857,10 @@ __device__ void stage_remain(Ctx& c, const DRegion* regions, int n_region, const
 
 // ----------------------------------------------------------------------- kernel --
 // Persistent warps pull reads (largest first) from an atomic counter.
-__global__ void __launch_bounds__(128)
+#ifndef LB2_SDP_MIN_BLOCKS
+#define LB2_SDP_MIN_BLOCKS 8      // 64 registers, 32 warps per SM: 25.4 vs 20.4 Gpairs/s at 4 (124 registers) on the 20k-read pacbio set
+#endif
+__global__ void __launch_bounds__(128, LB2_SDP_MIN_BLOCKS)
 sdp_kernel(const int stage, const __grid_constant__ lb2_sdp_para P, const int n_reads, const DRead* __restrict__ reads,
            const int32_t* __restrict__ order, const int32_t* __restrict__ seed_id, const int32_t* __restrict__ map_n,
            const int32_t* __restrict__ hoff, const lb2_sdp_hit* __restrict__ hits, const int32_t* __restrict__ hseed,
