@@ -81,7 +81,7 @@ size_t stack_bytes() {
     return v;
 }
 // scheduler threads per GPU unless LB2_HOST_THREADS says otherwise: two with CUDA's default 8 hardware work
-// queues, four when CUDA_DEVICE_MAX_CONNECTIONS >= 16 (see lb2_dropin_warmup in ksw_dropin.cu).  Measured on a
+// queues, four with 16+, eight with 32 (CUDA_DEVICE_MAX_CONNECTIONS; see lb2_dropin_warmup in ksw_dropin.cu).  Measured on a
 // 16-thread B200 host, steady-state chunk of 4 096 reads x 5 kbp:
 //    8 queues: 1 thread 0.58 s, 2 threads 0.38 s, 3 threads 0.44 s, 4 threads 0.60 s
 //   16 queues: 4 threads 0.27 s;   32 queues: 4 threads 0.25 s, 8 threads 0.22 s, 16 threads 0.45 s
@@ -114,7 +114,7 @@ int host_threads() {
     const char* d = getenv("LB2_DEVICES");
     const char* q = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
     const int ndev = d && *d && atoi(d) > 0 ? atoi(d) : 1;
-    const int per_gpu = q && atoi(q) >= 16 ? 4 : 2;
+    const int per_gpu = q && atoi(q) >= 32 ? 8 : q && atoi(q) >= 16 ? 4 : 2;
     int v = e && *e ? atoi(e) : std::min(per_gpu * ndev, (int)std::thread::hardware_concurrency());
     if (v < 1) v = 1;
     return v > 64 ? 64 : v;

@@ -14,6 +14,7 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <sys/stat.h>
 
 #include "../../include/lamsa_b200.h"
 #include "dropin_internal.h"
@@ -108,11 +109,33 @@ void lb2::dropin_dp_async_finish(DpAsync* a) {
 // thread); with CUDA's default of 8 hardware queues they alias and independent batches queue behind each other.
 // Measured, chunk of 4 096 reads: 4 scheduler threads need 0.60 s with 8 queues, 0.27 s with 16, 0.25 s with
 // 32 -- but CUDA start-up on a cold box grows from about 2 s (8) to 3-5 s (16) and 4.6 s and more (32).  So the
-// default stays at 8 queues with two scheduler threads per GPU (0.38 s per chunk), and long runs export
-// CUDA_DEVICE_MAX_CONNECTIONS=16 (or 32) before starting: fiber_sched.cu then uses four threads per GPU.
-// LB2_MAX_CONNECTIONS=n sets the variable from here (it only counts before CUDA starts).
+// default is 8 queues with two scheduler threads per GPU (0.38 s per chunk) for small runs and 32 queues with
+// eight threads for runs with 100 MB of reads or more (see below); CUDA_DEVICE_MAX_CONNECTIONS in the
+// environment, or LB2_MAX_CONNECTIONS=n (set from here; it only counts before CUDA starts), overrides.
 extern "C" void lb2_dropin_warmup(void) {
-    if (const char* e = getenv("LB2_MAX_CONNECTIONS")) if (*e) setenv("CUDA_DEVICE_MAX_CONNECTIONS", e, 0);
+    if (const char* e = getenv("LB2_MAX_CONNECTIONS")) { if (*e) setenv("CUDA_DEVICE_MAX_CONNECTIONS", e, 0); }
+    else if (!getenv("CUDA_DEVICE_MAX_CONNECTIONS")) {
+        // No setting given: decide by the size of the run.  The last command-line argument of `lamsa aln` is the
+        // read file; from about 100 MB of reads (10^4 reads of 10 kbp) the faster steady state of 32 queues pays
+        // for their slower start-up (measured: 20 000 x 10 kbp reads 7.3 s against 10.0 s, 8 000 x 5 kbp reads
+        // 4.7 s against 3.0 s).
+        FILE* f = fopen("/proc/self/cmdline", "rb");
+        if (f) {
+            std::vector<char> buf(1 << 16);
+            const size_t n = fread(buf.data(), 1, buf.size() - 1, f);
+            fclose(f);
+            size_t last = 0;
+            for (size_t i = 0; i + 1 < n; ++i) if (buf[i] == 0) last = i + 1;
+            buf[n] = 0;
+            struct stat st;
+            if (n > 0 && stat(buf.data() + last, &st) == 0 && S_ISREG(st.st_mode) && st.st_size >= (off_t)100 << 20)
+                setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+        }
+    }
+    if (getenv("LB2_FIBER_STATS")) {
+        const char* q = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+        fprintf(stderr, "[lamsa_b200] hardware work queues: %s\n", q ? q : "8 (CUDA default)");
+    }
     std::thread([] { default_ctx(); }).detach();
 }
 namespace {
