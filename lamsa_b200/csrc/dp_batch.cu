@@ -21,6 +21,7 @@
 #include "dp_trace.cuh"
 #include "int_peak.cuh"
 #include "ctx_internal.h"
+#include "dp_pack.h"
 
 using namespace lb2;
 
@@ -39,26 +40,7 @@ extern "C" const char* lb2_last_error(void) { return g_err.c_str(); }
 extern "C" void lb2_free(void* p) { free(p); }
 
 // ----------------------------------------------------------------- context --
-// A launch class = (kind, variant, S = window slots).
-// variants: 0..2 int32 lanes with G = 1,2,4 columns per lane; 3,4 packed int16 with NP = 2,4 pairs
-// per lane; 5 = int32 G=4 with the window in global memory (does not fit shared memory);
-// 6,7 = packed NP=2 in sub-warp bundles of L = 16 / 8 lanes per task (dp_fill16s.cuh); 8, 9 = packed NP=4, L = 8 / 16.
-constexpr int kMinLogS = 6, kMaxLogS = 18;          // 64 .. 262144 slots per warp
-constexpr int kNumLogS = kMaxLogS - kMinLogS + 1;
-constexpr int kNumVar = 10;
-constexpr int kVarGmem = 5;
-constexpr int kNumClass = 2 * kNumVar * kNumLogS;
-constexpr size_t kMaxDynSmem = 200 * 1024;
-static inline int class_id(int kind, int var, int logS) { return (kind * kNumVar + var) * kNumLogS + (logS - kMinLogS); }
-static inline int class_kind(int c) { return c / (kNumVar * kNumLogS); }
-static inline int class_var(int c) { return (c / kNumLogS) % kNumVar; }
-static inline int class_logS(int c) { return c % kNumLogS + kMinLogS; }
-static inline int var_gshift(int var) { return var >= 8 ? 3 : var == kVarGmem || var >= 6 ? 2 : var < 3 ? var : var - 1; }     // log2(columns per lane)
-static inline bool var_packed(int var) { return var == 3 || var == 4 || var >= 6; }
-static inline int var_tasks_per_warp(int var) { return var == 6 || var == 9 ? 2 : var >= 7 ? 4 : 1; }
-static inline size_t var_warp_smem(int var, int S) {
-    return var_packed(var) ? warp_smem_bytes16(S) * var_tasks_per_warp(var) : warp_smem_bytes(S);
-}
+// launch classes, variants and the per-task classification live in dp_pack.h
 static inline int class_warps(int var, int logS) {   // warps per block
     if (var == kVarGmem) return 4;
     int wpb = 8;
@@ -263,91 +245,13 @@ struct lb2_batch {
     unsigned int* d_counters = nullptr; int* d_err = nullptr;
     std::vector<Wave> waves;
     std::vector<uint8_t> flags;      // per task: LB2_FLAG_*
+    std::vector<int16_t> cls;        // per task: launch class
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // aliases of B.ev
     int64_t h2d_bytes = 0, d2h_bytes = 0, launches = 0;
     float fill_ms = 0, trace_ms = 0;
     bool uploaded = false, enqueued = false, computed = false;
     std::vector<cudaEvent_t> wave_ev;      // only when scratch forces several waves
 };
-
-// src/ksw.c:696-704 -- double division, truncation toward zero
-static int extend_band(int w, int qlen, int m, const int8_t* mat, int end_bonus,
-                       int o_del, int e_del, int o_ins, int e_ins) {
-    int best = 0;
-    for (int a = 0; a < m * m; ++a) best = best > mat[a] ? best : mat[a];
-    int lim = (int)((double)(qlen * best + end_bonus - o_ins) / e_ins + 1.);
-    lim = lim > 1 ? lim : 1;
-    w = w < lim ? w : lim;
-    lim = (int)((double)(qlen * best + end_bonus - o_del) / e_del + 1.);
-    lim = lim > 1 ? lim : 1;
-    w = w < lim ? w : lim;
-    return w;
-}
-
-static int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e && *e ? atoi(e) : dflt;
-}
-
-// Can every value of this task live in the packed-int16 domain of dp_fill16.cuh?
-static bool fits_int16(const lb2_task& t, int w) {
-    int maxs = 0, mins = 0;
-    for (int a = 0; a < t.m * t.m; ++a) { maxs = std::max<int>(maxs, t.mat[a]); mins = std::min<int>(mins, t.mat[a]); }
-    const long ncol = std::min<long>(t.qlen, 2L * w + 1);
-    const long maxo = std::max(t.o_del, t.o_ins), maxe = std::max(t.e_del, t.e_ins);
-    if (t.o_del < 0 || t.o_ins < 0 || maxe > 255 || maxo + maxe > 500) return false;
-    const long scan = (ncol + 300) * (long)t.e_ins;
-    if (t.kind == LB2_KIND_EXTEND) {
-        if (maxs > 1) return false;                       // M = min(H+s, 2H) needs s <= H for H >= 1
-        const long maxh = (long)t.h0 + (long)t.qlen * maxs;
-        return maxh <= 16000 && maxh + scan <= 32000;
-    }
-    // global fill, hat domain (values carry + column*e_ins): s + e_ins must stay an int8
-    if (maxs + t.e_ins > 127) return false;
-    const long lower = (long)(-mins) * std::min(t.qlen, t.tlen) + 2 * maxo + maxe * ((long)t.qlen + t.tlen + 2) + (maxo + maxe) + 64;
-    return lower <= 30000 && (long)t.qlen * (maxs + t.e_ins) + 64 <= 32000;
-}
-
-// kernel variant from the widest band a row can have
-static int pick_variant(const lb2_task& t, int w, long ncol, int logS) {
-    const int S_ = 1 << logS;
-    static const int force_gmem = env_int("LB2_FORCE_GMEM", 0);              // test hook
-    if (force_gmem || warp_smem_bytes16(S_) > kMaxDynSmem) return kVarGmem;   // window beyond shared memory
-    static const int use16 = env_int("LB2_P16", 1), p16_min = env_int("LB2_P16_MIN", 37),
-                     np4_min = env_int("LB2_NP4_MIN", 200), np4_min_ext = env_int("LB2_NP4_MIN_EXT", 1000000);
-    // narrow bands (the short interval fills of real reads) run 4 tasks per warp; so does every extension
-    // whose static band is below 410 columns: its LIVE band (src/ksw.c:775-778) is a few dozen columns wide,
-    // and the 32-column tiles of an 8-lane group follow it with less idle lanes than 128-column warp tiles
-    // (1 M-task C2: 437 vs 423 GCUPS, tools/kernel_probe.py)
-    static const int sub_l = env_int("LB2_SUBWARP", 8), sub_max_ext = env_int("LB2_SUBWARP_MAX_EXT", 410),
-                     sub_max_glb = env_int("LB2_SUBWARP_MAX_GLB", 200);
-    if (use16 && fits_int16(t, w)) {
-        const bool wide = ncol >= (t.kind == LB2_KIND_EXTEND ? np4_min_ext : np4_min);
-        const int sub_max = t.kind == LB2_KIND_EXTEND ? sub_max_ext : sub_max_glb;
-        // wide bands in 8-lane groups with 8 columns per lane (64-column tiles): LB2_SUB_NP4_MIN_EXT / _GLB
-        static const int sub4_ext = env_int("LB2_SUB_NP4_MIN_EXT", 160), sub4_glb = env_int("LB2_SUB_NP4_MIN_GLB", 100);
-        static const int sub16_ext = env_int("LB2_SUB16_NP4_MIN_EXT", 1000000);     // 16-lane groups, 128-column tiles
-        static const int sub16_glb = env_int("LB2_SUB16_NP4_MIN_GLB", 1000000), sub16_glb_max = env_int("LB2_SUB16_NP4_MAX_GLB", 1000000);
-        if (sub_l == 8 && t.kind == LB2_KIND_EXTEND && ncol < sub_max && ncol >= sub16_ext &&
-            warp_smem_bytes16(S_) * 2 * 2 <= kMaxDynSmem) return 9;
-        if (sub_l == 8 && t.kind == LB2_KIND_GLOBAL && ncol >= sub16_glb && ncol < sub16_glb_max &&
-            warp_smem_bytes16(S_) * 2 * 2 <= kMaxDynSmem) return 9;
-        if (sub_l == 8 && ncol < sub_max && ncol >= (t.kind == LB2_KIND_EXTEND ? sub4_ext : sub4_glb) &&
-            warp_smem_bytes16(S_) * 4 * 2 <= kMaxDynSmem) return 8;
-        if (sub_l && ncol < sub_max && warp_smem_bytes16(S_) * (32 / sub_l) * 2 <= kMaxDynSmem) return sub_l == 16 ? 6 : 7;
-        if (ncol >= p16_min) return wide ? 4 : 3;
-    }
-    if (warp_smem_bytes(S_) > kMaxDynSmem) return kVarGmem;
-    return ncol <= 36 ? 0 : ncol <= 72 ? 1 : 2;
-}
-// window slots: the whole eh[] array when it is small, else band window + look-ahead
-static int pick_logS(int qlen, int w) {
-    const long qpad = ((long)qlen + 1 + 31) & ~31L;
-    const long need = std::min<long>(qpad, 2L * w + 140);
-    int l = kMinLogS;
-    while ((1L << l) < need && l <= kMaxLogS) ++l;
-    return l <= kMaxLogS ? l : -1;
-}
 
 extern "C" void lb2_batch_destroy(lb2_batch* b) {
     if (!b) return;
@@ -391,92 +295,11 @@ static size_t grown(size_t need, size_t old_cap, size_t floor_) {
     return std::max(std::max(need + need / 4, old_cap * 2), floor_);
 }
 
-extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_batch** out) {
-    if (!ctx || !out || (n > 0 && !tasks)) return fail("lb2_batch_create: NULL argument");
-    if (n < 0 || n > (int64_t)1 << 30) return fail("lb2_batch_create: n=%lld out of range", (long long)n);
-    CU(cudaSetDevice(ctx->device));
-    lb2_batch* b = new lb2_batch();
-    b->ctx = ctx; b->n = n;
-    struct Guard { lb2_batch* b; bool ok = false; ~Guard() { if (!ok) lb2_batch_destroy(b); } } guard{b};
-
-    // ---- pass 1 (parallel): validate, final band, kernel variant, sizes
-    std::vector<uint64_t> qoff(n), toff(n), zsz(n);
-    std::vector<int32_t> wfin(n), ctmpw(n);
-    std::vector<int8_t> cshift(n), matid(n), logS(n), variant(n);
-    std::vector<std::vector<int8_t>> mats;           // distinct matrices, each 64 entries (8x8, zero padded)
-    std::mutex mats_mu;
-    std::mutex err_mu; int64_t err_i = -1; std::string err_msg;
-    b->flags.resize(n);
-    auto set_err = [&](int64_t i, const char* fmt, ...) {
-        char buf[256]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
-        std::lock_guard<std::mutex> lk(err_mu);
-        if (err_i < 0 || i < err_i) { err_i = i; err_msg = buf; }
-    };
-    auto matrix_id = [&](const lb2_task& t) -> int {
-        int8_t m8[64]; memset(m8, 0, sizeof m8);
-        for (int a = 0; a < t.m; ++a) for (int c = 0; c < t.m; ++c) m8[a * 8 + c] = t.mat[a * t.m + c];
-        std::lock_guard<std::mutex> lk(mats_mu);
-        for (size_t k = 0; k < mats.size(); ++k) if (!memcmp(mats[k].data(), m8, 64)) return (int)k;
-        if ((int)mats.size() == kMaxMats) return -1;
-        mats.emplace_back(m8, m8 + 64);
-        return (int)mats.size() - 1;
-    };
-    parallel_for(n, [&](int64_t lo_i, int64_t hi_i) {
-        const int8_t* last_mat = nullptr; int last_m = 0, last_id = -1;     // per-thread cache: tasks share matrices
-        for (int64_t i = lo_i; i < hi_i; ++i) {
-            const lb2_task& t = tasks[i];
-            if (t.qlen < 0 || t.tlen < 0) { set_err(i, "task %lld: qlen %d tlen %d", (long long)i, t.qlen, t.tlen); return; }
-            if (t.kind != LB2_KIND_GLOBAL && t.kind != LB2_KIND_EXTEND) { set_err(i, "task %lld: kind %d", (long long)i, t.kind); return; }
-            if (t.m < 1 || t.m > 8 || !t.mat) { set_err(i, "task %lld: alphabet size %d unsupported (1..8)", (long long)i, t.m); return; }
-            const bool tpac = (t.flags & LB2_FLAG_TARGET_PAC) != 0;
-            if ((t.qlen && !t.query) || (t.tlen && !tpac && !t.target)) { set_err(i, "task %lld: NULL sequence", (long long)i); return; }
-            if (tpac && (!ctx->d_pac || t.target_pac < 0 || t.target_pac + t.tlen > ctx->l_pac)) {
-                set_err(i, "task %lld: reference window [%lld,+%d) outside the resident reference (%lld bases)", (long long)i,
-                        (long long)t.target_pac, t.tlen, (long long)ctx->l_pac); return; }
-            if (t.e_del <= 0 || t.e_ins <= 0) { set_err(i, "task %lld: gap extension penalties must be > 0", (long long)i); return; }
-            int w = t.w;
-            if (t.kind == LB2_KIND_GLOBAL) {
-                const int dl = std::abs(t.qlen - t.tlen);
-                w = dl + 3 < w ? w : dl + 3;                                  // src/ksw.c:549
-            } else {
-                if (t.h0 <= 0) { set_err(i, "task %lld: h0 must be > 0 (src/ksw.c:682)", (long long)i); return; }
-                w = extend_band(w, t.qlen, t.m, t.mat, t.end_bonus, t.o_del, t.e_del, t.o_ins, t.e_ins);
-            }
-            if (w < 0) { set_err(i, "task %lld: negative band", (long long)i); return; }
-            wfin[i] = w;
-            const long ncol_i = std::min<long>(t.qlen, 2L * w + 1);
-            const int ls = pick_logS(t.qlen, w);
-            const int var = ls < 0 ? 0 : pick_variant(t, w, ncol_i, ls);
-            const int cs = var_gshift(var);
-            if (ls < 0) { set_err(i, "task %lld: qlen %d with band %d needs a window beyond %d slots (not supported yet)", (long long)i, t.qlen, w, 1 << kMaxLogS); return; }
-            cshift[i] = (int8_t)cs; logS[i] = (int8_t)ls; variant[i] = (int8_t)var;
-            if (t.mat != last_mat || t.m != last_m) {
-                last_id = matrix_id(t); last_mat = t.mat; last_m = t.m;
-                if (last_id < 0) { set_err(i, "more than %d distinct scoring matrices in one batch", kMaxMats); return; }
-            }
-            matid[i] = (int8_t)last_id;
-            b->flags[i] = (uint8_t)t.flags;
-            if (t.flags & LB2_FLAG_CIGAR) {
-                const int G = 1 << cs;
-                const int rt = row_tiles_for(ncol_i, G);
-                uint64_t z = (uint64_t)t.tlen * rt * 32 * dir_lane_bytes(G);
-                if (t.kind == LB2_KIND_EXTEND) z += ext_meta_bytes(t.tlen);
-                zsz[i] = (z + 15) & ~uint64_t(15);
-                ctmpw[i] = t.qlen + t.tlen + 2;
-            } else { zsz[i] = 0; ctmpw[i] = 0; }
-        }
-    });
-    if (err_i >= 0) return fail("%s", err_msg.c_str());
-    uint64_t pool = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        qoff[i] = pool; pool += ((uint64_t)tasks[i].qlen + 1 + 31) & ~uint64_t(31);
-        toff[i] = pool;
-        if (!(tasks[i].flags & LB2_FLAG_TARGET_PAC)) pool += ((uint64_t)tasks[i].tlen + 31) & ~uint64_t(31);
-    }
-    if (pool >> 37) return fail("sequence pool of %llu bytes is too large for one batch", (unsigned long long)pool);
-
-    // ---- waves: consecutive tasks whose scratch fits the limit, then class/cost order inside a wave
-    b->pool_bytes = pool + 64;
+// ---- the three steps every batch creator shares ------------------------------------------------
+// (1) pinned host staging for n tasks and pool_bytes of sequences (grow-only, taken from the context's parked set)
+static int alloc_host(lb2_batch* b, size_t pool_bytes) {
+    lb2_ctx* ctx = b->ctx;
+    b->pool_bytes = pool_bytes + 64;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         // prefer the parked set whose pinned pool is large enough
@@ -487,7 +310,7 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     }
     Buffers& B = b->B;
     B.valid = true;
-    const size_t n1c = (size_t)std::max<int64_t>(n, 1);
+    const size_t n1c = (size_t)std::max<int64_t>(b->n, 1);
     if (B.h_pool_cap < b->pool_bytes) {
         const size_t cap = grown(b->pool_bytes, B.h_pool_cap, (size_t)1 << 20);
         cudaFreeHost(B.h_pool); B.h_pool = nullptr; B.h_pool_cap = 0;
@@ -505,10 +328,15 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     if (!B.h_mats) CU(cudaMallocHost(&B.h_mats, sizeof(uint2) * kMaxMats * 8));
     b->h_pool = B.h_pool; b->h_tasks = B.h_tasks; b->h_results = B.h_results; b->h_order = B.h_order; b->h_mats = B.h_mats;
     memset(b->h_mats, 0, sizeof(uint2) * kMaxMats * 8);
-    for (size_t k = 0; k < mats.size(); ++k)
-        for (int r = 0; r < 8; ++r) memcpy(&b->h_mats[k * 8 + r], mats[k].data() + r * 8, 8);
+    return 0;
+}
 
-    const uint64_t zlimit = ctx->scratch_limit;
+// (2) waves (consecutive tasks whose scratch fits the limit), launch order inside a wave (counting sort by
+// class, then descending log-spaced cost bin: the persistent warps only need an approximately longest-first
+// order), scratch offsets.  h_tasks[i] must hold task i's descriptor; cls / bin / zsz / ctmpw describe it.
+static int layout_waves(lb2_batch* b, const int16_t* cls, const uint8_t* bin, const uint64_t* zsz, const int32_t* ctmpw) {
+    const int64_t n = b->n;
+    const uint64_t zlimit = b->ctx->scratch_limit;
     uint64_t dense = 0;
     {
         int64_t i = 0;
@@ -517,39 +345,39 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
             int64_t j = i;
             while (j < n) {
                 const uint64_t nz = wv.z_bytes + zsz[j], nc = wv.ctmp_words + (uint64_t)ctmpw[j];
-                if (j > i && nz + nc * 4 > zlimit) break;
+                if (j > i && nz + nc * 4 > zlimit) break;        // a single task larger than the limit still runs alone
                 wv.z_bytes = nz; wv.ctmp_words = nc; ++j;
             }
-            if (wv.z_bytes + wv.ctmp_words * 4 > zlimit && zlimit < (uint64_t)1 << 36)
-                ; // a single task larger than the limit still runs alone
             wv.count = (int)(j - i);
             dense += wv.ctmp_words;
             b->waves.push_back(wv);
             i = j;
         }
     }
-    // order + per-wave offsets: counting sort by (class, descending log-spaced cost bin) -- the
-    // persistent warps only need an approximately longest-first order
+    b->cls.assign(cls, cls + n);
     for (auto& wv : b->waves) {
-        constexpr int kBins = 48;
-        auto key = [&](int64_t a) {
-            const int64_t cost = (int64_t)tasks[a].tlen * std::min<int64_t>(tasks[a].qlen, 2L * wfin[a] + 1) + 1;
-            int bin = 0;                                      // ~3 bins per octave
-            { int64_t c = cost; int l2 = 63 - __builtin_clzll((unsigned long long)c);
-              const int frac = l2 >= 2 ? (int)((c >> (l2 - 2)) & 3) : 0;
-              bin = std::min(kBins - 1, std::max(0, (l2 * 4 + frac) / 3 - 4)); }
-            return class_id((int)tasks[a].kind, variant[a], logS[a]) * kBins + (kBins - 1 - bin);
-        };
-        std::vector<int32_t> keys(wv.count);
-        std::vector<int32_t> hist((size_t)kNumClass * kBins + 1, 0);
+        // classes in use are few: histogram only those (a producer submits thousands of small batches)
+        std::vector<int32_t> keys((size_t)wv.count);
         parallel_for(wv.count, [&](int64_t lo_i, int64_t hi_i) {
-            for (int64_t k = lo_i; k < hi_i; ++k) keys[k] = key(wv.first + k);
+            for (int64_t k = lo_i; k < hi_i; ++k) keys[(size_t)k] = (int32_t)cls[wv.first + k] * kCostBins + bin[wv.first + k];
         });
-        for (int k = 0; k < wv.count; ++k) ++hist[keys[k] + 1];
+        bool used[kNumClass] = {false};
+        for (int k = 0; k < wv.count; ++k) used[keys[(size_t)k] / kCostBins] = true;
+        int slot_of[kNumClass], nused = 0;
+        for (int c = 0; c < kNumClass; ++c) slot_of[c] = used[c] ? nused++ : -1;
+        std::vector<int32_t> hist((size_t)nused * kCostBins + 1, 0);
+        for (int k = 0; k < wv.count; ++k) {
+            const int c = keys[(size_t)k] / kCostBins, bb = keys[(size_t)k] % kCostBins;
+            keys[(size_t)k] = slot_of[c] * kCostBins + bb;
+            ++hist[(size_t)keys[(size_t)k] + 1];
+        }
         for (size_t k = 1; k < hist.size(); ++k) hist[k] += hist[k - 1];
-        for (int c = 0; c <= kNumClass; ++c) wv.cls_off[c] = hist[(size_t)c * kBins];
+        for (int c = 0, u = 0; c <= kNumClass; ++c) {
+            wv.cls_off[c] = hist[(size_t)u * kCostBins];
+            if (c < kNumClass && used[c]) ++u;
+        }
         int32_t* ord = b->h_order + wv.first;
-        for (int k = 0; k < wv.count; ++k) ord[hist[keys[k]]++] = wv.first + k;
+        for (int k = 0; k < wv.count; ++k) ord[hist[(size_t)keys[(size_t)k]]++] = wv.first + k;
         uint64_t z = 0, cw = 0;
         for (int k = 0; k < wv.count; ++k) {          // scratch offsets follow the original order
             const int64_t a = wv.first + k;
@@ -558,40 +386,15 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
             cw += (uint64_t)ctmpw[a]; d.ctmp_end = cw; d.ctmp_cap = ctmpw[a];
         }
     }
-    // ---- pass 2: fill descriptors and copy sequences (parallel)
-    uint8_t* hp = b->h_pool;
-    DTask* ht = b->h_tasks;
-    parallel_for(n, [&, hp, ht](int64_t a, int64_t e) {
-        for (int64_t i = a; i < e; ++i) {
-            const lb2_task& t = tasks[i];
-            DTask& d = ht[i];
-            const bool tpac = (t.flags & LB2_FLAG_TARGET_PAC) != 0;
-            d.q_off32 = (uint32_t)(qoff[i] >> 5);
-            d.t_off32 = tpac ? (uint32_t)t.target_pac : (uint32_t)(toff[i] >> 5);
-            d.qlen = t.qlen; d.tlen = t.tlen; d.w = wfin[i]; d.h0 = t.h0;
-            d.o_del = t.o_del; d.e_del = t.e_del; d.o_ins = t.o_ins; d.e_ins = t.e_ins;
-            d.end_bonus = t.end_bonus; d.zdrop = t.zdrop;
-            d.kind = (uint8_t)t.kind;
-            d.want_dir = (uint8_t)(((t.flags & LB2_FLAG_CIGAR) ? kWantDir : 0) | (tpac ? kTargetPac : 0) |
-                                   ((tpac && (t.flags & LB2_FLAG_TARGET_REV)) ? kTargetRev : 0));
-            d.mat_id = (uint8_t)matid[i]; d.cshift = (uint8_t)cshift[i];
-            const long ncol = std::min<long>(t.qlen, 2L * wfin[i] + 1);
-            d.row_chunks = row_tiles_for(ncol, 1 << cshift[i]);
-            d.dir_fmt = var_packed(variant[i]) ? 1 : 0;
-            uint8_t* q = hp + qoff[i];
-            const uint64_t qp = ((uint64_t)t.qlen + 1 + 31) & ~uint64_t(31);
-            if (t.qlen) memcpy(q, t.query, t.qlen);
-            memset(q + t.qlen, 0, qp - t.qlen);
-            if (!tpac) {
-                uint8_t* tt = hp + toff[i];
-                const uint64_t tp = ((uint64_t)t.tlen + 31) & ~uint64_t(31);
-                if (t.tlen) memcpy(tt, t.target, t.tlen);
-                memset(tt + t.tlen, 0, tp - t.tlen);
-            }
-        }
-    });
+    b->dense_cap = dense + 16;
+    return 0;
+}
 
-    // ---- device allocations (grow-only, reused across batches)
+// (3) device buffers (grow-only, reused across batches) and the context's scratch
+static int alloc_device(lb2_batch* b) {
+    lb2_ctx* ctx = b->ctx;
+    Buffers& B = b->B;
+    const size_t n1c = (size_t)std::max<int64_t>(b->n, 1);
     if (B.d_pool_cap < b->pool_bytes) {
         const size_t cap = grown(b->pool_bytes, B.d_pool_cap, (size_t)1 << 20);
         cudaFree(B.d_pool); B.d_pool = nullptr; B.d_pool_cap = 0;
@@ -607,7 +410,6 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
         B.d_n_cap = cap;
     }
     if (!B.d_mats) CU(cudaMalloc(&B.d_mats, sizeof(uint2) * kMaxMats * 8));
-    b->dense_cap = dense + 16;
     if (B.dense_cap < b->dense_cap) {
         const size_t cap = grown(b->dense_cap, B.dense_cap, (size_t)1 << 18);
         cudaFree(B.d_cdense); B.d_cdense = nullptr; B.dense_cap = 0;
@@ -625,21 +427,156 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     b->d_pool = B.d_pool; b->d_tasks = B.d_tasks; b->d_results = B.d_results; b->d_order = B.d_order; b->d_mats = B.d_mats;
     b->d_cdense = B.d_cdense; b->d_cursor = B.d_cursor; b->d_counters = B.d_counters; b->d_err = B.d_err;
     for (int k = 0; k < 4; ++k) b->ev[k] = B.ev[k];
-    // grow the context's scratch
+    // grow the context's scratch.  Kernels of an earlier batch of this context may still be using it
+    // (lb2_dp_run pipelines chunks): wait for them explicitly rather than rely on cudaFree's implicit barrier.
     uint64_t zmax = 16, cmax = 16;
     for (auto& wv : b->waves) { zmax = std::max(zmax, wv.z_bytes); cmax = std::max(cmax, wv.ctmp_words); }
-    if (ctx->z_cap < zmax) {
-        const size_t cap = grown(zmax, ctx->z_cap, (size_t)16 << 20);
-        if (ctx->d_z) CU(cudaFree(ctx->d_z));
-        ctx->d_z = nullptr; ctx->z_cap = 0;
-        CU(cudaMalloc(&ctx->d_z, cap + 64)); ctx->z_cap = cap;
+    if (ctx->z_cap < zmax || ctx->ctmp_cap < cmax) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (int q = 0; q < lb2_ctx::kAux; ++q) CU(cudaStreamSynchronize(ctx->aux[q]));
+        if (ctx->z_cap < zmax) {
+            const size_t cap = grown(zmax, ctx->z_cap, (size_t)16 << 20);
+            if (ctx->d_z) CU(cudaFree(ctx->d_z));
+            ctx->d_z = nullptr; ctx->z_cap = 0;
+            CU(cudaMalloc(&ctx->d_z, cap + 64)); ctx->z_cap = cap;
+        }
+        if (ctx->ctmp_cap < cmax) {
+            const size_t cap = grown(cmax, ctx->ctmp_cap, (size_t)1 << 20);
+            if (ctx->d_ctmp) CU(cudaFree(ctx->d_ctmp));
+            ctx->d_ctmp = nullptr; ctx->ctmp_cap = 0;
+            CU(cudaMalloc(&ctx->d_ctmp, (cap + 16) * 4)); ctx->ctmp_cap = cap;
+        }
     }
-    if (ctx->ctmp_cap < cmax) {
-        const size_t cap = grown(cmax, ctx->ctmp_cap, (size_t)1 << 20);
-        if (ctx->d_ctmp) CU(cudaFree(ctx->d_ctmp));
-        ctx->d_ctmp = nullptr; ctx->ctmp_cap = 0;
-        CU(cudaMalloc(&ctx->d_ctmp, (cap + 16) * 4)); ctx->ctmp_cap = cap;
+    return 0;
+}
+
+extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_batch** out) {
+    if (!ctx || !out || (n > 0 && !tasks)) return fail("lb2_batch_create: NULL argument");
+    if (n < 0 || n > (int64_t)1 << 30) return fail("lb2_batch_create: n=%lld out of range", (long long)n);
+    CU(cudaSetDevice(ctx->device));
+    lb2_batch* b = new lb2_batch();
+    b->ctx = ctx; b->n = n;
+    struct Guard { lb2_batch* b; bool ok = false; ~Guard() { if (!ok) lb2_batch_destroy(b); } } guard{b};
+
+    // ---- pass 1 (parallel): validate, final band, kernel variant, sizes
+    std::vector<PackedTask> pk((size_t)n);
+    std::vector<std::vector<int8_t>> mats;           // distinct matrices, each 64 entries (8x8, zero padded)
+    std::mutex mats_mu;
+    std::mutex err_mu; int64_t err_i = -1; std::string err_msg;
+    auto matrix_id = [&](const lb2_task& t) -> int {
+        int8_t m8[64]; memset(m8, 0, sizeof m8);
+        for (int a = 0; a < t.m; ++a) for (int c = 0; c < t.m; ++c) m8[a * 8 + c] = t.mat[a * t.m + c];
+        std::lock_guard<std::mutex> lk(mats_mu);
+        for (size_t k = 0; k < mats.size(); ++k) if (!memcmp(mats[k].data(), m8, 64)) return (int)k;
+        if ((int)mats.size() == kMaxMats) return -1;
+        mats.emplace_back(m8, m8 + 64);
+        return (int)mats.size() - 1;
+    };
+    const int64_t l_pac = ctx->d_pac ? ctx->l_pac : -1;
+    parallel_for(n, [&](int64_t lo_i, int64_t hi_i) {
+        const int8_t* last_mat = nullptr; int last_m = 0, last_id = -1;     // per-thread cache: tasks share matrices
+        char msg[200];
+        for (int64_t i = lo_i; i < hi_i; ++i) {
+            const lb2_task& t = tasks[i];
+            int bad = classify_task(t, l_pac, pk[(size_t)i], msg, sizeof msg);
+            if (!bad && (t.mat != last_mat || t.m != last_m)) {
+                last_id = matrix_id(t); last_mat = t.mat; last_m = t.m;
+                if (last_id < 0) { snprintf(msg, sizeof msg, "more than %d distinct scoring matrices in one batch", kMaxMats); bad = 1; }
+            }
+            if (bad) {
+                std::lock_guard<std::mutex> lk(err_mu);
+                if (err_i < 0 || i < err_i) { err_i = i; err_msg = "task " + std::to_string(i) + ": " + msg; }
+                return;
+            }
+            pk[(size_t)i].d.mat_id = (uint8_t)last_id;
+        }
+    });
+    if (err_i >= 0) return fail("%s", err_msg.c_str());
+    std::vector<uint64_t> qoff((size_t)n);
+    uint64_t pool = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        qoff[(size_t)i] = pool;
+        pool += pool_bytes_query(tasks[i].qlen);
+        if (!(tasks[i].flags & LB2_FLAG_TARGET_PAC)) pool += pool_bytes_target(tasks[i].tlen);
     }
+    if (pool >> 37) return fail("sequence pool of %llu bytes is too large for one batch", (unsigned long long)pool);
+    if (alloc_host(b, pool)) return 1;
+    for (size_t k = 0; k < mats.size(); ++k)
+        for (int r = 0; r < 8; ++r) memcpy(&b->h_mats[k * 8 + r], mats[k].data() + r * 8, 8);
+
+    // ---- pass 2: descriptors and sequences into the pinned staging (parallel)
+    b->flags.resize((size_t)n);
+    std::vector<int16_t> cls((size_t)n); std::vector<uint8_t> bin((size_t)n);
+    std::vector<uint64_t> zsz((size_t)n); std::vector<int32_t> ctmpw((size_t)n);
+    uint8_t* hp = b->h_pool;
+    DTask* ht = b->h_tasks;
+    parallel_for(n, [&, hp, ht](int64_t a, int64_t e) {
+        for (int64_t i = a; i < e; ++i) {
+            PackedTask& p = pk[(size_t)i];
+            copy_sequences(tasks[i], p, hp, qoff[(size_t)i]);
+            ht[i] = p.d;
+            b->flags[(size_t)i] = p.flags; cls[(size_t)i] = p.cls; bin[(size_t)i] = p.bin;
+            zsz[(size_t)i] = p.zsz; ctmpw[(size_t)i] = p.ctmpw;
+        }
+    });
+    if (layout_waves(b, cls.data(), bin.data(), zsz.data(), ctmpw.data())) return 1;
+    if (alloc_device(b)) return 1;
+    guard.ok = true;
+    *out = b;
+    return 0;
+}
+
+// The batch producer's creator: tasks arrive classified and copied by the threads that parked them
+// (dp_pack.h: TaskBlob); this only concatenates the blobs into the pinned staging and lays out the launch.
+int lb2::batch_create_staged(lb2_ctx* ctx, const TaskBlob* const* blobs, int nblobs, lb2_batch** out) {
+    if (!ctx || !out) return fail("batch_create_staged: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    int64_t n = 0; uint64_t pool = 0;
+    for (int k = 0; k < nblobs; ++k) { n += (int64_t)blobs[k]->tasks.size(); pool += blobs[k]->pool.size(); }
+    if (pool >> 37) return fail("sequence pool of %llu bytes is too large for one batch", (unsigned long long)pool);
+    lb2_batch* b = new lb2_batch();
+    b->ctx = ctx; b->n = n;
+    struct Guard { lb2_batch* b; bool ok = false; ~Guard() { if (!ok) lb2_batch_destroy(b); } } guard{b};
+    if (alloc_host(b, pool)) return 1;
+    // batch-wide matrix table
+    std::vector<std::array<int8_t, 64>> mats;
+    std::vector<std::vector<uint8_t>> remap((size_t)nblobs);
+    for (int k = 0; k < nblobs; ++k) {
+        for (const auto& m8 : blobs[k]->mats) {
+            size_t id = 0;
+            while (id < mats.size() && mats[id] != m8) ++id;
+            if (id == mats.size()) {
+                if ((int)mats.size() == kMaxMats) return fail("more than %d distinct scoring matrices in one batch", kMaxMats);
+                mats.push_back(m8);
+            }
+            remap[(size_t)k].push_back((uint8_t)id);
+        }
+    }
+    for (size_t k = 0; k < mats.size(); ++k)
+        for (int r = 0; r < 8; ++r) memcpy(&b->h_mats[k * 8 + r], mats[k].data() + r * 8, 8);
+    b->flags.resize((size_t)n);
+    std::vector<int16_t> cls((size_t)n); std::vector<uint8_t> bin((size_t)n);
+    std::vector<uint64_t> zsz((size_t)n); std::vector<int32_t> ctmpw((size_t)n);
+    int64_t at = 0; uint64_t pool_at = 0;
+    for (int k = 0; k < nblobs; ++k) {
+        const TaskBlob& bl = *blobs[k];
+        if (!bl.pool.empty()) memcpy(b->h_pool + pool_at, bl.pool.data(), bl.pool.size());
+        const uint32_t base32 = (uint32_t)(pool_at >> 5);
+        for (const PackedTask& p : bl.tasks) {
+            DTask d = p.d;
+            d.q_off32 += base32;
+            if (!(d.want_dir & kTargetPac)) d.t_off32 += base32;
+            d.mat_id = remap[(size_t)k][d.mat_id];
+            b->h_tasks[at] = d;
+            b->flags[(size_t)at] = p.flags; cls[(size_t)at] = p.cls; bin[(size_t)at] = p.bin;
+            zsz[(size_t)at] = p.zsz; ctmpw[(size_t)at] = p.ctmpw;
+            ++at;
+        }
+        pool_at += bl.pool.size();
+    }
+    if (layout_waves(b, cls.data(), bin.data(), zsz.data(), ctmpw.data())) return 1;
+    if (alloc_device(b)) return 1;
     guard.ok = true;
     *out = b;
     return 0;

@@ -71,6 +71,15 @@ __host__ __device__ inline uint64_t ext_meta_bytes(int tlen) {
     return ((uint64_t)tlen * 8 + 15) & ~uint64_t(15);
 }
 
+// bytes of direction storage per lane per tile (G nibbles; one byte when G==1)
+__host__ __device__ constexpr int dir_lane_bytes(int G) { return G >= 2 ? G / 2 : 1; }
+// tiles a row can span: columns [beg & ~(G-1), end] with end-beg <= ncol
+__host__ __device__ inline int row_tiles_for(long ncol, int G) { return (int)((ncol + G) / (32 * G)) + 1; }
+// shared-memory bytes one warp needs for a window of S slots
+__host__ __device__ constexpr size_t warp_smem_bytes(int S) { return (size_t)S * 10; }
+// ... of the packed-int16 kernels (h16, e16, one selector per pair, + 8 staged matrix rows)
+__host__ __device__ constexpr size_t warp_smem_bytes16(int S) { return (size_t)S * 5 + 64; }
+
 __device__ __forceinline__ TargetSrc make_target(const DTask& T, const uint8_t* pool, const uint8_t* pac) {
     TargetSrc t;
     const bool p = (T.want_dir & kTargetPac) != 0;

@@ -84,12 +84,6 @@ template <> struct Vec<4> {
         v[0] = t.x & 0xffffu; v[1] = t.x >> 16; v[2] = t.y & 0xffffu; v[3] = t.y >> 16; }
 };
 
-// bytes of direction storage per lane per tile (G nibbles; one byte when G==1)
-__host__ __device__ constexpr int dir_lane_bytes(int G) { return G >= 2 ? G / 2 : 1; }
-// tiles a row can span: columns [beg & ~(G-1), end] with end-beg <= ncol
-__host__ __device__ inline int row_tiles_for(long ncol, int G) { return (int)((ncol + G) / (32 * G)) + 1; }
-// shared-memory bytes one warp needs for a window of S slots
-__host__ __device__ constexpr size_t warp_smem_bytes(int S) { return (size_t)S * 10; }
 
 template <int G, int KIND>
 __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool, const uint8_t* __restrict__ pac,

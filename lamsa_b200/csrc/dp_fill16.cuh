@@ -98,8 +98,6 @@ __device__ __forceinline__ void stage_matrix(uint2* __restrict__ mrw, const uint
     }
 }
 
-// shared-memory bytes one warp needs for a window of S slots (h16, e16, one selector per pair)
-__host__ __device__ constexpr size_t warp_smem_bytes16(int S) { return (size_t)S * 5 + 64; }   // + 8 staged matrix rows
 // per-block table of half masks: entry [lo*(G+1)+hi][p] = mask of columns c in [lo,hi) of pair p
 template <int NP> __host__ __device__ constexpr int mask_table_words() { return (2 * NP + 1) * (2 * NP + 1) * NP; }
 

@@ -5,7 +5,7 @@
  * call this file; it exists so that tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline leg can check the CUDA path.  Parity of this
  * restatement is pinned against oracle/_ref/libksw_ref.so (the unmodified
- * reference ksw.c compiled by oracle/Makefile) in tests/test_oracle_vs_ref.py
+ * reference ksw.c compiled by oracle/Makefile) in tests/test_oracle.py and tests/test_wrappers_oracle.py
  * and against the committed fixtures under tests/golden/.
  *
  * Reference being restated (all paths relative to /root/reference):

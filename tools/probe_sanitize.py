@@ -1,7 +1,7 @@
 """Manual GPU triage: small mixed workload for compute-sanitizer (memcheck / racecheck)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import lamsa_b200
 from lamsa_b200 import workload

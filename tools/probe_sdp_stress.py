@@ -1,13 +1,13 @@
 """Manual GPU triage for the chaining kernel: heavy multi-hit reads (up to per_aln_m hits per seed,
 most seeds repetitive) against the oracle; meant to be run under compute-sanitizer as well:
-    compute-sanitizer --tool memcheck python tests/gpu_sdp_stress.py 40
+    compute-sanitizer --tool memcheck python tools/probe_sdp_stress.py 40
 """
 import os
 import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import _sdp
 import lamsa_b200
 from lamsa_b200.sdp import SdpBatch
