@@ -339,21 +339,23 @@ void lb2_sdp_destroy(lb2_sdp_batch *b);
 /* ------------------------------------------------------ 4. batch producer -- */
 /*
  * The reference aligns reads on `-t N` pthreads, one read per thread at a time, every DP call
- * blocking (src/lamsa_aln.c:825-891, :1151-1162).  These two functions have the signatures of
- * pthread_create / pthread_join and run the same worker functions as user-level fibers on
- * LB2_HOST_THREADS OS threads instead: a worker that reaches one of the drop-in entry points above
- * parks its request and yields, and when all workers of an OS thread are parked their requests go
- * to the GPU as ONE batch (fiber_sched.cu).  `lamsa aln -t 4096` then keeps 4096 reads in flight and
- * a launch carries thousands of DP tasks.  Redirecting the two pthread names when compiling the
- * reference's lamsa_aln.c is the whole integration (oracle/fiber_wrapper.c).
- * Workers start when the first of them is joined; results and output order are unchanged.
+ * blocking (src/lamsa_aln.c:825-891, :1151-1162).  These functions have the signatures of
+ * pthread_create / pthread_join and run the worker functions as user-level fibers on one OS thread per
+ * host core instead (LB2_HOST_THREADS): a worker that reaches one of the drop-in entry points above
+ * parks its request and yields; ONE submitter per GPU gathers the parked requests of all threads into
+ * batches, and the results come back to the fibers' home threads (producer.cu).  With tens of thousands
+ * of workers -- one per read in flight, lamsa_b200/host/aln_core.c -- a launch carries thousands of DP
+ * tasks.  Workers start when the first of them is joined.
  */
 int lb2_worker_spawn(pthread_t *id, const pthread_attr_t *attr, void *(*fn)(void *), void *arg);
 int lb2_worker_join(pthread_t id, void **ret);
-/* Self test of the worker scheduler and its context switch without a GPU: n workers yielding `yields`
- * times each on `threads` scheduler threads; returns the number of workers with a wrong result (0 = pass). */
+/* Called by a worker: lets the other workers of its thread run (a worker waiting for a sibling's progress). */
+void lb2_worker_yield(void);
+/* Self test of the worker scheduler, its context switch and the request round trip through another thread,
+ * without a GPU: n workers yielding `yields` times each on `threads` scheduler threads; returns the number of
+ * workers with a wrong result (0 = pass). */
 int lb2_fiber_selftest(int n, int yields, int threads);
-/* Opens the process-wide context of the drop-in entry points from a helper thread, so that CUDA
+/* Opens the batch producer's GPUs (contexts, batch slots, device threads) from a helper thread, so that CUDA
  * start-up overlaps the caller's own start-up (index loading).  Optional. */
 void lb2_dropin_warmup(void);
 

@@ -12,6 +12,6 @@ int ctx_sm_count(lb2_ctx* c);
 int set_error(const char* fmt, ...);     // stores the message for lb2_last_error(), returns 1
 // lb2_batch_create for tasks that were classified and copied by their producers (dp_batch.cu)
 int batch_create_staged(lb2_ctx* ctx, const TaskBlob* const* blobs, int nblobs, lb2_batch** out);
-// results of a computed batch without the CIGAR copy-out: lb2_result records for every task and the pinned
-// view of the dense CIGAR pool (valid until the batch is destroyed)
+// block (no spinning) until the kernels of an enqueued batch have finished
+int batch_wait_blocking(lb2_batch* b);
 }

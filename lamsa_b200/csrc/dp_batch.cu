@@ -65,6 +65,7 @@ struct Buffers {
     int* d_err = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t up_ev = nullptr;                        // H2D of this batch finished
+    cudaEvent_t done_ev = nullptr;                      // all kernels finished; blocking-sync flavour (no spinning host thread)
     bool valid = false;
     void release() {
         cudaFreeHost(h_pool); cudaFreeHost(h_tasks); cudaFreeHost(h_results); cudaFreeHost(h_order); cudaFreeHost(h_mats);
@@ -73,6 +74,7 @@ struct Buffers {
         cudaFree(d_cdense); cudaFree(d_cursor); cudaFree(d_counters); cudaFree(d_err);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (up_ev) cudaEventDestroy(up_ev);
+        if (done_ev) cudaEventDestroy(done_ev);
         *this = Buffers();
     }
 };
@@ -424,6 +426,7 @@ static int alloc_device(lb2_batch* b) {
     if (!B.d_err) CU(cudaMalloc(&B.d_err, sizeof(int)));
     for (auto& e : B.ev) if (!e) CU(cudaEventCreate(&e));
     if (!B.up_ev) CU(cudaEventCreateWithFlags(&B.up_ev, cudaEventDisableTiming));
+    if (!B.done_ev) CU(cudaEventCreateWithFlags(&B.done_ev, cudaEventDisableTiming | cudaEventBlockingSync));
     b->d_pool = B.d_pool; b->d_tasks = B.d_tasks; b->d_results = B.d_results; b->d_order = B.d_order; b->d_mats = B.d_mats;
     b->d_cdense = B.d_cdense; b->d_cursor = B.d_cursor; b->d_counters = B.d_counters; b->d_err = B.d_err;
     for (int k = 0; k < 4; ++k) b->ev[k] = B.ev[k];
@@ -694,6 +697,7 @@ static int compute_enqueue(lb2_batch* b) {
         if (!one_wave) CU(cudaEventRecord(b->wave_ev[wi * 3 + 2], s));
     }
     CU(cudaEventRecord(b->ev[3], s));
+    CU(cudaEventRecord(b->B.done_ev, s));
     b->enqueued = true;
     return 0;
 }
@@ -914,6 +918,12 @@ extern "C" int lb2_int_peak(lb2_ctx* ctx, double* gops_s16x2, double* gops_s32, 
 
 // ---- internal accessors for the other translation units (ctx_internal.h) ----
 namespace lb2 {
+int batch_wait_blocking(lb2_batch* b) {
+    if (!b || !b->enqueued) return fail("batch_wait_blocking: nothing enqueued");
+    CU(cudaSetDevice(b->ctx->device));
+    CU(cudaEventSynchronize(b->B.done_ev));
+    return 0;
+}
 cudaStream_t ctx_stream(lb2_ctx* c) { return c->stream; }
 int ctx_device(lb2_ctx* c) { return c->device; }
 int ctx_sm_count(lb2_ctx* c) { return c->sm_count; }

@@ -10,9 +10,11 @@ namespace lb2 {
 
 lb2_ctx* dropin_ctx();                       // the context of the drop-in symbols: the calling thread's own
                                              // (dropin_use_thread_ctx) or else the process-wide one
-// give the calling OS thread a context of its own (scheduler thread `index`: GPU index mod #GPUs)
-void dropin_use_thread_ctx(int index);
+// make `c` the context of the calling OS thread (the batch producer's chaining thread)
+void dropin_bind_thread_ctx(lb2_ctx* c);
 bool dropin_has_thread_ctx();                // false: the caller shares the process-wide context with other threads
+// open the batch producer's GPUs now (producer.cu)
+void producer_warmup();
 
 // one blocked banded-DP call (ksw_dropin.cu)
 struct DpRequest {
@@ -23,15 +25,6 @@ struct DpRequest {
 };
 // run requests as ONE GPU batch and hand the results back (ksw_dropin.cu)
 void dropin_submit_dp(std::vector<DpRequest*>& batch);
-
-// The same, overlapped with other work: submit on one of the calling scheduler thread's side
-// contexts (slot 0..kAsyncSlots-1, one batch in flight per slot), poll, then finish (waits if
-// needed, delivers results).
-constexpr int kAsyncSlots = 3;
-struct DpAsync;
-DpAsync* dropin_dp_async_submit(std::vector<DpRequest*>& batch, int slot);
-bool dropin_dp_async_done(DpAsync* a);
-void dropin_dp_async_finish(DpAsync* a);
 
 // one blocked chaining call (sdp_dropin.cu).  The read's flattened seed hits and the tracked
 // flags stage 1 leaves for stage 2 live in the worker's state.

@@ -14,7 +14,6 @@
 #include <mutex>
 #include <thread>
 #include <vector>
-#include <sys/stat.h>
 
 #include "../../include/lamsa_b200.h"
 #include "dropin_internal.h"
@@ -24,8 +23,7 @@ namespace {
 std::mutex g_mu;
 lb2_ctx* g_ctx = nullptr;
 
-thread_local lb2_ctx* tl_ctx = nullptr;        // scheduler threads of the batch producer own a context each
-thread_local lb2_ctx* tl_side_ctx[lb2::kAsyncSlots] = {nullptr};   // ... and side contexts for batches in flight
+thread_local lb2_ctx* tl_ctx = nullptr;        // device threads of the batch producer own a context each
 
 lb2_ctx* default_ctx() {
     if (tl_ctx) return tl_ctx;
@@ -44,99 +42,12 @@ lb2_ctx* default_ctx() {
 }  // namespace
 namespace lb2 { lb2_ctx* dropin_ctx() { return default_ctx(); } }   // shared with sdp_dropin.cu
 bool lb2::dropin_has_thread_ctx() { return tl_ctx != nullptr; }
-void lb2::dropin_use_thread_ctx(int index) {
-    if (tl_ctx) return;
-    // scheduler threads are re-created per read chunk; their contexts are kept by index
-    static std::mutex mu;
-    static std::vector<lb2_ctx*> table;
-    static std::vector<std::vector<lb2_ctx*>> side_table;
-    std::lock_guard<std::mutex> lk(mu);
-    if ((size_t)index < table.size() && table[(size_t)index]) {
-        tl_ctx = table[(size_t)index];
-        for (int k = 0; k < lb2::kAsyncSlots; ++k) tl_side_ctx[k] = side_table[(size_t)index][(size_t)k];
-        return;
-    }
-    if ((size_t)index >= table.size()) { table.resize((size_t)index + 1, nullptr); side_table.resize((size_t)index + 1); }
-    int ndev = 1;
-    if (const char* e = getenv("LB2_DEVICES")) ndev = atoi(e) > 0 ? atoi(e) : 1;
-    int base = 0;
-    if (const char* e = getenv("LB2_DEVICE")) base = atoi(e);
-    if (lb2_ctx_create(base + index % ndev, &tl_ctx)) {
-        fprintf(stderr, "[lamsa_b200] cannot open GPU %d: %s\n", base + index % ndev, lb2_last_error());
-        exit(1);
-    }
-    uint64_t lim = (uint64_t)4 << 30;              // direction scratch per launch wave of this thread
-    if (const char* e = getenv("LB2_THREAD_SCRATCH_MB")) lim = (uint64_t)atol(e) << 20;
-    lb2_ctx_set_scratch_limit(tl_ctx, lim);
-    table[(size_t)index] = tl_ctx;
-    for (int k = 0; k < lb2::kAsyncSlots; ++k) {
-        if (lb2_ctx_create(base + index % ndev, &tl_side_ctx[k])) { fprintf(stderr, "[lamsa_b200] %s\n", lb2_last_error()); exit(1); }
-        lb2_ctx_set_scratch_limit(tl_side_ctx[k], lim);
-        side_table[(size_t)index].push_back(tl_side_ctx[k]);
-    }
-}
+void lb2::dropin_bind_thread_ctx(lb2_ctx* c) { tl_ctx = c; }
 
-namespace { void deliver(std::vector<lb2::DpRequest*>& batch, const lb2_result* results, const cigar32_t* pool); }
-struct lb2::DpAsync {
-    lb2_batch* b = nullptr;
-    std::vector<DpRequest*> reqs;
-};
-lb2::DpAsync* lb2::dropin_dp_async_submit(std::vector<DpRequest*>& batch, int slot) {
-    if (slot < 0 || slot >= kAsyncSlots || !tl_side_ctx[slot]) { fprintf(stderr, "[lamsa_b200] asynchronous DP batch outside a scheduler thread\n"); exit(1); }
-    lb2_ctx* tl_slow_ctx = tl_side_ctx[slot];
-    DpAsync* a = new DpAsync();
-    a->reqs = batch;
-    std::vector<lb2_task> tasks(batch.size());
-    for (size_t i = 0; i < batch.size(); ++i) tasks[i] = batch[i]->task;
-    if (lb2_batch_create(tl_slow_ctx, (int64_t)tasks.size(), tasks.data(), &a->b) || lb2_batch_upload(a->b) || lb2_batch_compute_async(a->b)) {
-        fprintf(stderr, "[lamsa_b200] DP launch failed: %s\n", lb2_last_error()); exit(1);
-    }
-    return a;
-}
-bool lb2::dropin_dp_async_done(DpAsync* a) { return lb2_batch_compute_done(a->b) != 0; }
-void lb2::dropin_dp_async_finish(DpAsync* a) {
-    std::vector<lb2_result> results(a->reqs.size());
-    const cigar32_t* pool = nullptr; int64_t pn = 0;
-    if (lb2_batch_compute_wait(a->b, nullptr) || lb2_batch_download_view(a->b, results.data(), &pool, &pn)) {
-        fprintf(stderr, "[lamsa_b200] DP batch failed: %s\n", lb2_last_error()); exit(1);
-    }
-    deliver(a->reqs, results.data(), pool);
-    lb2_batch_destroy(a->b);
-    delete a;
-}
-// open the drop-in context from a helper thread (CUDA start-up overlaps the caller's own start-up)
-// Hardware work queues.  The batch producer drives tens of streams (4 contexts x 6 streams per scheduler
-// thread); with CUDA's default of 8 hardware queues they alias and independent batches queue behind each other.
-// Measured, chunk of 4 096 reads: 4 scheduler threads need 0.60 s with 8 queues, 0.27 s with 16, 0.25 s with
-// 32 -- but CUDA start-up on a cold box grows from about 2 s (8) to 3-5 s (16) and 4.6 s and more (32).  So the
-// default is 8 queues with two scheduler threads per GPU (0.38 s per chunk) for small runs and 32 queues with
-// eight threads for runs with 100 MB of reads or more (see below); CUDA_DEVICE_MAX_CONNECTIONS in the
-// environment, or LB2_MAX_CONNECTIONS=n (set from here; it only counts before CUDA starts), overrides.
+// Opens the batch producer's GPUs (contexts, batch slots, device threads: producer.cu) from a helper thread,
+// so that CUDA start-up overlaps the caller's own start-up (index loading).  Optional.
 extern "C" void lb2_dropin_warmup(void) {
-    if (const char* e = getenv("LB2_MAX_CONNECTIONS")) { if (*e) setenv("CUDA_DEVICE_MAX_CONNECTIONS", e, 0); }
-    else if (!getenv("CUDA_DEVICE_MAX_CONNECTIONS")) {
-        // No setting given: decide by the size of the run.  The last command-line argument of `lamsa aln` is the
-        // read file; from about 100 MB of reads (10^4 reads of 10 kbp) the faster steady state of 32 queues pays
-        // for their slower start-up (measured: 20 000 x 10 kbp reads 7.3 s against 10.0 s, 8 000 x 5 kbp reads
-        // 4.7 s against 3.0 s).
-        FILE* f = fopen("/proc/self/cmdline", "rb");
-        if (f) {
-            std::vector<char> buf(1 << 16);
-            const size_t n = fread(buf.data(), 1, buf.size() - 1, f);
-            fclose(f);
-            size_t last = 0;
-            for (size_t i = 0; i + 1 < n; ++i) if (buf[i] == 0) last = i + 1;
-            buf[n] = 0;
-            struct stat st;
-            if (n > 0 && stat(buf.data() + last, &st) == 0 && S_ISREG(st.st_mode) && st.st_size >= (off_t)100 << 20)
-                setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
-        }
-    }
-    if (getenv("LB2_FIBER_STATS")) {
-        const char* q = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
-        fprintf(stderr, "[lamsa_b200] hardware work queues: %s\n", q ? q : "8 (CUDA default)");
-    }
-    std::thread([] { default_ctx(); }).detach();
+    std::thread([] { lb2::producer_warmup(); }).detach();
 }
 namespace {
 

@@ -1,0 +1,615 @@
+// producer.cu -- the batch producer: the per-read host control flow of LAMSA's aligner (the worker
+// loop of src/lamsa_aln.c:825-891, restated by lamsa_b200/host/aln_core.c) runs as thousands of
+// user-level fibers on the host cores, and every banded-DP / chaining call a fiber makes is parked,
+// classified and copied by the thread that runs it, and served by ONE submitter per GPU:
+//
+//   worker threads (one per host core)      device (one per GPU)
+//   ----------------------------------      -------------------------------------------------------
+//   run fibers until they park        --->  pending groups (tasks already packed: dp_pack.h TaskBlob)
+//   hand the parked requests over            submitter thread: concatenates what is pending into one
+//   as a packed group                        batch per free slot (lb2::batch_create_staged), H2D, launch
+//   <--- inbox: fibers whose requests        one completer thread per slot: waits for the batch's event,
+//        were served                         reads results + CIGARs back, writes them into the callers'
+//                                            out-pointers, returns the fibers to their home threads
+//                                            chaining thread: parked frag_line_BCC / _remain requests of
+//                                            all threads as one batch per stage
+//
+// A launch therefore carries the requests of ALL threads that parked since the last launch (thousands
+// when tens of thousands of reads are in flight), batches overlap (slot k+1 is packed and launched while
+// slot k runs; long tasks travel in a slot of their own so that short ones are not held back by them),
+// and nothing but these few device threads ever touches CUDA.  Dependent calls of one read
+// (merge_cigar loops, the three stages of ksw_bi_extend, the read-level stages) simply take several
+// rounds while the other reads keep the batches full; results are bit-identical because every request
+// is served by the same kernels as a batch of one.
+//
+// lb2_worker_spawn / lb2_worker_join have the signatures of pthread_create / pthread_join.
+#include <pthread.h>
+#include <sys/mman.h>
+#include <ucontext.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "ctx_internal.h"
+#include "dp_pack.h"
+#include "dropin_internal.h"
+
+namespace {
+
+using Clock = std::chrono::steady_clock;
+double secs(Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double>(b - a).count(); }
+
+#if defined(__x86_64__) && !defined(LB2_FIBER_UCONTEXT)
+#define LB2_FAST_SWITCH 1
+extern "C" void lb2_fiber_swap(void** save_sp, void* load_sp);      // fiber_switch.cpp
+extern "C" void lb2_fiber_entry_thunk(void);
+#else
+#define LB2_FAST_SWITCH 0
+#endif
+
+int env_i(const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; }
+bool verbose() { static const bool v = getenv("LB2_FIBER_STATS") != nullptr; return v; }
+
+struct Worker;
+struct Fiber {
+#if LB2_FAST_SWITCH
+    void* sp = nullptr;                  // saved stack pointer while the fiber is not running
+#else
+    ucontext_t ctx;
+#endif
+    void* map = nullptr; size_t map_bytes = 0;      // the mapping: one guard page + the stack
+    void* (*fn)(void*) = nullptr; void* arg = nullptr;
+    Worker* home = nullptr;
+    bool done = false;
+};
+
+// requests one worker thread parked since its last hand-over, packed for the device
+struct DpGroup {
+    lb2::TaskBlob blob;
+    std::vector<lb2::DpRequest*> reqs;
+    std::vector<Fiber*> owners;
+};
+struct SdpGroup {
+    std::vector<lb2::SdpRequest*> reqs;
+    std::vector<Fiber*> owners;
+};
+
+struct Device;
+struct Worker {                          // one OS thread
+    int index = 0;
+    Device* dev = nullptr;
+#if LB2_FAST_SWITCH
+    void* main_sp = nullptr;
+#else
+    ucontext_t main;
+#endif
+    Fiber* cur = nullptr;
+    std::deque<Fiber*> resumed, fresh;   // run queue: fibers with a served request first, then fibers not started yet
+    std::mutex in_mu; std::condition_variable in_cv; std::vector<Fiber*> inbox;
+    std::atomic<int> inbox_n{0};
+    DpGroup* fast = nullptr; DpGroup* slow = nullptr; SdpGroup* sdp = nullptr;
+    size_t live = 0;
+    int64_t switches = 0, handovers = 0;
+    double idle_s = 0;
+};
+thread_local Worker* tl_worker = nullptr;
+
+// ---- the device side ---------------------------------------------------------------------------
+constexpr int kFastSlots = 3, kSlots = kFastSlots + 1;      // the last slot serves long tasks
+struct Slot {
+    lb2_ctx* ctx = nullptr;
+    lb2_batch* batch = nullptr;
+    std::vector<DpGroup*> groups;
+    bool busy = false, launched = false;
+    std::thread completer;
+};
+struct Device {
+    int device = 0;
+    bool loopback = false;                       // self test: no GPU, requests are handed straight back
+    lb2_ctx* sdp_ctx = nullptr;
+    std::mutex mu;
+    std::condition_variable cv_submit, cv_slot, cv_sdp;
+    std::vector<DpGroup*> pend_fast, pend_slow;
+    int64_t pend_fast_tasks = 0, pend_slow_tasks = 0;
+    Clock::time_point pend_fast_since;           // arrival of the oldest pending group
+    std::vector<SdpGroup*> pend_sdp;
+    Slot slot[kSlots];
+    bool stop = false;
+    std::thread submitter, sdp_thread;
+    // statistics (under mu)
+    std::vector<int> batch_tasks;
+    int64_t dp_tasks = 0, slow_batches = 0, slow_tasks = 0, sdp_reqs = 0, sdp_batches = 0;
+    double pack_s = 0, deliver_s = 0, sdp_s = 0, kernel_ms = 0;
+};
+
+void route_home(std::vector<Fiber*>& owners) {
+    // group by home thread: one lock and one wake-up per thread
+    std::sort(owners.begin(), owners.end(), [](Fiber* a, Fiber* b) { return a->home < b->home; });
+    for (size_t i = 0; i < owners.size();) {
+        Worker* w = owners[i]->home;
+        size_t j = i;
+        while (j < owners.size() && owners[j]->home == w) ++j;
+        {
+            std::lock_guard<std::mutex> lk(w->in_mu);
+            w->inbox.insert(w->inbox.end(), owners.begin() + (long)i, owners.begin() + (long)j);
+            w->inbox_n.store((int)w->inbox.size(), std::memory_order_release);
+        }
+        w->in_cv.notify_one();
+        i = j;
+    }
+}
+
+[[noreturn]] void die(const char* what) {
+    fprintf(stderr, "[lamsa_b200] %s: %s\n", what, lb2_last_error());
+    exit(1);
+}
+
+// results of a finished batch -> the callers' out-pointers (CIGARs malloc'd with the capacity the reference's
+// doubling pushes would have reached, src/ksw.c:506-516)
+void deliver_slot(Device* d, Slot& s) {
+    const auto t0 = Clock::now();
+    int64_t n = 0;
+    for (DpGroup* g : s.groups) n += (int64_t)g->reqs.size();
+    std::vector<lb2_result> results((size_t)n);
+    const cigar32_t* pool = nullptr; int64_t pn = 0;
+    float ms = 0;
+    if (lb2::batch_wait_blocking(s.batch) || lb2_batch_compute_wait(s.batch, &ms) ||
+        lb2_batch_download_view(s.batch, results.data(), &pool, &pn)) die("DP batch failed");
+    int64_t at = 0;
+    std::vector<Fiber*> owners;
+    owners.reserve((size_t)n);
+    for (DpGroup* g : s.groups) {
+        for (size_t i = 0; i < g->reqs.size(); ++i, ++at) {
+            lb2::DpRequest* p = g->reqs[i];
+            const lb2_result& r = results[(size_t)at];
+            *p->res = r;
+            if (p->cig) {
+                if (r.n_cigar > 0) {
+                    cigar32_t* out = (cigar32_t*)malloc(sizeof(cigar32_t) * (size_t)r.reserved);
+                    memcpy(out, pool + r.cigar_off, sizeof(cigar32_t) * (size_t)r.n_cigar);
+                    *p->cig = out;
+                } else *p->cig = nullptr;
+            }
+        }
+        owners.insert(owners.end(), g->owners.begin(), g->owners.end());
+        delete g;
+    }
+    s.groups.clear();
+    lb2_batch_destroy(s.batch);
+    s.batch = nullptr;
+    route_home(owners);
+    std::lock_guard<std::mutex> lk(d->mu);
+    d->deliver_s += secs(t0, Clock::now());
+    d->kernel_ms += ms;
+}
+
+void completer_main(Device* d, int k) {
+    Slot& s = d->slot[k];
+    cudaSetDevice(d->device);
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(d->mu);
+            d->cv_slot.wait(lk, [&] { return d->stop || s.launched; });
+            if (!s.launched) return;
+        }
+        deliver_slot(d, s);
+        {
+            std::lock_guard<std::mutex> lk(d->mu);
+            s.launched = false; s.busy = false;
+        }
+        d->cv_submit.notify_one();
+    }
+}
+
+// Gather policy.  A free slot takes everything that is pending at once when the GPU has nothing else to do
+// (latency first); while other batches are in flight it waits until LB2_MIN_BATCH tasks have gathered or the
+// oldest pending group is LB2_GATHER_US old (throughput: fewer, larger launches).
+void submitter_main(Device* d) {
+    cudaSetDevice(d->device);
+    static const int min_batch = env_i("LB2_MIN_BATCH", 2048), gather_us = env_i("LB2_GATHER_US", 300);
+    for (;;) {
+        std::vector<DpGroup*> take;
+        int k = -1;
+        bool slow = false;
+        {
+            std::unique_lock<std::mutex> lk(d->mu);
+            for (;;) {
+                if (d->stop) return;
+                int free_fast = -1, busy_fast = 0;
+                for (int q = 0; q < kFastSlots; ++q) { if (!d->slot[q].busy) { if (free_fast < 0) free_fast = q; } else ++busy_fast; }
+                if (!d->pend_slow.empty() && !d->slot[kFastSlots].busy) { k = kFastSlots; slow = true; break; }
+                if (!d->pend_fast.empty() && free_fast >= 0) {
+                    const auto due = d->pend_fast_since + std::chrono::microseconds(gather_us);
+                    if (busy_fast == 0 || d->pend_fast_tasks >= min_batch || Clock::now() >= due) { k = free_fast; break; }
+                    // something is running: give the other threads a moment to add to this launch
+                    d->cv_submit.wait_until(lk, due);
+                    continue;
+                }
+                d->cv_submit.wait(lk);
+            }
+            if (slow) { take.swap(d->pend_slow); d->slow_tasks += d->pend_slow_tasks; d->pend_slow_tasks = 0; ++d->slow_batches; }
+            else { take.swap(d->pend_fast); d->batch_tasks.push_back((int)d->pend_fast_tasks); d->dp_tasks += d->pend_fast_tasks; d->pend_fast_tasks = 0; }
+            d->slot[k].busy = true;
+        }
+        const auto t0 = Clock::now();
+        Slot& s = d->slot[k];
+        std::vector<const lb2::TaskBlob*> blobs;
+        for (DpGroup* g : take) blobs.push_back(&g->blob);
+        if (lb2::batch_create_staged(s.ctx, blobs.data(), (int)blobs.size(), &s.batch) || lb2_batch_upload(s.batch) ||
+            lb2_batch_compute_async(s.batch)) die("DP launch failed");
+        s.groups.swap(take);
+        {
+            std::lock_guard<std::mutex> lk(d->mu);
+            s.launched = true;
+            d->pack_s += secs(t0, Clock::now());
+        }
+        d->cv_slot.notify_all();
+    }
+}
+
+void sdp_main(Device* d) {
+    cudaSetDevice(d->device);
+    lb2::dropin_bind_thread_ctx(d->sdp_ctx);
+    for (;;) {
+        std::vector<SdpGroup*> take;
+        {
+            std::unique_lock<std::mutex> lk(d->mu);
+            d->cv_sdp.wait(lk, [&] { return d->stop || !d->pend_sdp.empty(); });
+            if (d->pend_sdp.empty()) return;
+            take.swap(d->pend_sdp);
+        }
+        const auto t0 = Clock::now();
+        std::vector<Fiber*> owners;
+        int64_t nreq = 0; int nb = 0;
+        for (int stage = 1; stage <= 2; ++stage) {
+            std::vector<lb2::SdpRequest*> grp;
+            for (SdpGroup* g : take) for (lb2::SdpRequest* q : g->reqs) if (q->stage == stage) grp.push_back(q);
+            if (!grp.empty()) { lb2::dropin_submit_sdp(grp); ++nb; nreq += (int64_t)grp.size(); }
+        }
+        for (SdpGroup* g : take) { owners.insert(owners.end(), g->owners.begin(), g->owners.end()); delete g; }
+        route_home(owners);
+        std::lock_guard<std::mutex> lk(d->mu);
+        d->sdp_s += secs(t0, Clock::now()); d->sdp_reqs += nreq; d->sdp_batches += nb;
+    }
+}
+
+// self test: the "device" hands every request straight back from another thread
+void loopback_main(Device* d) {
+    for (;;) {
+        std::vector<DpGroup*> take;
+        {
+            std::unique_lock<std::mutex> lk(d->mu);
+            d->cv_submit.wait(lk, [&] { return d->stop || !d->pend_fast.empty(); });
+            if (d->pend_fast.empty()) return;
+            take.swap(d->pend_fast);
+        }
+        std::vector<Fiber*> owners;
+        for (DpGroup* g : take) { owners.insert(owners.end(), g->owners.begin(), g->owners.end()); delete g; }
+        route_home(owners);
+    }
+}
+
+// devices are opened once per process (from lb2_dropin_warmup's helper thread, or by the first join) and
+// never torn down: the process is over when the aligner returns
+std::mutex g_dev_mu;
+std::vector<Device*> g_devices;
+Device* g_loopback = nullptr;
+
+// Opens the GPUs on first use.  A process whose workers never park a request (a build that links CPU
+// implementations of the entry points, used to test the read pipeline on a box without a GPU) may run without
+// one: the failure is kept and raised by the first request that needs a device.
+std::string g_dev_error;
+std::vector<Device*>& devices() {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (!g_devices.empty() || !g_dev_error.empty()) return g_devices;
+    const auto t0 = Clock::now();
+    const int ndev = std::max(1, env_i("LB2_DEVICES", 1)), base = env_i("LB2_DEVICE", 0);
+    const uint64_t scratch = (uint64_t)env_i("LB2_SLOT_SCRATCH_MB", 8192) << 20;
+    std::vector<Device*> opened;
+    for (int k = 0; k < ndev; ++k) {
+        Device* d = new Device();
+        d->device = base + k;
+        bool ok = true;
+        for (int q = 0; q < kSlots && ok; ++q) {
+            ok = lb2_ctx_create(d->device, &d->slot[q].ctx) == 0;
+            if (ok) lb2_ctx_set_scratch_limit(d->slot[q].ctx, scratch);
+        }
+        ok = ok && lb2_ctx_create(d->device, &d->sdp_ctx) == 0;
+        if (!ok) { g_dev_error = lb2_last_error(); return g_devices; }      // g_devices stays empty
+        opened.push_back(d);
+    }
+    for (Device* d : opened) {
+        d->submitter = std::thread(submitter_main, d);
+        d->sdp_thread = std::thread(sdp_main, d);
+        for (int q = 0; q < kSlots; ++q) d->slot[q].completer = std::thread(completer_main, d, q);
+    }
+    g_devices = opened;
+    if (verbose()) fprintf(stderr, "[lamsa_b200] %d GPU(s) opened in %.3f s (%d batch slots each)\n", ndev, secs(t0, Clock::now()), kSlots);
+    return g_devices;
+}
+[[noreturn]] void no_device() {
+    fprintf(stderr, "[lamsa_b200] cannot open the GPU: %s \n", g_dev_error.c_str());
+    exit(1);
+}
+
+// ---- fibers ------------------------------------------------------------------------------------
+size_t stack_bytes() {
+    static const size_t v = (size_t)env_i("LB2_FIBER_STACK_KB", 1024) * 1024;
+    return v;
+}
+
+#if LB2_FAST_SWITCH
+inline void switch_to_fiber(Worker* w, Fiber* f) { lb2_fiber_swap(&w->main_sp, f->sp); }
+inline void switch_to_sched(Worker* w, Fiber* f) { lb2_fiber_swap(&f->sp, w->main_sp); }
+#else
+void trampoline(unsigned lo, unsigned hi) {
+    Fiber* f = (Fiber*)(((uintptr_t)hi << 32) | (uintptr_t)lo);
+    f->fn(f->arg);
+    f->done = true;
+    swapcontext(&f->ctx, &tl_worker->main);       // never resumed
+}
+inline void switch_to_fiber(Worker* w, Fiber* f) { swapcontext(&w->main, &f->ctx); }
+inline void switch_to_sched(Worker* w, Fiber* f) { swapcontext(&f->ctx, &w->main); }
+#endif
+
+void yield_to_scheduler() {
+    Worker* w = tl_worker;
+    ++w->switches;
+    switch_to_sched(w, w->cur);
+}
+
+void hand_over_dp(Worker* w) {
+    Device* d = w->dev;
+    const bool f = w->fast && !w->fast->reqs.empty(), s = w->slow && !w->slow->reqs.empty();
+    if (!f && !s) return;
+    {
+        std::lock_guard<std::mutex> lk(d->mu);
+        if (f) { if (d->pend_fast.empty()) d->pend_fast_since = Clock::now(); d->pend_fast_tasks += (int64_t)w->fast->reqs.size(); d->pend_fast.push_back(w->fast); }
+        if (s) { d->pend_slow_tasks += (int64_t)w->slow->reqs.size(); d->pend_slow.push_back(w->slow); }
+    }
+    if (f) w->fast = nullptr;
+    if (s) w->slow = nullptr;
+    ++w->handovers;
+    d->cv_submit.notify_one();
+}
+void hand_over_sdp(Worker* w) {
+    if (!w->sdp || w->sdp->reqs.empty()) return;
+    Device* d = w->dev;
+    {
+        std::lock_guard<std::mutex> lk(d->mu);
+        d->pend_sdp.push_back(w->sdp);
+    }
+    w->sdp = nullptr;
+    d->cv_sdp.notify_one();
+}
+
+void worker_main(Worker* w) {
+    tl_worker = w;
+    static const size_t flush_dp = (size_t)env_i("LB2_FLUSH_TASKS", 256), flush_sdp = (size_t)env_i("LB2_FLUSH_READS", 32);
+    while (w->live > 0) {
+        if (w->inbox_n.load(std::memory_order_acquire) > 0) {
+            std::lock_guard<std::mutex> lk(w->in_mu);
+            w->resumed.insert(w->resumed.end(), w->inbox.begin(), w->inbox.end());
+            w->inbox.clear();
+            w->inbox_n.store(0, std::memory_order_release);
+        }
+        Fiber* f = nullptr;
+        if (!w->resumed.empty()) { f = w->resumed.front(); w->resumed.pop_front(); }
+        else if (!w->fresh.empty()) { f = w->fresh.front(); w->fresh.pop_front(); }
+        if (f) {
+            w->cur = f;
+            switch_to_fiber(w, f);
+            w->cur = nullptr;
+            if (f->done) { --w->live; munmap(f->map, f->map_bytes); f->map = nullptr; }
+            // hand over early when enough has gathered: the device should not wait for this thread's whole queue
+            if ((w->fast && w->fast->reqs.size() >= flush_dp) || (w->slow && w->slow->reqs.size() >= flush_dp / 8 + 1)) hand_over_dp(w);
+            if (w->sdp && w->sdp->reqs.size() >= flush_sdp) hand_over_sdp(w);
+            continue;
+        }
+        if (w->live == 0) break;
+        hand_over_dp(w);
+        hand_over_sdp(w);
+        const auto t0 = Clock::now();
+        std::unique_lock<std::mutex> lk(w->in_mu);
+        w->in_cv.wait(lk, [&] { return !w->inbox.empty(); });
+        w->idle_s += secs(t0, Clock::now());
+    }
+    tl_worker = nullptr;
+}
+
+std::mutex g_spawn_mu;
+std::vector<Fiber*> g_spawned;       // workers created since the last join
+int g_selftest_threads = 0;
+
+int host_threads() {
+    if (g_selftest_threads > 0) return g_selftest_threads;
+    int v = env_i("LB2_HOST_THREADS", (int)std::thread::hardware_concurrency());
+    if (v < 1) v = 1;
+    return v > 256 ? 256 : v;
+}
+
+void run_all(std::vector<Fiber*>& fibers) {
+    const auto t0 = Clock::now();
+    std::vector<Device*> devs;
+    if (g_selftest_threads > 0) {
+        if (!g_loopback) { g_loopback = new Device(); g_loopback->loopback = true; g_loopback->submitter = std::thread(loopback_main, g_loopback); }
+        devs.push_back(g_loopback);
+    } else devs = devices();
+    const int K = std::max(1, std::min(host_threads(), (int)fibers.size()));
+    std::vector<Worker> workers((size_t)K);
+    for (int k = 0; k < K; ++k) { workers[(size_t)k].index = k; workers[(size_t)k].dev = devs.empty() ? nullptr : devs[(size_t)k % devs.size()]; }
+    for (size_t i = 0; i < fibers.size(); ++i) {
+        Worker& w = workers[i % (size_t)K];
+        fibers[i]->home = &w;
+        w.fresh.push_back(fibers[i]);
+        ++w.live;
+    }
+    std::vector<std::thread> th;
+    for (int k = 1; k < K; ++k) th.emplace_back(worker_main, &workers[(size_t)k]);
+    worker_main(&workers[0]);
+    for (auto& t : th) t.join();
+    if (verbose() && g_selftest_threads == 0) {
+        int64_t sw = 0, ho = 0; double idle = 0;
+        for (Worker& w : workers) { sw += w.switches; ho += w.handovers; idle += w.idle_s; }
+        const double wall = secs(t0, Clock::now());
+        fprintf(stderr, "[lamsa_b200] %zu workers on %d threads: %.3f s, %lld switches, %lld hand-overs, threads idle %.0f %% of the time\n",
+                fibers.size(), K, wall, (long long)sw, (long long)ho, 100.0 * idle / (wall * K));
+        for (Device* d : devs) {
+            std::lock_guard<std::mutex> lk(d->mu);
+            std::vector<int> bt = d->batch_tasks;
+            std::sort(bt.begin(), bt.end());
+            const int med = bt.empty() ? 0 : bt[bt.size() / 2], mx = bt.empty() ? 0 : bt.back();
+            fprintf(stderr, "[lamsa_b200] GPU %d: %lld DP tasks in %zu launches (median %d per launch, max %d), %lld long DP tasks in %lld side batches, "
+                            "%lld chaining requests in %lld batches; submitter packing %.3f s, completers %.3f s, kernels %.3f s, chaining thread %.3f s\n",
+                    d->device, (long long)d->dp_tasks, bt.size(), med, mx, (long long)d->slow_tasks, (long long)d->slow_batches,
+                    (long long)d->sdp_reqs, (long long)d->sdp_batches, d->pack_s, d->deliver_s, d->kernel_ms * 1e-3, d->sdp_s);
+        }
+    }
+    for (Fiber* f : fibers) delete f;
+    fibers.clear();
+}
+
+}  // namespace
+
+namespace lb2 {
+bool fiber_active() { return tl_worker && tl_worker->cur; }
+
+// tasks of more than LB2_FAST_ROWS target rows travel in the slot for long tasks: a batch lasts as long as its
+// longest task, and the owners of short tasks should resume early
+void fiber_wait_dp(DpRequest* r) {
+    Worker* w = tl_worker;
+    if (!w->dev) no_device();
+    static const int fast_rows = env_i("LB2_FAST_ROWS", 256);
+    const bool slow = fast_rows > 0 && r->task.tlen > fast_rows;
+    DpGroup*& g = slow ? w->slow : w->fast;
+    if (!g) g = new DpGroup();
+    if (!w->dev->loopback) {
+        char msg[200];
+        if (g->blob.add(r->task, -1, msg, sizeof msg)) { fprintf(stderr, "[lamsa_b200] DP task rejected: %s\n", msg); exit(1); }
+    }
+    g->reqs.push_back(r); g->owners.push_back(w->cur);
+    yield_to_scheduler();
+}
+void fiber_wait_sdp(SdpRequest* r) {
+    Worker* w = tl_worker;
+    if (!w->dev) no_device();
+    if (!w->sdp) w->sdp = new SdpGroup();
+    w->sdp->reqs.push_back(r); w->sdp->owners.push_back(w->cur);
+    yield_to_scheduler();
+}
+void producer_warmup() { devices(); }
+}  // namespace lb2
+
+#if LB2_FAST_SWITCH
+extern "C" void lb2_fiber_main(void* p) {                 // entered once per fiber from lb2_fiber_entry_thunk
+    Fiber* f = (Fiber*)p;
+    f->fn(f->arg);
+    f->done = true;
+    switch_to_sched(tl_worker, f);                         // never resumed
+    abort();
+}
+#endif
+
+// Let the other workers of this thread run (a worker that has to wait for something a sibling produces).
+extern "C" void lb2_worker_yield(void) {
+    Worker* w = tl_worker;
+    if (!w || !w->cur) { std::this_thread::yield(); return; }
+    w->fresh.push_back(w->cur);
+    yield_to_scheduler();
+}
+
+// ---- self test of the scheduler and the context switch (no GPU needed; tests/test_fibers.py) ----------
+namespace {
+struct SelfTestArg { int id, yields; double result; long long sum; };
+void* selftest_worker(void* p) {
+    SelfTestArg* a = (SelfTestArg*)p;
+    double acc = (double)a->id;
+    long long sum = 0;
+    volatile int local[64];
+    for (int k = 0; k < 64; ++k) local[k] = a->id * 64 + k;
+    for (int y = 0; y < a->yields; ++y) {
+        acc = acc * 1.0000001 + (double)y * 0.5;          // floating-point state across switches
+        for (int k = 0; k < 64; ++k) sum += local[k] ^ y;  // stack contents across switches
+        if (y & 1) lb2_worker_yield();                     // plain yield inside the thread
+        else { lb2::DpRequest r{}; lb2::fiber_wait_dp(&r); }   // park, travel through the (loopback) device, come back
+    }
+    a->result = acc; a->sum = sum;
+    return nullptr;
+}
+}  // namespace
+// Runs n workers that yield `yields` times each (alternating between a plain yield and a request that goes
+// through another thread and back) on `threads` scheduler threads; returns the number of workers whose results
+// differ from the same computation done without any switch (0 = pass).
+extern "C" int lb2_fiber_selftest(int n, int yields, int threads) {
+    g_selftest_threads = threads > 0 ? threads : 1;
+    std::vector<SelfTestArg> args((size_t)n);
+    std::vector<pthread_t> ids((size_t)n);
+    for (int i = 0; i < n; ++i) { args[(size_t)i] = SelfTestArg{i, yields, 0.0, 0}; lb2_worker_spawn(&ids[(size_t)i], nullptr, selftest_worker, &args[(size_t)i]); }
+    for (int i = 0; i < n; ++i) lb2_worker_join(ids[(size_t)i], nullptr);
+    g_selftest_threads = 0;
+    int bad = 0;
+    for (int i = 0; i < n; ++i) {
+        double acc = (double)i; long long sum = 0;
+        for (int y = 0; y < yields; ++y) { acc = acc * 1.0000001 + (double)y * 0.5; for (int k = 0; k < 64; ++k) sum += (i * 64 + k) ^ y; }
+        if (acc != args[(size_t)i].result || sum != args[(size_t)i].sum) ++bad;
+    }
+    return bad;
+}
+
+// pthread_create-shaped: registers a worker; it starts when the first of the workers is joined
+extern "C" int lb2_worker_spawn(pthread_t* id, const pthread_attr_t*, void* (*fn)(void*), void* arg) {
+    Fiber* f = new Fiber();
+    f->fn = fn; f->arg = arg;
+    // one inaccessible page below the stack: an overflow faults instead of running into the next mapping
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE), sb = stack_bytes();
+    f->map_bytes = sb + page;
+    f->map = mmap(nullptr, f->map_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE | MAP_STACK, -1, 0);
+    if (f->map == MAP_FAILED) { fprintf(stderr, "[lamsa_b200] cannot map a %zu-byte worker stack\n", f->map_bytes); exit(1); }
+    mprotect(f->map, page, PROT_NONE);
+    char* stack = (char*)f->map + page;
+#if LB2_FAST_SWITCH
+    {   // first switch "returns" into lb2_fiber_entry_thunk with the Fiber* in r12 (frame laid out as lb2_fiber_swap pops it)
+        uintptr_t top = ((uintptr_t)stack + sb) & ~(uintptr_t)15;
+        uint64_t* a = (uint64_t*)(top - 8);                 // return address slot: rsp == top (16-aligned) inside the thunk
+        a[0] = (uint64_t)(uintptr_t)&lb2_fiber_entry_thunk;
+        a[-1] = 0;                                          // rbp
+        a[-2] = 0;                                          // rbx
+        a[-3] = (uint64_t)(uintptr_t)f;                     // r12
+        a[-4] = 0; a[-5] = 0; a[-6] = 0;                    // r13, r14, r15
+        a[-7] = (uint64_t)0x1F80u | ((uint64_t)0x037Fu << 32);   // MXCSR and x87 control word defaults
+        f->sp = (void*)(a - 7);
+    }
+#else
+    getcontext(&f->ctx);
+    f->ctx.uc_stack.ss_sp = stack; f->ctx.uc_stack.ss_size = sb; f->ctx.uc_link = nullptr;
+    const uintptr_t p = (uintptr_t)f;
+    makecontext(&f->ctx, (void (*)())trampoline, 2, (unsigned)(p & 0xffffffffu), (unsigned)(p >> 32));
+#endif
+    std::lock_guard<std::mutex> lk(g_spawn_mu);
+    g_spawned.push_back(f);
+    if (id) *id = (pthread_t)g_spawned.size();
+    return 0;
+}
+
+// pthread_join-shaped: the first join after a series of spawns runs ALL spawned workers to completion
+extern "C" int lb2_worker_join(pthread_t, void** ret) {
+    std::vector<Fiber*> batch;
+    {
+        std::lock_guard<std::mutex> lk(g_spawn_mu);
+        batch.swap(g_spawned);
+    }
+    if (!batch.empty()) run_all(batch);
+    if (ret) *ret = nullptr;
+    return 0;
+}

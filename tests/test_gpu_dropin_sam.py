@@ -18,8 +18,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # (banded DP and sparse-DP chaining both on the GPU; `make -C oracle dropin_sdp`)
 EXES = {"dp": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin"),
         "dp+sdp": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin_sdp"),
-        # + the worker pool run as fibers whose DP / chaining calls are batched (`make -C oracle dropin_fiber`)
-        "fiber": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin_fiber")}
+        # + the alignment stage replaced by this repo's read pipeline (lamsa_b200/host/aln_core.c): reads as worker
+        # fibers, every DP / chaining call served in batches gathered over all reads (`make -C oracle producer`)
+        "producer": os.path.join(ROOT, "oracle", "_ref", "lamsa_b200_aln")}
 FIXTURES = [
     ("small", os.path.join(ROOT, "tests", "golden", "sam_small")),
     ("c1", os.path.join(ROOT, "oracle", "_ref", "sam_c1")),
@@ -41,15 +42,18 @@ def stage(src, dst):
 
 @pytest.mark.parametrize("name,src", FIXTURES, ids=[f[0] for f in FIXTURES])
 @pytest.mark.parametrize("threads", [1, 4])
-@pytest.mark.parametrize("link", ["dp", "dp+sdp", "fiber"])
+@pytest.mark.parametrize("link", ["dp", "dp+sdp", "producer"])
 def test_dropin_sam_identical_to_reference(tmp_path, name, src, threads, link):
     EXE = EXES[link]
     if not os.path.exists(EXE):
         pytest.skip(f"{EXE} not built (needs the reference tree at build time)")
     if not os.path.isdir(src):
         pytest.skip(f"fixture {src} not present")
-    if link == "fiber":
-        threads = 2048 if threads != 1 else 37        # workers = fibers; 37: fewer workers than reads, odd count
+    env = dict(os.environ)
+    if link == "producer":
+        # reads in flight: the default (thousands), or fewer workers than reads with an odd count
+        if threads == 1:
+            env["LB2_READS_IN_FLIGHT"] = "37"
     elif threads != 1 and name not in ("small", "c1"):
         pytest.skip("multi-thread run only on two fixtures")
     work = str(tmp_path / name)
@@ -57,7 +61,7 @@ def test_dropin_sam_identical_to_reference(tmp_path, name, src, threads, link):
     opts = open(os.path.join(work, "cmd.txt")).read().split()
     with open(os.path.join(work, "out.sam"), "w") as f:
         r = subprocess.run([EXE, "aln", "-t", str(threads), "-N", *opts, "ref.fa", "reads.fa"], cwd=work, stdout=f,
-                           stderr=subprocess.PIPE, timeout=1200)
+                           stderr=subprocess.PIPE, timeout=1200, env=env)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     got = [l for l in open(os.path.join(work, "out.sam")) if not l.startswith("@PG")]
     exp = list(open(os.path.join(work, "expected.sam")))
