@@ -918,6 +918,32 @@ extern "C" int lb2_int_peak(lb2_ctx* ctx, double* gops_s16x2, double* gops_s32, 
 
 // ---- internal accessors for the other translation units (ctx_internal.h) ----
 namespace lb2 {
+int ctx_reserve(lb2_ctx* ctx, int64_t n_tasks, size_t pool_bytes, size_t z_bytes, size_t cigar_words) {
+    if (!ctx) return fail("ctx_reserve: ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    lb2_batch* b = new lb2_batch();
+    b->ctx = ctx; b->n = n_tasks;
+    struct Guard { lb2_batch* b; ~Guard() { lb2_batch_destroy(b); } } guard{b};
+    // take no parked set: this call is there to CREATE one
+    Buffers keep[2];
+    { std::lock_guard<std::mutex> lk(ctx->mu); for (int k = 0; k < 2; ++k) { keep[k] = ctx->parked[k]; ctx->parked[k] = Buffers(); } }
+    int rc = alloc_host(b, pool_bytes);
+    if (!rc) {
+        Wave wv; memset(&wv, 0, sizeof wv);
+        wv.z_bytes = z_bytes; wv.ctmp_words = cigar_words;
+        b->waves.push_back(wv);
+        b->dense_cap = cigar_words + 16;
+        rc = alloc_device(b);
+        b->waves.clear();
+    }
+    if (!rc && b->B.h_cigar_cap < cigar_words) {
+        cudaFreeHost(b->B.h_cigar); b->B.h_cigar = nullptr; b->B.h_cigar_cap = 0;
+        if (cudaMallocHost(&b->B.h_cigar, cigar_words * sizeof(cigar32_t)) != cudaSuccess) rc = fail("ctx_reserve: pinned CIGAR buffer");
+        else b->B.h_cigar_cap = cigar_words;
+    }
+    { std::lock_guard<std::mutex> lk(ctx->mu); for (int k = 0; k < 2; ++k) if (keep[k].valid) ctx->parked[k] = keep[k]; }
+    return rc;          // the guard parks the new set in a free place (or releases it when both are taken)
+}
 int batch_wait_blocking(lb2_batch* b) {
     if (!b || !b->enqueued) return fail("batch_wait_blocking: nothing enqueued");
     CU(cudaSetDevice(b->ctx->device));

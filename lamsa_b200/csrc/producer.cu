@@ -61,6 +61,20 @@ extern "C" void lb2_fiber_entry_thunk(void);
 int env_i(const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; }
 bool verbose() { static const bool v = getenv("LB2_FIBER_STATS") != nullptr; return v; }
 
+// LB2_TRACE=<file>: one line per device-thread event (seconds since the first event, thread, what, slot, tasks)
+struct Trace {
+    FILE* f = nullptr; std::mutex mu; Clock::time_point t0;
+    Trace() { const char* e = getenv("LB2_TRACE"); if (e && *e) { f = fopen(e, "w"); t0 = Clock::now(); } }
+    void ev(const char* who, const char* what, int slot, long n) {
+        if (!f) return;
+        const double t = secs(t0, Clock::now());
+        std::lock_guard<std::mutex> lk(mu);
+        fprintf(f, "%.6f %s %s %d %ld\n", t, who, what, slot, n);
+    }
+    ~Trace() { if (f) fclose(f); }
+};
+Trace& trace() { static Trace* t = new Trace(); return *t; }
+
 struct Worker;
 struct Fiber {
 #if LB2_FAST_SWITCH
@@ -100,8 +114,8 @@ struct Worker {                          // one OS thread
     std::atomic<int> inbox_n{0};
     DpGroup* fast = nullptr; DpGroup* slow = nullptr; SdpGroup* sdp = nullptr;
     size_t live = 0;
-    int64_t switches = 0, handovers = 0;
-    double idle_s = 0;
+    int64_t switches = 0, handovers = 0, dp_n = 0, sdp_n = 0;
+    double dev_wait_s = 0, idle_s = 0, fiber_s = 0, pack_s = 0, dp_lat_s = 0, sdp_lat_s = 0, dp_lat_max = 0;
 };
 thread_local Worker* tl_worker = nullptr;
 
@@ -164,8 +178,11 @@ void deliver_slot(Device* d, Slot& s) {
     std::vector<lb2_result> results((size_t)n);
     const cigar32_t* pool = nullptr; int64_t pn = 0;
     float ms = 0;
-    if (lb2::batch_wait_blocking(s.batch) || lb2_batch_compute_wait(s.batch, &ms) ||
-        lb2_batch_download_view(s.batch, results.data(), &pool, &pn)) die("DP batch failed");
+    const int slot_k = (int)(&s - d->slot);
+    if (lb2::batch_wait_blocking(s.batch)) die("DP batch failed");
+    trace().ev("completer", "kernels_done", slot_k, (long)n);
+    if (lb2_batch_compute_wait(s.batch, &ms) || lb2_batch_download_view(s.batch, results.data(), &pool, &pn)) die("DP batch failed");
+    trace().ev("completer", "downloaded", slot_k, (long)n);
     int64_t at = 0;
     std::vector<Fiber*> owners;
     owners.reserve((size_t)n);
@@ -189,6 +206,7 @@ void deliver_slot(Device* d, Slot& s) {
     lb2_batch_destroy(s.batch);
     s.batch = nullptr;
     route_home(owners);
+    trace().ev("completer", "delivered", slot_k, (long)n);
     std::lock_guard<std::mutex> lk(d->mu);
     d->deliver_s += secs(t0, Clock::now());
     d->kernel_ms += ms;
@@ -244,11 +262,13 @@ void submitter_main(Device* d) {
         }
         const auto t0 = Clock::now();
         Slot& s = d->slot[k];
+        { long nt = 0; for (DpGroup* g : take) nt += (long)g->reqs.size(); trace().ev("submitter", "pack_begin", k, nt); }
         std::vector<const lb2::TaskBlob*> blobs;
         for (DpGroup* g : take) blobs.push_back(&g->blob);
         if (lb2::batch_create_staged(s.ctx, blobs.data(), (int)blobs.size(), &s.batch) || lb2_batch_upload(s.batch) ||
             lb2_batch_compute_async(s.batch)) die("DP launch failed");
         s.groups.swap(take);
+        trace().ev("submitter", "launched", k, 0);
         {
             std::lock_guard<std::mutex> lk(d->mu);
             s.launched = true;
@@ -272,6 +292,7 @@ void sdp_main(Device* d) {
         const auto t0 = Clock::now();
         std::vector<Fiber*> owners;
         int64_t nreq = 0; int nb = 0;
+        { long nt = 0; for (SdpGroup* g : take) nt += (long)g->reqs.size(); trace().ev("chaining", "begin", 0, nt); }
         for (int stage = 1; stage <= 2; ++stage) {
             std::vector<lb2::SdpRequest*> grp;
             for (SdpGroup* g : take) for (lb2::SdpRequest* q : g->reqs) if (q->stage == stage) grp.push_back(q);
@@ -279,6 +300,7 @@ void sdp_main(Device* d) {
         }
         for (SdpGroup* g : take) { owners.insert(owners.end(), g->owners.begin(), g->owners.end()); delete g; }
         route_home(owners);
+        trace().ev("chaining", "end", 0, (long)nreq);
         std::lock_guard<std::mutex> lk(d->mu);
         d->sdp_s += secs(t0, Clock::now()); d->sdp_reqs += nreq; d->sdp_batches += nb;
     }
@@ -323,7 +345,14 @@ std::vector<Device*>& devices() {
         bool ok = true;
         for (int q = 0; q < kSlots && ok; ++q) {
             ok = lb2_ctx_create(d->device, &d->slot[q].ctx) == 0;
-            if (ok) lb2_ctx_set_scratch_limit(d->slot[q].ctx, scratch);
+            if (ok) {
+                lb2_ctx_set_scratch_limit(d->slot[q].ctx, scratch);
+                // steady-state sizes up front: growing pinned or device buffers later stalls every slot for milliseconds
+                const bool slow = q == kFastSlots;
+                for (int r = 0; r < 2 && ok; ++r)
+                    ok = lb2::ctx_reserve(d->slot[q].ctx, slow ? 4096 : 16384, (size_t)(slow ? 64 : 16) << 20,
+                                          (size_t)(slow ? 1024 : 256) << 20, (size_t)(slow ? 8 : 4) << 20) == 0;
+            }
         }
         ok = ok && lb2_ctx_create(d->device, &d->sdp_ctx) == 0;
         if (!ok) { g_dev_error = lb2_last_error(); return g_devices; }      // g_devices stays empty
@@ -369,7 +398,18 @@ void yield_to_scheduler() {
     switch_to_sched(w, w->cur);
 }
 
+[[noreturn]] void no_device();
+void bind_device(Worker* w) {
+    if (w->dev) return;
+    const auto t0 = Clock::now();
+    std::vector<Device*>& devs = devices();
+    if (devs.empty()) no_device();
+    w->dev = devs[(size_t)w->index % devs.size()];
+    w->dev_wait_s += secs(t0, Clock::now());
+}
+
 void hand_over_dp(Worker* w) {
+    bind_device(w);
     Device* d = w->dev;
     const bool f = w->fast && !w->fast->reqs.empty(), s = w->slow && !w->slow->reqs.empty();
     if (!f && !s) return;
@@ -385,6 +425,7 @@ void hand_over_dp(Worker* w) {
 }
 void hand_over_sdp(Worker* w) {
     if (!w->sdp || w->sdp->reqs.empty()) return;
+    bind_device(w);
     Device* d = w->dev;
     {
         std::lock_guard<std::mutex> lk(d->mu);
@@ -409,7 +450,9 @@ void worker_main(Worker* w) {
         else if (!w->fresh.empty()) { f = w->fresh.front(); w->fresh.pop_front(); }
         if (f) {
             w->cur = f;
+            const auto tf0 = Clock::now();
             switch_to_fiber(w, f);
+            w->fiber_s += secs(tf0, Clock::now());
             w->cur = nullptr;
             if (f->done) { --w->live; munmap(f->map, f->map_bytes); f->map = nullptr; }
             // hand over early when enough has gathered: the device should not wait for this thread's whole queue
@@ -425,6 +468,7 @@ void worker_main(Worker* w) {
         w->in_cv.wait(lk, [&] { return !w->inbox.empty(); });
         w->idle_s += secs(t0, Clock::now());
     }
+    trace().ev("worker", "exit", w->index, (long)w->switches);
     tl_worker = nullptr;
 }
 
@@ -434,21 +478,23 @@ int g_selftest_threads = 0;
 
 int host_threads() {
     if (g_selftest_threads > 0) return g_selftest_threads;
-    int v = env_i("LB2_HOST_THREADS", (int)std::thread::hardware_concurrency());
+    // the device threads (submitter, completers, chaining) need cores of their own
+    int v = env_i("LB2_HOST_THREADS", std::max(1, (int)std::thread::hardware_concurrency() - 3));
     if (v < 1) v = 1;
     return v > 256 ? 256 : v;
 }
 
 void run_all(std::vector<Fiber*>& fibers) {
     const auto t0 = Clock::now();
-    std::vector<Device*> devs;
-    if (g_selftest_threads > 0) {
-        if (!g_loopback) { g_loopback = new Device(); g_loopback->loopback = true; g_loopback->submitter = std::thread(loopback_main, g_loopback); }
-        devs.push_back(g_loopback);
-    } else devs = devices();
+    // The GPUs are opened by lb2_dropin_warmup's helper thread (or by the first request); the workers start at once
+    // and only the first hand-over of a thread waits for its device, so reading and parsing the first reads overlap
+    // CUDA start-up.
+    if (g_selftest_threads > 0 && !g_loopback) {
+        g_loopback = new Device(); g_loopback->loopback = true; g_loopback->submitter = std::thread(loopback_main, g_loopback);
+    }
     const int K = std::max(1, std::min(host_threads(), (int)fibers.size()));
     std::vector<Worker> workers((size_t)K);
-    for (int k = 0; k < K; ++k) { workers[(size_t)k].index = k; workers[(size_t)k].dev = devs.empty() ? nullptr : devs[(size_t)k % devs.size()]; }
+    for (int k = 0; k < K; ++k) { workers[(size_t)k].index = k; workers[(size_t)k].dev = g_selftest_threads > 0 ? g_loopback : nullptr; }
     for (size_t i = 0; i < fibers.size(); ++i) {
         Worker& w = workers[i % (size_t)K];
         fibers[i]->home = &w;
@@ -459,12 +505,17 @@ void run_all(std::vector<Fiber*>& fibers) {
     for (int k = 1; k < K; ++k) th.emplace_back(worker_main, &workers[(size_t)k]);
     worker_main(&workers[0]);
     for (auto& t : th) t.join();
+    std::vector<Device*> devs;
+    if (g_selftest_threads == 0) { std::lock_guard<std::mutex> lk(g_dev_mu); devs = g_devices; }
     if (verbose() && g_selftest_threads == 0) {
-        int64_t sw = 0, ho = 0; double idle = 0;
-        for (Worker& w : workers) { sw += w.switches; ho += w.handovers; idle += w.idle_s; }
+        int64_t sw = 0, ho = 0, dn = 0, sn = 0; double dw = 0, idle = 0, fib = 0, pack = 0, dl = 0, sl = 0, dmax = 0;
+        for (Worker& w : workers) { dw = std::max(dw, w.dev_wait_s); sw += w.switches; ho += w.handovers; idle += w.idle_s; fib += w.fiber_s; pack += w.pack_s;
+                                    dn += w.dp_n; sn += w.sdp_n; dl += w.dp_lat_s; sl += w.sdp_lat_s; dmax = std::max(dmax, w.dp_lat_max); }
         const double wall = secs(t0, Clock::now());
-        fprintf(stderr, "[lamsa_b200] %zu workers on %d threads: %.3f s, %lld switches, %lld hand-overs, threads idle %.0f %% of the time\n",
-                fibers.size(), K, wall, (long long)sw, (long long)ho, 100.0 * idle / (wall * K));
+        fprintf(stderr, "[lamsa_b200] %zu workers on %d threads: %.3f s, %lld switches, %lld hand-overs; of the threads' time %.0f %% inside workers "
+                        "(%.0f %% of it packing DP requests), %.0f %% idle, up to %.3f s waiting for the GPU to open; a DP request waits %.2f ms on average (max %.1f), a chaining request %.2f ms\n",
+                fibers.size(), K, wall, (long long)sw, (long long)ho, 100.0 * fib / (wall * K), fib > 0 ? 100.0 * pack / fib : 0.0, 100.0 * idle / (wall * K), dw,
+                dn ? 1e3 * dl / dn : 0.0, 1e3 * dmax, sn ? 1e3 * sl / sn : 0.0);
         for (Device* d : devs) {
             std::lock_guard<std::mutex> lk(d->mu);
             std::vector<int> bt = d->batch_tasks;
@@ -489,24 +540,31 @@ bool fiber_active() { return tl_worker && tl_worker->cur; }
 // longest task, and the owners of short tasks should resume early
 void fiber_wait_dp(DpRequest* r) {
     Worker* w = tl_worker;
-    if (!w->dev) no_device();
     static const int fast_rows = env_i("LB2_FAST_ROWS", 256);
     const bool slow = fast_rows > 0 && r->task.tlen > fast_rows;
     DpGroup*& g = slow ? w->slow : w->fast;
     if (!g) g = new DpGroup();
-    if (!w->dev->loopback) {
+    const auto t0 = Clock::now();
+    if (g_selftest_threads == 0) {
         char msg[200];
         if (g->blob.add(r->task, -1, msg, sizeof msg)) { fprintf(stderr, "[lamsa_b200] DP task rejected: %s\n", msg); exit(1); }
     }
     g->reqs.push_back(r); g->owners.push_back(w->cur);
+    const auto t1 = Clock::now();
+    w->pack_s += secs(t0, t1);
     yield_to_scheduler();
+    w = tl_worker;
+    const double lat = secs(t1, Clock::now());
+    w->dp_lat_s += lat; ++w->dp_n; if (lat > w->dp_lat_max) w->dp_lat_max = lat;
 }
 void fiber_wait_sdp(SdpRequest* r) {
     Worker* w = tl_worker;
-    if (!w->dev) no_device();
     if (!w->sdp) w->sdp = new SdpGroup();
     w->sdp->reqs.push_back(r); w->sdp->owners.push_back(w->cur);
+    const auto t1 = Clock::now();
     yield_to_scheduler();
+    w = tl_worker;
+    w->sdp_lat_s += secs(t1, Clock::now()); ++w->sdp_n;
 }
 void producer_warmup() { devices(); }
 }  // namespace lb2

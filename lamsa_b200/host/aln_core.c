@@ -53,8 +53,7 @@ extern void get_reg(aln_res *res, aln_reg *reg);                                
 extern float get_cov_f(aln_res *res, aln_reg *reg);                                          /* :639  */
 extern void rearr_aln_res(aln_res *res, int n, float ovlp_r);                                /* :654  */
 extern void map_cal_msg(map_msg *m_msg, bntseq_t *bns);                                      /* :767  */
-extern int lamsa_read_seq(lamsa_seq_t *la_seqs, kseq_t *read_seq_t, FILE *seed_mapfp, char *gem_line,
-                          int line_size, seed_msg *s_msg, int chunk_read_n);                 /* :927  */
+extern void init_aln_per_para(lamsa_aln_per_para *APP, seed_msg *s_msg, int read_n);          /* :776  */
 extern void aln_res_output(lamsa_aln_para AP, aln_res *res, int res_n, char *name, char *seq, char *qual,
                            bntseq_t *bns);                                                   /* :1001 */
 #define LB2_LINE_SIZE 65536                                                                   /* LINE_SIZE, :21 */
@@ -74,6 +73,8 @@ typedef struct {
 	pthread_mutex_t out_mu;
 	out_slot *ring; long ring_n; long next_out;
 	long done;
+	double read_hold_s, out_hold_s;   /* time inside the two locks (LB2_FIBER_STATS) */
+	double t_begin; float *t_start, *t_end;   /* LB2_READ_TRACE: per read, seconds since the stage began */
 } pipeline_t;
 
 /* The chaining entry points of liblamsa_b200 keep their node tables on the GPU and never look at the per-thread
@@ -95,13 +96,17 @@ typedef struct {
 	pipeline_t *P;
 	lamsa_seq_t slot;          /* APP, m_msg, a_res of the read being aligned */
 	kseq_t seq;                /* its name / bases / qualities (shares the pipeline's stream) */
+	char *lines; size_t lines_n, lines_m;   /* the read's lines of the seed map, as read: text, NUL after each line */
 	chain_scratch cs;          /* cs.f_node identifies this worker to frag_line_BCC / frag_line_remain */
 } worker_t;
 
 /* hand the records of read `seq` to the writer; writes every read that has become due */
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
 static void emit(pipeline_t *P, long seq, char *buf, size_t len)
 {
 	pthread_mutex_lock(&P->out_mu);
+	const double t0 = now_s();
 	out_slot *s = &P->ring[seq % P->ring_n];
 	s->buf = buf; s->len = len; s->ready = 1;
 	for (;;) {
@@ -112,7 +117,60 @@ static void emit(pipeline_t *P, long seq, char *buf, size_t len)
 		o->buf = NULL; o->len = 0; o->ready = 0;
 		__atomic_store_n(&P->next_out, P->next_out + 1, __ATOMIC_RELEASE);
 	}
+	P->out_hold_s += now_s() - t0;
 	pthread_mutex_unlock(&P->out_mu);
+}
+
+/* The input step of the reference (lamsa_read_seq, src/lamsa_aln.c:927-956) in two halves.  Only what has to be
+ * sequential stays under the input lock: the next FASTA/FASTQ record and the read's seed_all lines of the seed map,
+ * taken as text.  Returns 0 at the end of the input. */
+static int take_next_read(pipeline_t *P, worker_t *w)
+{
+	if (kseq_read(&w->seq) < 0) return 0;
+	++(P->s_msg->read_count);
+	init_aln_per_para(w->slot.APP, P->s_msg, P->s_msg->read_count);
+	const int seed_all = w->slot.APP->seed_all;
+	int k;
+	w->lines_n = 0;
+	for (k = 0; k < seed_all; ++k) {
+		if (fgets(P->gem_line, LB2_LINE_SIZE, P->seed_mapfp) == NULL) {
+			fprintf(stderr, "[lamsa_read_seq] Seeds' GEM map-result do NOT match.\n"); exit(1);      /* src/gem_parse.c:213-214 */
+		}
+		const size_t l = strlen(P->gem_line) + 1;
+		if (w->lines_n + l > w->lines_m) {
+			w->lines_m = (w->lines_n + l) * 2 + 1024;
+			w->lines = (char *)realloc(w->lines, w->lines_m);
+		}
+		memcpy(w->lines + w->lines_n, P->gem_line, l);
+		w->lines_n += l;
+	}
+	return 1;
+}
+/* ... and everything else a worker does for itself: the map_msg table and, per line, what gem_map_read does after
+ * its fgets (src/gem_parse.c:216-227: drop the newline, skip four tab-separated fields, keep the hit list unless
+ * it is "-") with lamsa_read_seq's seed numbering (:945-952). */
+static void parse_seed_lines(worker_t *w)
+{
+	lamsa_seq_t *p = &w->slot;
+	const int seed_all = p->APP->seed_all;
+	int seed_n, seed_out = 0;
+	char *line = w->lines;
+	p->m_msg = map_init_msg(seed_all);
+	for (seed_n = 0; seed_n < seed_all; ++seed_n) {
+		size_t l = strlen(line), i; int ct = 0;
+		char *next = line + l + 1;
+		if (l) line[--l] = 0;
+		for (i = 0; i < l; ++i) {
+			if (line[i] == '\t') { if (ct == 3) break; else ct++; }
+		}
+		if (line[i + 1] != '-') {
+			p->m_msg[seed_out].map_str = strdup(line + i + 1);
+			p->m_msg[seed_out].seed_id = seed_n + 1;
+			++seed_out;
+		}
+		line = next;
+	}
+	p->APP->seed_out = seed_out;
 }
 
 /* one read through the reference's stages, in the order of src/lamsa_aln.c:846-880 */
@@ -189,14 +247,18 @@ static void *read_worker(void *arg)
 			lb2_worker_yield();
 			pthread_mutex_lock(&P->read_mu);
 		}
-		if (P->eof || lamsa_read_seq(&w->slot, &w->seq, P->seed_mapfp, P->gem_line, LB2_LINE_SIZE, P->s_msg, 1) == 0) {
+		const double tr0 = now_s();
+		if (P->eof || !take_next_read(P, w)) {
 			P->eof = 1;
 			pthread_mutex_unlock(&P->read_mu);
 			break;
 		}
 		const long seq = P->next_seq++;
+		P->read_hold_s += now_s() - tr0;
+		if (P->t_start) P->t_start[seq] = (float)(now_s() - P->t_begin);
 		pthread_mutex_unlock(&P->read_mu);
 
+		parse_seed_lines(w);
 		align_read(w, f_msg, &hash_num, &hash_node);
 
 		/* the read's SAM records, formatted here and written by whoever completes the input order */
@@ -209,6 +271,7 @@ static void *read_worker(void *arg)
 		fclose(mem);
 		map_free_msg(w->slot.m_msg, w->slot.APP->seed_all);
 		emit(P, seq, buf, len);
+		if (P->t_end) P->t_end[seq] = (float)(now_s() - P->t_begin);
 		const long done = __atomic_add_fetch(&P->done, 1, __ATOMIC_RELAXED);
 		if (done % 100000 == 0) fprintf(stderr, "%16ld reads have been aligned.\n", done);
 	}
@@ -221,7 +284,7 @@ static void *read_worker(void *arg)
 	for (k = 0; k < n_key; ++k) free(hash_node[k]);
 	free(hash_node); free(hash_num);
 	free(w->slot.APP); aln_res_free(w->slot.a_res, 3);
-	free(w->seq.name.s); free(w->seq.comment.s); free(w->seq.seq.s); free(w->seq.qual.s);
+	free(w->seq.name.s); free(w->seq.comment.s); free(w->seq.seq.s); free(w->seq.qual.s); free(w->lines);
 	return NULL;
 }
 
@@ -253,6 +316,11 @@ int lamsa_aln_core(const char *read_prefix, char *seed_result, seed_msg *s_msg,
 	P.ring_n = 4 * n_workers;
 	P.ring = (out_slot *)calloc(P.ring_n, sizeof(out_slot));
 
+	const char *read_trace = getenv("LB2_READ_TRACE");
+	if (read_trace && *read_trace && s_msg->read_all > 0) {
+		P.t_start = (float *)calloc(s_msg->read_all + 1, sizeof(float)); P.t_end = (float *)calloc(s_msg->read_all + 1, sizeof(float));
+		P.t_begin = now_s();
+	}
 	worker_t *ws = (worker_t *)calloc(n_workers, sizeof(worker_t));
 	pthread_t *ids = (pthread_t *)calloc(n_workers, sizeof(pthread_t));
 	long i;
@@ -263,12 +331,17 @@ int lamsa_aln_core(const char *read_prefix, char *seed_result, seed_msg *s_msg,
 	}
 	for (i = 0; i < n_workers; ++i) lb2_worker_join(ids[i], NULL);
 
+	if (P.t_start) {
+		FILE *tf = fopen(read_trace, "w");
+		if (tf) { for (i = 0; i < P.done; ++i) fprintf(tf, "%ld %.6f %.6f\n", i, P.t_start[i], P.t_end[i]); fclose(tf); }
+		free(P.t_start); free(P.t_end);
+	}
 	free(ids); free(ws); free(P.ring); free(P.gem_line);
 	fclose(P.seed_mapfp); ks_destroy(P.fs); gzclose(readfp);
 	pthread_mutex_destroy(&P.read_mu); pthread_mutex_destroy(&P.out_mu);
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	if (getenv("LB2_FIBER_STATS"))
-		fprintf(stderr, "[lamsa_b200] alignment stage: %ld reads, %ld in flight, %.3f s wall\n", P.done, n_workers,
-		        (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
+		fprintf(stderr, "[lamsa_b200] alignment stage: %ld reads, %ld in flight, %.3f s wall (%.3f s inside the input lock, %.3f s inside the output lock)\n",
+		        P.done, n_workers, (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec), P.read_hold_s, P.out_hold_s);
 	return 0;
 }
