@@ -351,6 +351,8 @@ int lb2_worker_spawn(pthread_t *id, const pthread_attr_t *attr, void *(*fn)(void
 int lb2_worker_join(pthread_t id, void **ret);
 /* Called by a worker: lets the other workers of its thread run (a worker waiting for a sibling's progress). */
 void lb2_worker_yield(void);
+/* Called by a worker: seconds it has spent parked on DP / chaining requests so far (statistics). */
+double lb2_worker_parked_seconds(void);
 /* Self test of the worker scheduler, its context switch and the request round trip through another thread,
  * without a GPU: n workers yielding `yields` times each on `threads` scheduler threads; returns the number of
  * workers with a wrong result (0 = pass). */

@@ -76,7 +76,7 @@ EXPORTS = [
     "lb2_batch_create", "lb2_batch_upload", "lb2_batch_compute", "lb2_batch_compute_async", "lb2_batch_compute_done", "lb2_batch_compute_wait", "lb2_batch_download", "lb2_batch_download_view", "lb2_batch_stats",
     "lb2_batch_destroy", "lb2_free", "lb2_int_peak",
     "lb2_sdp_create", "lb2_sdp_reset", "lb2_sdp_run_bcc", "lb2_sdp_run_remain", "lb2_sdp_stats", "lb2_sdp_destroy", "lb2_sdp_get_tracked", "lb2_sdp_set_tracked",
-    "lb2_ref_abi_offsets", "lb2_ref_abi_sizes", "lb2_worker_spawn", "lb2_worker_join", "lb2_worker_yield", "lb2_dropin_warmup", "lb2_fiber_selftest",
+    "lb2_ref_abi_offsets", "lb2_ref_abi_sizes", "lb2_worker_spawn", "lb2_worker_join", "lb2_worker_yield", "lb2_worker_parked_seconds", "lb2_dropin_warmup", "lb2_fiber_selftest",
     "frag_line_BCC", "frag_line_remain", "node_init_score", "node_free_score", "cover_rate",
     "build_node_max_heap", "build_node_min_heap", "build_node_minpos_heap",
 ]

@@ -145,7 +145,8 @@ extern "C" int lb2_ctx_create(int device, lb2_ctx** out) {
     if (device < 0 || device >= ndev) return fail("lb2_ctx_create: device %d of %d", device, ndev);
     CU(cudaSetDevice(device));
     // per-device facts and the one-time kernel attributes are looked up once per process: a batch producer
-    // opens many contexts (fiber_sched.cu), and cudaGetDeviceProperties / cudaFuncSetAttribute are slow
+    // opens several contexts; the kernels' shared-memory attribute is set when a kernel is first launched on a
+    // device (compute_enqueue), so that opening a context does not load every kernel of the library
     static std::mutex dev_mu;
     static int dev_major[64], dev_minor[64], dev_sms[64];
     static bool dev_known[64] = {false};
@@ -156,10 +157,6 @@ extern "C" int lb2_ctx_create(int device, lb2_ctx** out) {
             CU(cudaDeviceGetAttribute(&dev_major[device], cudaDevAttrComputeCapabilityMajor, device));
             CU(cudaDeviceGetAttribute(&dev_minor[device], cudaDevAttrComputeCapabilityMinor, device));
             CU(cudaDeviceGetAttribute(&dev_sms[device], cudaDevAttrMultiProcessorCount, device));
-            if (dev_major[device] >= 10)
-                for (int kind = 0; kind < 2; ++kind)
-                    for (int var = 0; var < kNumVar; ++var)
-                        CU(cudaFuncSetAttribute(fill_table(kind, var), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
             dev_known[device] = true;
         }
     }
@@ -639,6 +636,9 @@ static int compute_enqueue(lb2_batch* b) {
             const int wpb = class_warps(var, ls);
             const size_t smem = var == kVarGmem ? 0 : (size_t)wpb * var_warp_smem(var, 1 << ls);
             if (!c->occ[k]) {
+                // first launch of this kernel through this context: opt in to the large dynamic shared memory, then
+                // ask how many blocks fit (both load the kernel's module on demand)
+                CU(cudaFuncSetAttribute(fill_table(kind, var), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
                 int nb = 0;
                 CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fill_table(kind, var), wpb * 32, smem));
                 c->occ[k] = nb > 0 ? nb : 1;

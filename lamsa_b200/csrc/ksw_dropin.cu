@@ -12,6 +12,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -47,6 +48,16 @@ void lb2::dropin_bind_thread_ctx(lb2_ctx* c) { tl_ctx = c; }
 // Opens the batch producer's GPUs (contexts, batch slots, device threads: producer.cu) from a helper thread,
 // so that CUDA start-up overlaps the caller's own start-up (index loading).  Optional.
 extern "C" void lb2_dropin_warmup(void) {
+    // CUDA start-up time grows with the number of GPUs it has to initialise: show it only the ones this process
+    // will use (LB2_DEVICE .. LB2_DEVICE + LB2_DEVICES - 1), unless the environment already chose
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        const char* nd = getenv("LB2_DEVICES"); const char* b = getenv("LB2_DEVICE");
+        const int ndev = nd && atoi(nd) > 0 ? atoi(nd) : 1, base = b ? atoi(b) : 0;
+        std::string v;
+        for (int k = 0; k < ndev; ++k) v += (k ? "," : "") + std::to_string(base + k);
+        setenv("CUDA_VISIBLE_DEVICES", v.c_str(), 0);
+        setenv("LB2_DEVICE", "0", 1);
+    }
     std::thread([] { lb2::producer_warmup(); }).detach();
 }
 namespace {
@@ -124,8 +135,54 @@ void submit_batch(std::vector<Pending*>& batch) {
     lb2_free(pool);
 }
 
+// Tasks without a single DP cell -- an empty query or an empty target: about 30 % of the extension calls of
+// LAMSA's PacBio mode -- are answered in closed form: what the reference's code leaves behind
+// when its cell loop is never entered (global: src/ksw.c:549,569-572,577-579,632-650; extension: :692-694,
+// :709-712,:718-725,:758-763,:785-803).  No DP cell is evaluated on the host; a round trip to the GPU for nothing
+// would only lengthen the read's chain of dependent calls.  Returns false for the one shape the reference itself
+// leaves undefined (ksw_extend2 with an empty query writes past its eh[] array, :399,407), which stays on the GPU path.
+cigar32_t* one_op(int len, int op) {
+    cigar32_t* c = (cigar32_t*)malloc(4 * sizeof(cigar32_t));          // push_cigar's first allocation, :509-511
+    c[0] = (cigar32_t)(len << 4 | op);
+    return c;
+}
+bool zero_cell_task(const lb2_task& t, lb2_result* r, cigar32_t** cig) {
+    const bool want = (t.flags & LB2_FLAG_CIGAR) != 0;
+    memset(r, 0, sizeof *r);
+    if (cig) *cig = nullptr;
+    if (t.kind == LB2_KIND_GLOBAL) {
+        r->qle = t.qlen; r->tle = t.tlen;
+        if (t.qlen == 0 && t.tlen == 0) { r->score = 0; return true; }
+        if (t.qlen == 0) {                       // every row only moves eh[0].h = -(o_del + e_del (i+1)); one deletion
+            r->score = -(t.o_del + t.e_del * t.tlen);
+            if (want) { r->n_cigar = 1; r->reserved = 4; if (cig) *cig = one_op(t.tlen, LB2_CDEL); }
+        } else {                                 // no rows: eh[qlen].h of the first row (the band is >= qlen + 3); one insertion
+            r->score = -(t.o_ins + t.e_ins * t.qlen);
+            if (want) { r->n_cigar = 1; r->reserved = 4; if (cig) *cig = one_op(t.qlen, LB2_CINS); }
+        }
+        return true;
+    }
+    if (t.h0 <= 0) return false;
+    if (t.tlen == 0) {                           // no rows: max = h0, max_i = max_j = max_ie = -1, gscore = -1
+        r->score = t.h0; r->gscore = -1;
+        return true;
+    }
+    if (!want) return false;                     // empty query, score-only form
+    // empty query, row 0 has no cells: gscore = h1 = max(h0 - oe_del, 0), max_ie = 0, then m == 0 ends the loop
+    r->score = t.h0;
+    const int h1 = t.h0 - (t.o_del + t.e_del) > 0 ? t.h0 - (t.o_del + t.e_del) : 0;
+    r->gscore = h1;
+    if (!(h1 <= 0 || h1 <= t.h0 - t.end_bonus)) {    // end point (max_ie, qlen-1) = (0, -1): one deleted base
+        r->tle = 1; r->gtle = 1;
+        r->n_cigar = 1; r->reserved = 4;
+        if (cig) *cig = one_op(1, LB2_CDEL);
+    }
+    return true;
+}
+
 // run one task; returns malloc'd CIGAR (or NULL) through *cig
 void run_one(const lb2_task& t, lb2_result* r, cigar32_t** cig) {
+    if ((t.qlen == 0 || t.tlen == 0) && !(t.flags & LB2_FLAG_TARGET_PAC) && zero_cell_task(t, r, cig)) return;
     Pending me{t, r, cig, false};
     if (lb2::fiber_active()) { lb2::fiber_wait_dp(&me); return; }      // worker fiber: park and let the scheduler batch it
     std::unique_lock<std::mutex> lk(q_mu);

@@ -86,15 +86,18 @@ struct Fiber {
     void* (*fn)(void*) = nullptr; void* arg = nullptr;
     Worker* home = nullptr;
     bool done = false;
+    double parked_s = 0;                 // total time this worker spent parked on requests
 };
 
 // requests one worker thread parked since its last hand-over, packed for the device
 struct DpGroup {
+    Clock::time_point t_first;            // when the first request was parked
     lb2::TaskBlob blob;
     std::vector<lb2::DpRequest*> reqs;
     std::vector<Fiber*> owners;
 };
 struct SdpGroup {
+    Clock::time_point t_first;
     std::vector<lb2::SdpRequest*> reqs;
     std::vector<Fiber*> owners;
 };
@@ -125,7 +128,7 @@ struct Slot {
     lb2_ctx* ctx = nullptr;
     lb2_batch* batch = nullptr;
     std::vector<DpGroup*> groups;
-    bool busy = false, launched = false;
+    bool busy = true, launched = false;         // busy until the slot's thread has sized its buffers
     std::thread completer;
 };
 struct Device {
@@ -215,6 +218,16 @@ void deliver_slot(Device* d, Slot& s) {
 void completer_main(Device* d, int k) {
     Slot& s = d->slot[k];
     cudaSetDevice(d->device);
+    {
+        // steady-state sizes up front (two sets: one batch being packed while the previous one is read back): growing
+        // pinned or device buffers later would stall every slot for milliseconds.  Each slot's thread does its own.
+        const bool slow = k == kFastSlots;
+        for (int r = 0; r < 2; ++r)
+            if (lb2::ctx_reserve(s.ctx, slow ? 4096 : 16384, (size_t)(slow ? 64 : 16) << 20,
+                                 (size_t)(slow ? 1024 : 256) << 20, (size_t)(slow ? 8 : 4) << 20)) die("cannot size the batch buffers");
+        { std::lock_guard<std::mutex> lk(d->mu); s.busy = false; }
+        d->cv_submit.notify_one();
+    }
     for (;;) {
         {
             std::unique_lock<std::mutex> lk(d->mu);
@@ -290,16 +303,26 @@ void sdp_main(Device* d) {
             take.swap(d->pend_sdp);
         }
         const auto t0 = Clock::now();
-        std::vector<Fiber*> owners;
         int64_t nreq = 0; int nb = 0;
         { long nt = 0; for (SdpGroup* g : take) nt += (long)g->reqs.size(); trace().ev("chaining", "begin", 0, nt); }
-        for (int stage = 1; stage <= 2; ++stage) {
-            std::vector<lb2::SdpRequest*> grp;
-            for (SdpGroup* g : take) for (lb2::SdpRequest* q : g->reqs) if (q->stage == stage) grp.push_back(q);
-            if (!grp.empty()) { lb2::dropin_submit_sdp(grp); ++nb; nreq += (int64_t)grp.size(); }
+        // One batch per stage and at most LB2_SDP_MAX_BATCH reads: the owners of a served batch go home (and on to
+        // their DP calls) while the next one runs, instead of all waiting for one launch over thousands of reads.
+        static const size_t max_batch = (size_t)env_i("LB2_SDP_MAX_BATCH", 512);
+        for (int stage = 2; stage >= 1; --stage) {           // stage 2 first: those reads are closer to their end
+            std::vector<lb2::SdpRequest*> grp; std::vector<Fiber*> own;
+            for (SdpGroup* g : take)
+                for (size_t i = 0; i < g->reqs.size(); ++i)
+                    if (g->reqs[i]->stage == stage) { grp.push_back(g->reqs[i]); own.push_back(g->owners[i]); }
+            for (size_t lo = 0; lo < grp.size(); lo += max_batch) {
+                const size_t hi = std::min(grp.size(), lo + max_batch);
+                std::vector<lb2::SdpRequest*> part(grp.begin() + (long)lo, grp.begin() + (long)hi);
+                std::vector<Fiber*> owners(own.begin() + (long)lo, own.begin() + (long)hi);
+                lb2::dropin_submit_sdp(part);
+                route_home(owners);
+                ++nb; nreq += (int64_t)part.size();
+            }
         }
-        for (SdpGroup* g : take) { owners.insert(owners.end(), g->owners.begin(), g->owners.end()); delete g; }
-        route_home(owners);
+        for (SdpGroup* g : take) delete g;
         trace().ev("chaining", "end", 0, (long)nreq);
         std::lock_guard<std::mutex> lk(d->mu);
         d->sdp_s += secs(t0, Clock::now()); d->sdp_reqs += nreq; d->sdp_batches += nb;
@@ -345,26 +368,20 @@ std::vector<Device*>& devices() {
         bool ok = true;
         for (int q = 0; q < kSlots && ok; ++q) {
             ok = lb2_ctx_create(d->device, &d->slot[q].ctx) == 0;
-            if (ok) {
-                lb2_ctx_set_scratch_limit(d->slot[q].ctx, scratch);
-                // steady-state sizes up front: growing pinned or device buffers later stalls every slot for milliseconds
-                const bool slow = q == kFastSlots;
-                for (int r = 0; r < 2 && ok; ++r)
-                    ok = lb2::ctx_reserve(d->slot[q].ctx, slow ? 4096 : 16384, (size_t)(slow ? 64 : 16) << 20,
-                                          (size_t)(slow ? 1024 : 256) << 20, (size_t)(slow ? 8 : 4) << 20) == 0;
-            }
+            if (ok) lb2_ctx_set_scratch_limit(d->slot[q].ctx, scratch);
         }
         ok = ok && lb2_ctx_create(d->device, &d->sdp_ctx) == 0;
         if (!ok) { g_dev_error = lb2_last_error(); return g_devices; }      // g_devices stays empty
         opened.push_back(d);
     }
+    const double t_ctx = secs(t0, Clock::now());
     for (Device* d : opened) {
         d->submitter = std::thread(submitter_main, d);
         d->sdp_thread = std::thread(sdp_main, d);
         for (int q = 0; q < kSlots; ++q) d->slot[q].completer = std::thread(completer_main, d, q);
     }
     g_devices = opened;
-    if (verbose()) fprintf(stderr, "[lamsa_b200] %d GPU(s) opened in %.3f s (%d batch slots each)\n", ndev, secs(t0, Clock::now()), kSlots);
+    if (verbose()) fprintf(stderr, "[lamsa_b200] %d GPU(s) opened in %.3f s (%d batch slots each; buffers are sized by the slots' own threads)\n", ndev, t_ctx, kSlots);
     return g_devices;
 }
 [[noreturn]] void no_device() {
@@ -438,6 +455,7 @@ void hand_over_sdp(Worker* w) {
 void worker_main(Worker* w) {
     tl_worker = w;
     static const size_t flush_dp = (size_t)env_i("LB2_FLUSH_TASKS", 256), flush_sdp = (size_t)env_i("LB2_FLUSH_READS", 32);
+    static const auto flush_wait = std::chrono::microseconds(env_i("LB2_FLUSH_US", 250));
     while (w->live > 0) {
         if (w->inbox_n.load(std::memory_order_acquire) > 0) {
             std::lock_guard<std::mutex> lk(w->in_mu);
@@ -452,12 +470,15 @@ void worker_main(Worker* w) {
             w->cur = f;
             const auto tf0 = Clock::now();
             switch_to_fiber(w, f);
-            w->fiber_s += secs(tf0, Clock::now());
+            const auto tf1 = Clock::now();
+            w->fiber_s += secs(tf0, tf1);
             w->cur = nullptr;
             if (f->done) { --w->live; munmap(f->map, f->map_bytes); f->map = nullptr; }
-            // hand over early when enough has gathered: the device should not wait for this thread's whole queue
-            if ((w->fast && w->fast->reqs.size() >= flush_dp) || (w->slow && w->slow->reqs.size() >= flush_dp / 8 + 1)) hand_over_dp(w);
-            if (w->sdp && w->sdp->reqs.size() >= flush_sdp) hand_over_sdp(w);
+            // hand over early when enough has gathered or the oldest parked request has waited long enough: the
+            // device should not wait for this thread's whole run queue
+            if ((w->fast && (w->fast->reqs.size() >= flush_dp || tf1 - w->fast->t_first > flush_wait)) ||
+                (w->slow && (w->slow->reqs.size() >= flush_dp / 8 + 1 || tf1 - w->slow->t_first > flush_wait))) hand_over_dp(w);
+            if (w->sdp && (w->sdp->reqs.size() >= flush_sdp || tf1 - w->sdp->t_first > flush_wait)) hand_over_sdp(w);
             continue;
         }
         if (w->live == 0) break;
@@ -543,8 +564,8 @@ void fiber_wait_dp(DpRequest* r) {
     static const int fast_rows = env_i("LB2_FAST_ROWS", 256);
     const bool slow = fast_rows > 0 && r->task.tlen > fast_rows;
     DpGroup*& g = slow ? w->slow : w->fast;
-    if (!g) g = new DpGroup();
     const auto t0 = Clock::now();
+    if (!g) { g = new DpGroup(); g->t_first = t0; }
     if (g_selftest_threads == 0) {
         char msg[200];
         if (g->blob.add(r->task, -1, msg, sizeof msg)) { fprintf(stderr, "[lamsa_b200] DP task rejected: %s\n", msg); exit(1); }
@@ -555,16 +576,17 @@ void fiber_wait_dp(DpRequest* r) {
     yield_to_scheduler();
     w = tl_worker;
     const double lat = secs(t1, Clock::now());
+    w->cur->parked_s += lat;
     w->dp_lat_s += lat; ++w->dp_n; if (lat > w->dp_lat_max) w->dp_lat_max = lat;
 }
 void fiber_wait_sdp(SdpRequest* r) {
     Worker* w = tl_worker;
-    if (!w->sdp) w->sdp = new SdpGroup();
+    if (!w->sdp) { w->sdp = new SdpGroup(); w->sdp->t_first = Clock::now(); }
     w->sdp->reqs.push_back(r); w->sdp->owners.push_back(w->cur);
     const auto t1 = Clock::now();
     yield_to_scheduler();
     w = tl_worker;
-    w->sdp_lat_s += secs(t1, Clock::now()); ++w->sdp_n;
+    { const double lat = secs(t1, Clock::now()); w->cur->parked_s += lat; w->sdp_lat_s += lat; ++w->sdp_n; }
 }
 void producer_warmup() { devices(); }
 }  // namespace lb2
@@ -578,6 +600,12 @@ extern "C" void lb2_fiber_main(void* p) {                 // entered once per fi
     abort();
 }
 #endif
+
+// Seconds the calling worker has spent parked on DP / chaining requests so far (statistics of a host pipeline).
+extern "C" double lb2_worker_parked_seconds(void) {
+    Worker* w = tl_worker;
+    return w && w->cur ? w->cur->parked_s : 0.0;
+}
 
 // Let the other workers of this thread run (a worker that has to wait for something a sibling produces).
 extern "C" void lb2_worker_yield(void) {

@@ -42,6 +42,7 @@
 extern int lb2_worker_spawn(pthread_t *id, const pthread_attr_t *attr, void *(*fn)(void *), void *arg);
 extern int lb2_worker_join(pthread_t id, void **ret);
 extern void lb2_worker_yield(void);
+extern double lb2_worker_parked_seconds(void);
 extern void lb2_dropin_warmup(void);
 
 /* non-static parts of the reference's src/lamsa_aln.c that its header does not declare */
@@ -74,6 +75,7 @@ typedef struct {
 	out_slot *ring; long ring_n; long next_out;
 	long done;
 	double read_hold_s, out_hold_s;   /* time inside the two locks (LB2_FIBER_STATS) */
+	pthread_mutex_t stat_mu; double ph[6];  /* summed over workers: input-lock wait, parse, align (host part), format, emit, set-up */
 	double t_begin; float *t_start, *t_end;   /* LB2_READ_TRACE: per read, seconds since the stage began */
 } pipeline_t;
 
@@ -222,6 +224,8 @@ static void *read_worker(void *arg)
 	const int n_key = (int)pow(NT_N, AP->hash_key_len);
 	int k;
 	/* per-worker state, as lamsa_seq_init (src/lamsa_aln.c:912-923) and aux_dp_init (:982-983) set it up */
+	double ph[6] = {0, 0, 0, 0, 0, 0};
+	double tp = now_s();
 	w->slot.a_res = aln_init_res(1, 3, AP->res_mul_max);
 	w->slot.APP = (lamsa_aln_per_para *)malloc(sizeof(lamsa_aln_per_para));
 	uint32_t *hash_num = (uint32_t *)calloc(n_key, sizeof(uint32_t));
@@ -239,7 +243,9 @@ static void *read_worker(void *arg)
 #else
 	w->cs.f_node = (frag_dp_node ***)&w->cs;       /* a unique address per worker; never dereferenced */
 #endif
+	ph[5] += now_s() - tp;
 	for (;;) {
+		tp = now_s();
 		pthread_mutex_lock(&P->read_mu);
 		/* keep the writer's window: a read far behind must not let the others run ahead without bound */
 		while (!P->eof && P->next_seq - __atomic_load_n(&P->next_out, __ATOMIC_ACQUIRE) >= P->ring_n) {
@@ -257,9 +263,13 @@ static void *read_worker(void *arg)
 		P->read_hold_s += now_s() - tr0;
 		if (P->t_start) P->t_start[seq] = (float)(now_s() - P->t_begin);
 		pthread_mutex_unlock(&P->read_mu);
+		{ const double t = now_s(); ph[0] += t - tp; tp = t; }
 
 		parse_seed_lines(w);
+		{ const double t = now_s(); ph[1] += t - tp; tp = t; }
+		const double parked0 = lb2_worker_parked_seconds();
 		align_read(w, f_msg, &hash_num, &hash_node);
+		{ const double t = now_s(); ph[2] += t - tp - (lb2_worker_parked_seconds() - parked0); tp = t; }
 
 		/* the read's SAM records, formatted here and written by whoever completes the input order */
 		char *buf = NULL; size_t len = 0;
@@ -270,11 +280,16 @@ static void *read_worker(void *arg)
 		aln_res_output(ap, w->slot.a_res, 3, w->seq.name.s, w->seq.seq.s, w->seq.qual.s, P->bns);
 		fclose(mem);
 		map_free_msg(w->slot.m_msg, w->slot.APP->seed_all);
+		{ const double t = now_s(); ph[3] += t - tp; tp = t; }
 		emit(P, seq, buf, len);
+		ph[4] += now_s() - tp;
 		if (P->t_end) P->t_end[seq] = (float)(now_s() - P->t_begin);
 		const long done = __atomic_add_fetch(&P->done, 1, __ATOMIC_RELAXED);
 		if (done % 100000 == 0) fprintf(stderr, "%16ld reads have been aligned.\n", done);
 	}
+	pthread_mutex_lock(&P->stat_mu);
+	for (k = 0; k < 6; ++k) P->ph[k] += ph[k];
+	pthread_mutex_unlock(&P->stat_mu);
 	free(f_msg);
 #ifdef LB2_CORE_REF_CHAINING
 	fnode_free(w->cs.f_node, P->s_msg->seed_max + 2, AP->per_aln_m);
@@ -306,6 +321,7 @@ int lamsa_aln_core(const char *read_prefix, char *seed_result, seed_msg *s_msg,
 	s_msg->read_count = 0;
 	pthread_mutex_init(&P.read_mu, NULL);
 	pthread_mutex_init(&P.out_mu, NULL);
+	pthread_mutex_init(&P.stat_mu, NULL);
 
 	/* reads in flight: `-t` counts host threads in the reference; here the host threads are the library's
 	 * (one per core, LB2_HOST_THREADS) and the number that matters is how many reads are open at once */
@@ -343,5 +359,9 @@ int lamsa_aln_core(const char *read_prefix, char *seed_result, seed_msg *s_msg,
 	if (getenv("LB2_FIBER_STATS"))
 		fprintf(stderr, "[lamsa_b200] alignment stage: %ld reads, %ld in flight, %.3f s wall (%.3f s inside the input lock, %.3f s inside the output lock)\n",
 		        P.done, n_workers, (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec), P.read_hold_s, P.out_hold_s);
+	if (getenv("LB2_FIBER_STATS") && P.done)
+		fprintf(stderr, "[lamsa_b200] host time per read, summed over the workers (ms): taking the read (input lock incl. waiting) %.3f, seed-map lines %.3f, "
+		        "alignment stages without the time parked on the GPU %.3f, SAM formatting %.3f, handing to the writer %.3f, worker set-up %.3f\n",
+		        1e3 * P.ph[0] / P.done, 1e3 * P.ph[1] / P.done, 1e3 * P.ph[2] / P.done, 1e3 * P.ph[3] / P.done, 1e3 * P.ph[4] / P.done, 1e3 * P.ph[5] / P.done);
 	return 0;
 }

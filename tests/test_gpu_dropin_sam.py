@@ -23,6 +23,9 @@ EXES = {"dp": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin"),
         "producer": os.path.join(ROOT, "oracle", "_ref", "lamsa_b200_aln")}
 FIXTURES = [
     ("small", os.path.join(ROOT, "tests", "golden", "sam_small")),
+    # 4 contigs; donor with deletions / insertions / inversions / duplications and translocations BETWEEN contigs
+    # (oracle/make_big_fixtures.py multi): E_CHR_DIF edges of the chaining and records on several contigs per read
+    ("multi_contig_sv", os.path.join(ROOT, "tests", "golden", "sam_multi")),
     ("c1", os.path.join(ROOT, "oracle", "_ref", "sam_c1")),
     ("c3_reduced_pacbio", os.path.join(ROOT, "oracle", "_ref", "sam_c3s")),
     ("c4_reduced_sv", os.path.join(ROOT, "oracle", "_ref", "sam_c4s")),
@@ -54,7 +57,7 @@ def test_dropin_sam_identical_to_reference(tmp_path, name, src, threads, link):
         # reads in flight: the default (thousands), or fewer workers than reads with an odd count
         if threads == 1:
             env["LB2_READS_IN_FLIGHT"] = "37"
-    elif threads != 1 and name not in ("small", "c1"):
+    elif threads != 1 and name not in ("small", "c1", "multi_contig_sv"):
         pytest.skip("multi-thread run only on two fixtures")
     work = str(tmp_path / name)
     stage(src, work)
