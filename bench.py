@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- banded-DP throughput (GCUPS) of the B200 path, BASELINE.json configs[1]:
-the ksw_global2 / ksw_extend_core microbenchmark (1 M synthetic DP tasks, 50-1000 bp,
-band 10..200, half global / half extension, CIGARs produced).
+"""bench.py -- the two throughput figures of BASELINE.json's metric, on B200:
+
+  1. banded-DP GCUPS on BASELINE configs[1] (the ksw_global2 / ksw_extend_core microbenchmark: 1 M synthetic
+     DP tasks, 50-1000 bp, band 10..200, half global / half extension, CIGARs produced) -- the JSON line's
+     `value`, `e2e`, `roofline`;
+  2. aligned Mbp/s of the whole alignment stage of `lamsa aln` (sum of read lengths / wall seconds
+     of the stage, seeding and index loading excluded) on a C3-shaped fixture -- the line's `pipeline` object and
+     `aligned_mbp_per_s`.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--tasks T] [--impl reference]
 
-A "step" = one pass of the hot path (fill + traceback kernels) over the whole task
-batch, inputs resident in HBM.  `value` = DP cells the reference would evaluate
-(counted by the kernels, identical to the oracle's count) / device time, summed over
-ranks; `e2e` = the same through lb2_dp_run with HOST task records (pack + H2D +
-kernels + D2H of scores/CIGARs).  N>1: one process per GPU (torchrun), tasks sharded
-by rank (independent batches, no collective on the data path), weak scaling.
-`--impl reference` times the reference's own CPU ksw.c (oracle/_ref, or the oracle
-port when that was not built) on all host cores, on a bounded sample of the workload.
+A "step" = one pass of the hot path (fill + traceback kernels) over the whole task batch, inputs resident in
+HBM.  `value` = DP cells the reference would evaluate (counted by the kernels, identical to the oracle's count) /
+device time, summed over ranks; `e2e` = the same through lb2_dp_run with HOST task records (pack + H2D + kernels
++ D2H of scores/CIGARs), timed over the same number of steps.  N>1: one process per GPU (torchrun), tasks sharded
+by rank (independent batches, no collective on the data path), weak scaling; the pipeline leg then runs ONE
+process that drives all N GPUs (reads are spread over the GPUs by the batch producer).
+`--impl reference` times the reference's own CPU code on all host cores: ksw.c (oracle/_ref/libksw_ref.so, or the
+oracle port when that was not built) on a bounded sample of the DP workload, and the unmodified `lamsa aln`
+(oracle/_ref/lamsa_ref) on the same pipeline fixture.
 """
 import argparse
 import json
@@ -30,6 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 OPS_EXTEND, OPS_GLOBAL = 22, 16        # algorithmic integer ops per cell
 METRIC = "banded_dp_gcups"
+DTYPE = "s16x2 (packed int16 DPX lanes where the value range is provably safe, int32 lanes otherwise; bit-exact with the reference's int32)"
 
 
 def env_int(name, default):
@@ -100,6 +107,73 @@ def cpu_reference(tasks, threads):
     return cells / secs / 1e9, kind, secs, cells
 
 
+# ------------------------------------------------------------------- pipeline leg
+def pipeline_fixture():
+    """(dir, replicate, description) of the C3-shaped fixture the pipeline leg runs, or None.  The fixtures are outputs
+    of the unmodified reference (oracle/make_sam_fixtures.py); the larger ones live under oracle/_ref/ (not in git,
+    shipped with the snapshot), the committed small one is the fall-back."""
+    cands = [(os.path.join(ROOT, "oracle", "_ref", "sam_c3m"), 4,
+              "C3 shape: 4 Mbp random reference, 2 000 x 10 kbp reads at 15 % error (1.5/9/4.5 sub/ins/del), `-T pacbio`, reads taken 4 times = 8 000 reads, 84 Mbp"),
+             (os.path.join(ROOT, "oracle", "_ref", "sam_c3s"), 16,
+              "C3 shape, reduced: 1 Mbp reference, 100 x 10 kbp reads at 15 % error, `-T pacbio`, reads taken 16 times"),
+             (os.path.join(ROOT, "tests", "golden", "sam_small"), 64,
+              "committed fall-back: 60 kbp reference, 24 x 2.5 kbp reads at 5 % error, reads taken 64 times")]
+    for d, rep, desc in cands:
+        if os.path.isdir(d):
+            return d, env_int("LB2_PIPE_REPLICATE", rep), desc
+    return None
+
+
+def pipeline_leg(impl, n_gpus, repeat=2):
+    """Whole `lamsa aln -N` on the pipeline fixture -> dict for the JSON line (never raises)."""
+    try:
+        from lamsa_b200 import pipeline
+        fx = pipeline_fixture()
+        exe = pipeline.REFBIN if impl == "reference" else pipeline.PRODUCER
+        if fx is None or not os.path.exists(exe):
+            return {"unavailable": f"{'fixture' if fx is None else exe} not present (built where the reference tree is mounted)"}
+        work = pipeline.temp_workdir(fx[0], fx[1])
+        bases = pipeline.read_bases(work)
+        exp = list(open(os.path.join(work, "expected.sam")))
+        cores = os.cpu_count() or 1
+        in_flight = env_int("LB2_READS_IN_FLIGHT", 4096 * n_gpus)
+        env = {} if impl == "reference" else {"LB2_DEVICES": str(n_gpus), "LB2_READS_IN_FLIGHT": str(in_flight), "LB2_FIBER_STATS": "1",
+                                              "LB2_READ_TRACE": os.path.join(work, "read_trace.txt")}
+        best, steady = None, None
+        for _ in range(repeat):
+            r = pipeline.run(exe, work, cores if impl == "reference" else 1, env)
+            if best is None or r["stage_s"] < best["stage_s"]:
+                best = r
+                steady = None
+                if env:       # steady state: reads completed between 10 % and 90 % of the run, from the per-read trace
+                    try:
+                        t_end = np.sort(np.loadtxt(os.path.join(work, "read_trace.txt"))[:, 2])
+                        lo, hi = int(0.1 * len(t_end)), int(0.9 * len(t_end))
+                        if hi > lo and t_end[hi] > t_end[lo]:
+                            steady = (hi - lo) / len(t_end) * bases / (t_end[hi] - t_end[lo]) / 1e6
+                    except Exception:
+                        steady = None
+        out = {"metric": "aligned_mbp_per_s", "value": bases / best["stage_s"] / 1e6, "unit": "Mbp/s",
+               "definition": "sum of read lengths / wall seconds of the alignment stage (lamsa_aln_core), seeding and index loading excluded (SURVEY.md 8d); "
+                             "the stage is bracketed by the program's own stderr lines 'Mapping reads to genome' / 'Mapping done'",
+               "stage_s": best["stage_s"], "whole_process_s": best["wall_s"], "whole_process_mbp_per_s": bases / best["wall_s"] / 1e6,
+               "fixture": fx[2], "reads_bases": bases, "sam_records": len([l for l in best["sam"] if not l.startswith("@")]),
+               "sam_identical_to_reference": best["sam"] == exp, "runs": repeat, "host_cores": cores}
+        if impl == "reference":
+            out["program"] = f"unmodified reference lamsa aln -t {cores} -N (oracle/_ref/lamsa_ref)"
+        else:
+            out["program"] = ("reference lamsa aln -N with ksw.c / lamsa_dp_con.c / lamsa_heap.c replaced by liblamsa_b200.so and the alignment "
+                              "stage by lamsa_b200/host/aln_core.c (oracle/_ref/lamsa_b200_aln)")
+            out["n_gpus"] = n_gpus
+            out["reads_in_flight"] = in_flight
+            out["steady_state_mbp_per_s"] = steady
+            out["stats"] = [l.strip() for l in best["stderr"] if "[lamsa_b200]" in l]
+        pipeline.cleanup(work)
+        return out
+    except Exception as e:
+        return {"error": repr(e)[:500]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -108,13 +182,14 @@ def main():
     ap.add_argument("--tasks", type=int, default=env_int("LB2_BENCH_TASKS", 1_000_000), help="DP tasks per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=200_000)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (default: --steps)")
     ap.add_argument("--seed", type=int, default=20260101)
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the whole-program leg")
     a = ap.parse_args()
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if world > 1 and "LB2_HOST_THREADS" not in os.environ:      # ranks share the host cores for packing
-        os.environ["LB2_HOST_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
+        os.environ["LB2_HOST_THREADS"] = str(max(8, (os.cpu_count() or 1) // world))
     from lamsa_b200 import workload
     workload_name = (f"ksw microbenchmark C2: {a.tasks} tasks/GPU, qlen U[50,1000], w U[10,200], "
                      "half ksw_global2 / half ksw_extend_core, CIGAR on")
@@ -133,6 +208,7 @@ def main():
             if s >= a.warmup:
                 vals.append(g); secs_all.append(secs)
         v = float(np.mean(vals))
+        pipe = None if a.no_pipeline else pipeline_leg("reference", a.gpus)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(secs_all)),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
@@ -140,7 +216,10 @@ def main():
                 "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": threads, "kind": kind,
                                  "sample": f"first {n} tasks of the workload, pthread pool over all host cores"},
                 "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        if pipe is not None:
+            line["pipeline"] = pipe
+            line["aligned_mbp_per_s"] = pipe.get("value")
+        print(json.dumps(line), flush=True)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -148,10 +227,7 @@ def main():
     import lamsa_b200
     dist = None
     if world > 1:
-        # NCCL only carries the timing barrier and the reduction of the reported numbers; keep its version
-        # banner (printed to stdout at NCCL_DEBUG=VERSION/INFO) out of the one-JSON-line output
-        if "LB2_KEEP_NCCL_DEBUG" not in os.environ:
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL only carries the timing barrier and the reduction of the reported numbers (no data-path collective)
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -192,12 +268,28 @@ def main():
     seq_bytes = int(tasks["qlen"].sum() + tasks["tlen"].sum())
     dir_bytes = cells // 2
     cigar_bytes = int(res["n_cigar"].sum()) * 4
+    # one more, untimed pass with the kernel classes launched ONE AFTER THE OTHER, each with its own CUDA events:
+    # per kernel its cells, its time alone and its fraction of the integer roof (in a step the classes overlap)
+    classes = []
+    if rank == 0:
+        batch.set_class_timing(True)
+        batch.compute()
+        batch.download()
+        peak_ops = peak["gops_s16x2"] * 1e9
+        for c in batch.class_stats():
+            opc = OPS_EXTEND if c["kind"] == "extend" else OPS_GLOBAL
+            c["gcups"] = c["cells"] / (c["ms"] * 1e-3) / 1e9 if c["ms"] > 0 else None
+            c["frac_of_int_roof"] = c["cells"] * opc / (c["ms"] * 1e-3) / peak_ops if c["ms"] > 0 else None
+            c["dir_bytes_written"] = c["cells"] // 2
+            classes.append(c)
+        classes.sort(key=lambda c: -c["ms"])
     batch.close()
 
     # ---- end to end through the public one-shot call (lb2_dp_run): host task records in, host
     # results + CIGAR words out; packing, H2D and D2H are inside the timed region
+    e2e_steps = a.e2e_steps or a.steps
     e2e_secs, h2d, d2h = [], 0, 0
-    for s in range(1 + a.e2e_steps):
+    for s in range(1 + e2e_steps):
         barrier()
         t0 = time.perf_counter()
         r2, c2 = ctx.run(tasks, keep)
@@ -230,7 +322,7 @@ def main():
         try:
             import _sdp
             from lamsa_b200.sdp import SdpBatch
-            rs = _sdp.gen_reads(4000, seed=7, mode="pacbio", repeat_frac=0.2, sv_rate=0.3, miss_frac=0.3, read_len=(8000, 12000))
+            rs = _sdp.gen_reads(8000, seed=7, mode="pacbio", repeat_frac=0.2, sv_rate=0.3, miss_frac=0.3, read_len=(8000, 12000))
             best_ms, pairs = None, 0
             for _ in range(3):
                 t0 = time.perf_counter()
@@ -242,14 +334,28 @@ def main():
                 if best_ms is None or k < best_ms:
                     best_ms, pairs, best_e2e = k, p1 + p2, e2e_sdp
             sub = rs.subset(np.arange(300))
-            t0 = time.perf_counter(); _, _, op = _sdp.oracle_run(sub); t_cpu = time.perf_counter() - t0
+            use_ref = _sdp.have_ref()
+            t0 = time.perf_counter()
+            _, _, op = (_sdp.ref_run(sub) if use_ref else _sdp.oracle_run(sub))
+            t_cpu = time.perf_counter() - t0
+            if use_ref:      # the reference library has no pair counter: take the count from the port (same pairs by construction)
+                op = _sdp.oracle_run(sub)[2]
             sdp = {"workload": f"{len(rs)} reads x 10 kbp, -T pacbio seeds, {len(rs.hits)} hits, both chaining stages",
                    "gpairs_per_s_kernel": pairs / (best_ms * 1e-3) / 1e9, "reads_per_s_kernel": len(rs) / (best_ms * 1e-3),
                    "reads_per_s_e2e": len(rs) / best_e2e, "unit": "predecessor pairs classified (src/lamsa_dp_con.c:713-751)",
-                   "cpu_baseline": {"kind": "port", "cores": 1, "gpairs_per_s": float(op.sum()) / t_cpu / 1e9,
-                                    "reads_per_s": len(sub) / t_cpu, "sample": "first 300 reads, oracle/sdp_oracle.c"}}
+                   "cpu_baseline": {"kind": "reference" if use_ref else "port", "cores": 1, "gpairs_per_s": float(np.sum(op)) / t_cpu / 1e9,
+                                    "reads_per_s": len(sub) / t_cpu,
+                                    "sample": "first 300 reads, " + ("oracle/_ref/liblamsa_ref.so (unmodified lamsa_dp_con.c)" if use_ref else "oracle/sdp_oracle.c")}}
         except Exception as e:      # the leg is informative; the headline metric does not depend on it
             sdp = {"error": repr(e)}
+
+    ctx.close()
+    barrier()
+    pipe = None
+    if rank == 0 and not a.no_pipeline:
+        torch.cuda.empty_cache()
+        pipe = pipeline_leg("b200", world)
+    barrier()
 
     traffic, traffic_note = None, "no ncu capture committed"
     try:        # dram bytes of the dominant kernel from the committed ncu capture, scaled to this task count
@@ -262,26 +368,30 @@ def main():
         peak_tops = peak["gops_s16x2"] / 1e3
         fill_step_ms = fill_max / a.steps
         achieved = (ops_all / world) / (fill_step_ms * 1e-3) / 1e12
+        dom = classes[0] if classes else None
         line = {
             "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": workload_name, "tasks_per_gpu": a.tasks, "cells_per_gpu": cells,
                        "l2": "inputs (sequence pool + direction scratch) far larger than the 126 MB L2",
                        "parallelism": f"task-sharded x{world}, no collective"},
-            "aligned_mbp_per_s": float(tasks["qlen"].sum()) * world / (ms_step * 1e-3) / 1e6,
             "wall_ms_per_step": 1e3 * t_wall / a.steps,
             "e2e": {"value": cells_all / e2e_max / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "seconds_per_step": e2e_max},
+                    "d2h_bytes_per_step": int(d2h), "seconds_per_step": e2e_max, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak_tops, "unit": "Tops/s (int16 lane-ops)",
                          "frac": achieved / peak_tops,
                          "peak_source": "measured live: VIADDMNMX.S16x2 issue rate (lb2_int_peak); "
                                         "MEASURED_PEAKS.json has no integer figure",
-                         "kernel": "fill_kernel<C,KIND> (all launches of a step)", "kernel_ms_per_step": fill_step_ms,
+                         "scope": "all fill kernels of a step (they run concurrently on side streams): ops of every cell / CUDA-event time from the first fill launch to the last one's end",
+                         "kernel": dom["kernel"] if dom else None,
+                         "kernel_alone": dom,
+                         "kernel_ms_per_step": fill_step_ms,
                          "trace_ms_per_step": trace_ms / a.steps,
                          "ops_per_cell": {"extend": OPS_EXTEND, "global": OPS_GLOBAL},
+                         "classes_alone": classes,
                          "hbm": {"algorithmic_bytes": seq_bytes + 2 * dir_bytes + cigar_bytes,
                                  "achieved_gbs": (seq_bytes + 2 * dir_bytes + cigar_bytes) / (ms_step * 1e-3) / 1e9},
                          "traffic": traffic, "traffic_note": traffic_note},
@@ -291,10 +401,13 @@ def main():
             line["cpu_baseline"] = cpu
         if sdp:
             line["sdp"] = sdp
-        print(json.dumps(line))
-    ctx.close()
+        if pipe is not None:
+            line["pipeline"] = pipe
+            line["aligned_mbp_per_s"] = pipe.get("value")
     if dist is not None:
         dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     return 0
 
 

@@ -249,6 +249,17 @@ int  lb2_batch_download_view(lb2_batch *b, lb2_result *results,
                              const cigar32_t **cigar_pool, int64_t *cigar_pool_n);
 int  lb2_batch_stats(const lb2_batch *b, int64_t *h2d_bytes, int64_t *d2h_bytes,
                      int64_t *launches, float *fill_ms, float *trace_ms);
+/* Roofline bookkeeping: with class timing on, lb2_batch_compute launches the batch's kernel classes one after the
+ * other (instead of concurrently) and times each with its own CUDA events; after a download, lb2_batch_class_stats
+ * reports per class the kernel, its tasks, the DP cells it evaluated and its time.  Returns the number of classes. */
+typedef struct {
+    int32_t class_id, kind, variant, window_slots;
+    int64_t tasks, cells;
+    float ms;
+    char kernel[44];
+} lb2_class_stat;
+int  lb2_batch_set_class_timing(lb2_batch *b, int on);
+int  lb2_batch_class_stats(const lb2_batch *b, lb2_class_stat *out, int cap);
 void lb2_batch_destroy(lb2_batch *b);
 void lb2_free(void *p);
 

@@ -59,6 +59,12 @@ class AlnPara(C.Structure):
     ]
 
 
+class ClassStat(C.Structure):
+    """lb2_class_stat"""
+    _fields_ = [("class_id", C.c_int32), ("kind", C.c_int32), ("variant", C.c_int32), ("window_slots", C.c_int32),
+                ("tasks", C.c_int64), ("cells", C.c_int64), ("ms", C.c_float), ("kernel", C.c_char * 44)]
+
+
 # order of oracle/ref_shim.c:ref_para_offsets
 PARA_FIELDS = [
     "n_thread", "seed_len", "seed_step", "seed_inv", "per_aln_m", "first_loci_thd", "SV_len_thd", "ske_max",
@@ -73,7 +79,7 @@ EXPORTS = [
     "ksw_global2", "ksw_global", "ksw_extend2", "ksw_extend", "ksw_extend_core", "ksw_extend_c",
     "ksw_extend_r", "ksw_bi_extend", "sw_mid_fix",
     "lb2_ctx_create", "lb2_ctx_destroy", "lb2_last_error", "lb2_ctx_set_scratch_limit", "lb2_ctx_set_reference", "lb2_ctx_last_run_stats", "lb2_ctx_last_run_kernel_ms", "lb2_ctx_set_chunk_tasks", "lb2_dp_run",
-    "lb2_batch_create", "lb2_batch_upload", "lb2_batch_compute", "lb2_batch_compute_async", "lb2_batch_compute_done", "lb2_batch_compute_wait", "lb2_batch_download", "lb2_batch_download_view", "lb2_batch_stats",
+    "lb2_batch_create", "lb2_batch_upload", "lb2_batch_compute", "lb2_batch_compute_async", "lb2_batch_compute_done", "lb2_batch_compute_wait", "lb2_batch_download", "lb2_batch_download_view", "lb2_batch_stats", "lb2_batch_set_class_timing", "lb2_batch_class_stats",
     "lb2_batch_destroy", "lb2_free", "lb2_int_peak",
     "lb2_sdp_create", "lb2_sdp_reset", "lb2_sdp_run_bcc", "lb2_sdp_run_remain", "lb2_sdp_stats", "lb2_sdp_destroy", "lb2_sdp_get_tracked", "lb2_sdp_set_tracked",
     "lb2_ref_abi_offsets", "lb2_ref_abi_sizes", "lb2_worker_spawn", "lb2_worker_join", "lb2_worker_yield", "lb2_worker_parked_seconds", "lb2_dropin_warmup", "lb2_fiber_selftest",
@@ -116,6 +122,8 @@ def load_library():
     lib.lb2_batch_download_view.argtypes = [P, P, C.POINTER(P), C.POINTER(I64)]
     lib.lb2_batch_stats.argtypes = [P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64),
                                     C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.lb2_batch_set_class_timing.argtypes = [P, I]
+    lib.lb2_batch_class_stats.argtypes = [P, C.POINTER(ClassStat), I]
     lib.lb2_batch_destroy.argtypes = [P]
     lib.lb2_batch_destroy.restype = None
     lib.lb2_free.argtypes = [P]

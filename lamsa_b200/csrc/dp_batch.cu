@@ -250,6 +250,9 @@ struct lb2_batch {
     float fill_ms = 0, trace_ms = 0;
     bool uploaded = false, enqueued = false, computed = false;
     std::vector<cudaEvent_t> wave_ev;      // only when scratch forces several waves
+    bool class_timing = false;             // lb2_batch_set_class_timing: classes one after the other, each with its own events
+    struct ClassRun { int cls; int tasks; cudaEvent_t t0, t1; float ms; };
+    std::vector<ClassRun> class_runs;
 };
 
 extern "C" void lb2_batch_destroy(lb2_batch* b) {
@@ -262,6 +265,7 @@ extern "C" void lb2_batch_destroy(lb2_batch* b) {
     }
     if (b->B.valid) b->B.release();
     for (auto& e : b->wave_ev) cudaEventDestroy(e);
+    for (auto& r : b->class_runs) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
     delete b;
 }
 
@@ -610,6 +614,8 @@ static int compute_enqueue(lb2_batch* b) {
     CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned int) * b->n_counters, s));
     CU(cudaMemsetAsync(b->d_err, 0, sizeof(int), s));
     b->launches = 0; b->fill_ms = 0; b->trace_ms = 0;
+    for (auto& r : b->class_runs) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
+    b->class_runs.clear();
     CU(cudaEventRecord(b->ev[0], s));
     const bool one_wave = b->waves.size() == 1;
     for (auto& e : b->wave_ev) cudaEventDestroy(e);
@@ -622,7 +628,7 @@ static int compute_enqueue(lb2_batch* b) {
             CU(cudaEventRecord(b->wave_ev[wi * 3], s));
         }
         static const int multi = env_int("LB2_MULTI_STREAM", 1);
-        const bool fan = multi && !class_timing;
+        const bool fan = multi && !class_timing && !b->class_timing;
         if (fan) {
             CU(cudaEventRecord(c->fork_ev, s));
             for (int k = 0; k < lb2_ctx::kAux; ++k) CU(cudaStreamWaitEvent(c->aux[k], c->fork_ev, 0));
@@ -659,12 +665,13 @@ static int compute_enqueue(lb2_batch* b) {
                 }
             }
             cudaEvent_t t0 = nullptr, t1 = nullptr;
-            if (class_timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, s); }
+            if (class_timing || b->class_timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, s); }
             // global-window classes share one scratch: keep them all on aux[0] (in order)
             cudaStream_t ls_ = fan ? c->aux[var == kVarGmem ? 0 : nlaunch++ % lb2_ctx::kAux] : s;
             fill_table(kind, var)<<<grid, wpb * 32, smem, ls_>>>(b->d_tasks, b->d_order + wv.first + wv.cls_off[k], cnt,
                                                              b->d_pool, c->d_pac, c->d_z, b->d_results, b->d_mats,
                                                              b->d_counters + wi * kNumClass + k, 1 << ls, c->d_gwin);
+            if (b->class_timing && !class_timing) { cudaEventRecord(t1, s); b->class_runs.push_back({k, cnt, t0, t1, 0.f}); }
             if (class_timing) {
                 cudaEventRecord(t1, s); cudaEventSynchronize(t1);
                 float ms = 0; cudaEventElapsedTime(&ms, t0, t1);
@@ -722,6 +729,7 @@ static int compute_finish(lb2_batch* b, float* kernel_ms) {
         }
     }
     b->fill_ms = fill_acc; b->trace_ms = trace_acc;
+    for (auto& r : b->class_runs) CU(cudaEventElapsedTime(&r.ms, r.t0, r.t1));
     if (kernel_ms) *kernel_ms = total;
     // read-backs go through the COPY stream: the compute stream may already hold the kernels of the next
     // chunk (lb2_dp_run pipelines chunks), and a copy queued behind them would stall the pipeline
@@ -829,6 +837,48 @@ extern "C" int lb2_batch_stats(const lb2_batch* b, int64_t* h2d, int64_t* d2h, i
     if (fill_ms) *fill_ms = b->fill_ms;
     if (trace_ms) *trace_ms = b->trace_ms;
     return 0;
+}
+
+static const char* kernel_name(int kind, int var) {
+    static const char* g[] = {"fill_kernel<1,global>", "fill_kernel<2,global>", "fill_kernel<4,global>", "fill16_kernel<2,global>", "fill16_kernel<4,global>",
+                              "fill_kernel<4,global,gmem window>", "fill16d_kernel<2,global,16>", "fill16d_kernel<2,global,8>", "fill16d_kernel<4,global,8>",
+                              "fill16d_kernel<4,global,16>", "fill_long_kernel<global>"};
+    static const char* e[] = {"fill_kernel<1,extend>", "fill_kernel<2,extend>", "fill_kernel<4,extend>", "fill16_kernel<2,extend>", "fill16_kernel<4,extend>",
+                              "fill_kernel<4,extend,gmem window>", "fill16d_kernel<2,extend,16>", "fill16d_kernel<2,extend,8>", "fill16d_kernel<4,extend,8>",
+                              "fill16d_kernel<4,extend,16>", "fill_long_kernel<extend>"};
+    return (kind == kKindGlobal ? g : e)[var];
+}
+
+extern "C" int lb2_batch_set_class_timing(lb2_batch* b, int on) {
+    if (!b) return fail("batch is NULL");
+    b->class_timing = on != 0;
+    return 0;
+}
+
+// Per launch class of the last lb2_batch_compute with class timing on (and after a download, which brings the cell
+// counts back): the kernel, its tasks, the DP cells it evaluated and its own CUDA-event time, launched ALONE.
+extern "C" int lb2_batch_class_stats(const lb2_batch* b, lb2_class_stat* out, int cap) {
+    if (!b || (cap > 0 && !out)) return -1;
+    int n = 0;
+    // classes may appear once per wave: merge by class id
+    for (const auto& r : b->class_runs) {
+        int at = -1;
+        for (int q = 0; q < n; ++q) if (out[q].class_id == r.cls) at = q;
+        if (at < 0) {
+            if (n == cap) break;
+            at = n++;
+            memset(&out[at], 0, sizeof out[at]);
+            out[at].class_id = r.cls; out[at].kind = class_kind(r.cls); out[at].variant = class_var(r.cls);
+            out[at].window_slots = 1 << class_logS(r.cls);
+            snprintf(out[at].kernel, sizeof out[at].kernel, "%s", kernel_name(class_kind(r.cls), class_var(r.cls)));
+        }
+        out[at].tasks += r.tasks; out[at].ms += r.ms;
+    }
+    if (b->computed || true)
+        for (int64_t i = 0; i < b->n; ++i)
+            for (int q = 0; q < n; ++q)
+                if (out[q].class_id == b->cls[(size_t)i]) { out[q].cells += b->h_results[i].cells; break; }
+    return n;
 }
 
 // One-shot run.  Large batches are cut into chunks and pipelined: while the GPU

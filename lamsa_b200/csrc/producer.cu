@@ -124,6 +124,9 @@ thread_local Worker* tl_worker = nullptr;
 
 // ---- the device side ---------------------------------------------------------------------------
 constexpr int kFastSlots = 3, kSlots = kFastSlots + 1;      // the last slot serves long tasks
+// chaining batches in flight at once: a batch lasts about as long as its slowest read (one warp walks a read), so a
+// request that arrives while one batch runs should not have to wait for it
+constexpr int kSdpThreads = 3;
 struct Slot {
     lb2_ctx* ctx = nullptr;
     lb2_batch* batch = nullptr;
@@ -134,7 +137,7 @@ struct Slot {
 struct Device {
     int device = 0;
     bool loopback = false;                       // self test: no GPU, requests are handed straight back
-    lb2_ctx* sdp_ctx = nullptr;
+    lb2_ctx* sdp_ctx[kSdpThreads] = {nullptr};
     std::mutex mu;
     std::condition_variable cv_submit, cv_slot, cv_sdp;
     std::vector<DpGroup*> pend_fast, pend_slow;
@@ -143,7 +146,7 @@ struct Device {
     std::vector<SdpGroup*> pend_sdp;
     Slot slot[kSlots];
     bool stop = false;
-    std::thread submitter, sdp_thread;
+    std::thread submitter, sdp_thread[kSdpThreads];
     // statistics (under mu)
     std::vector<int> batch_tasks;
     int64_t dp_tasks = 0, slow_batches = 0, slow_tasks = 0, sdp_reqs = 0, sdp_batches = 0;
@@ -291,9 +294,9 @@ void submitter_main(Device* d) {
     }
 }
 
-void sdp_main(Device* d) {
+void sdp_main(Device* d, int k) {
     cudaSetDevice(d->device);
-    lb2::dropin_bind_thread_ctx(d->sdp_ctx);
+    lb2::dropin_bind_thread_ctx(d->sdp_ctx[k]);
     for (;;) {
         std::vector<SdpGroup*> take;
         {
@@ -305,23 +308,27 @@ void sdp_main(Device* d) {
         const auto t0 = Clock::now();
         int64_t nreq = 0; int nb = 0;
         { long nt = 0; for (SdpGroup* g : take) nt += (long)g->reqs.size(); trace().ev("chaining", "begin", 0, nt); }
-        // One batch per stage and at most LB2_SDP_MAX_BATCH reads: the owners of a served batch go home (and on to
-        // their DP calls) while the next one runs, instead of all waiting for one launch over thousands of reads.
-        static const size_t max_batch = (size_t)env_i("LB2_SDP_MAX_BATCH", 512);
-        for (int stage = 2; stage >= 1; --stage) {           // stage 2 first: those reads are closer to their end
-            std::vector<lb2::SdpRequest*> grp; std::vector<Fiber*> own;
-            for (SdpGroup* g : take)
-                for (size_t i = 0; i < g->reqs.size(); ++i)
-                    if (g->reqs[i]->stage == stage) { grp.push_back(g->reqs[i]); own.push_back(g->owners[i]); }
-            for (size_t lo = 0; lo < grp.size(); lo += max_batch) {
-                const size_t hi = std::min(grp.size(), lo + max_batch);
-                std::vector<lb2::SdpRequest*> part(grp.begin() + (long)lo, grp.begin() + (long)hi);
-                std::vector<Fiber*> owners(own.begin() + (long)lo, own.begin() + (long)hi);
+        // One batch per stage (at most LB2_SDP_MAX_BATCH reads).  The chaining kernel walks a read with one warp, so a
+        // launch lasts about as long as its slowest read whatever the number of reads: large batches are the fast
+        // ones (measured on 10 kbp PacBio-mode reads: a request waits 30-50 ms uncapped, 250 ms with 512-read batches).
+        static const size_t max_batch = (size_t)env_i("LB2_SDP_MAX_BATCH", 1 << 20);
+        // (both stages are sorted out before anything is served: a served request lives on its owner's stack and is
+        // gone as soon as the owner runs again)
+        std::vector<lb2::SdpRequest*> grp[2]; std::vector<Fiber*> own[2];
+        for (SdpGroup* g : take)
+            for (size_t i = 0; i < g->reqs.size(); ++i) {
+                const int s2 = g->reqs[i]->stage == 2 ? 0 : 1;           // stage 2 first: those reads are closer to their end
+                grp[s2].push_back(g->reqs[i]); own[s2].push_back(g->owners[i]);
+            }
+        for (int q = 0; q < 2; ++q)
+            for (size_t lo = 0; lo < grp[q].size(); lo += max_batch) {
+                const size_t hi = std::min(grp[q].size(), lo + max_batch);
+                std::vector<lb2::SdpRequest*> part(grp[q].begin() + (long)lo, grp[q].begin() + (long)hi);
+                std::vector<Fiber*> owners(own[q].begin() + (long)lo, own[q].begin() + (long)hi);
                 lb2::dropin_submit_sdp(part);
                 route_home(owners);
                 ++nb; nreq += (int64_t)part.size();
             }
-        }
         for (SdpGroup* g : take) delete g;
         trace().ev("chaining", "end", 0, (long)nreq);
         std::lock_guard<std::mutex> lk(d->mu);
@@ -370,14 +377,14 @@ std::vector<Device*>& devices() {
             ok = lb2_ctx_create(d->device, &d->slot[q].ctx) == 0;
             if (ok) lb2_ctx_set_scratch_limit(d->slot[q].ctx, scratch);
         }
-        ok = ok && lb2_ctx_create(d->device, &d->sdp_ctx) == 0;
+        for (int q = 0; q < kSdpThreads && ok; ++q) ok = lb2_ctx_create(d->device, &d->sdp_ctx[q]) == 0;
         if (!ok) { g_dev_error = lb2_last_error(); return g_devices; }      // g_devices stays empty
         opened.push_back(d);
     }
     const double t_ctx = secs(t0, Clock::now());
     for (Device* d : opened) {
         d->submitter = std::thread(submitter_main, d);
-        d->sdp_thread = std::thread(sdp_main, d);
+        for (int q = 0; q < kSdpThreads; ++q) d->sdp_thread[q] = std::thread(sdp_main, d, q);
         for (int q = 0; q < kSlots; ++q) d->slot[q].completer = std::thread(completer_main, d, q);
     }
     g_devices = opened;

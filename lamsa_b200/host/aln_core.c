@@ -19,6 +19,7 @@
  * units (its lamsa_aln.c included: that file's own lamsa_aln_core is marked weak at compile time so
  * that this definition is the one `lamsa_aln_c` calls -- oracle/Makefile `producer`).
  */
+#include <malloc.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdint.h>
@@ -310,6 +311,13 @@ int lamsa_aln_core(const char *read_prefix, char *seed_result, seed_msg *s_msg,
 {
 	struct timespec t0, t1;
 	clock_gettime(CLOCK_MONOTONIC, &t0);
+	/* Thousands of reads in flight allocate and free gigabytes in small pieces (map_msg tables, CIGARs, sequences).
+	 * glibc's defaults hand freed memory back to the kernel and take it again page fault by page fault; keep it. */
+	if (!getenv("LB2_DEFAULT_MALLOC")) {
+		mallopt(M_TRIM_THRESHOLD, 1 << 30);
+		mallopt(M_MMAP_THRESHOLD, 32 << 20);
+		mallopt(M_TOP_PAD, 64 << 20);
+	}
 	pipeline_t P;
 	memset(&P, 0, sizeof P);
 	P.AP = AP; P.bwt = bwt; P.bns = bns; P.pac = pac; P.s_msg = s_msg;

@@ -151,6 +151,18 @@ class Batch:
             self.lib.lb2_free(pool)
         return res, cig
 
+    def set_class_timing(self, on=True):
+        self.lib.lb2_batch_set_class_timing(self.handle, 1 if on else 0)
+
+    def class_stats(self):
+        """Per kernel class of the last compute() with class timing on, after download(): list of dicts."""
+        from ._lib import ClassStat
+        arr = (ClassStat * 64)()
+        n = self.lib.lb2_batch_class_stats(self.handle, arr, 64)
+        return [{"kernel": arr[i].kernel.decode(), "kind": "extend" if arr[i].kind else "global", "variant": arr[i].variant,
+                 "window_slots": arr[i].window_slots, "tasks": arr[i].tasks, "cells": arr[i].cells, "ms": arr[i].ms}
+                for i in range(max(n, 0))]
+
     def stats(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         f, t = C.c_float(), C.c_float()

@@ -145,7 +145,7 @@ def make(outdir, contig_lens, n_reads, read_len, err, seed, aln_opts=(), sv_ever
 
 
 if __name__ == "__main__":
-    big = os.path.join(ROOT, "bigfix")      # top level, git- and gpurun-ignored; moved into the snapshot on demand
+    big = os.environ.get("LB2_BIGFIX", os.path.join(ROOT, "bigfix"))      # top level, git- and gpurun-ignored; moved into the snapshot on demand
     for what in sys.argv[1:]:
         if what == "multi":
             d = os.path.join(ROOT, "tests", "golden", "sam_multi")
