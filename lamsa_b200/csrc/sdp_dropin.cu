@@ -175,6 +175,9 @@ void lb2::dropin_submit_sdp(std::vector<lb2::SdpRequest*>& batch) {
     const int64_t n = (int64_t)batch.size();
     std::vector<lb2_sdp_read> reads((size_t)n);
     std::vector<int32_t> sid, mn; std::vector<lb2_sdp_hit> hits; std::vector<lb2_sdp_reg> regs; std::vector<uint8_t> flags;
+    // a batch may consist of reads without a single seed hit (most reads of a 15 %-error set at default seeding):
+    // the arrays are empty then, but their pointers must not be NULL
+    sid.reserve(16); mn.reserve(16); hits.reserve(16); regs.reserve(16); flags.reserve(16);
     for (int64_t i = 0; i < n; ++i) {
         const lb2::SdpRequest* q = batch[(size_t)i];
         const lb2::SdpWorkerState* ws = q->ws;
