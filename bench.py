@@ -136,7 +136,7 @@ def pipeline_leg(impl, n_gpus, repeat=2):
         bases = pipeline.read_bases(work)
         exp = list(open(os.path.join(work, "expected.sam")))
         cores = os.cpu_count() or 1
-        in_flight = env_int("LB2_READS_IN_FLIGHT", 4096 * n_gpus)
+        in_flight = env_int("LB2_READS_IN_FLIGHT", 8192 * n_gpus)
         env = {} if impl == "reference" else {"LB2_DEVICES": str(n_gpus), "LB2_READS_IN_FLIGHT": str(in_flight), "LB2_FIBER_STATS": "1",
                                               "LB2_READ_TRACE": os.path.join(work, "read_trace.txt")}
         best, steady = None, None

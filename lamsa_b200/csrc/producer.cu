@@ -123,7 +123,10 @@ struct Worker {                          // one OS thread
 thread_local Worker* tl_worker = nullptr;
 
 // ---- the device side ---------------------------------------------------------------------------
-constexpr int kFastSlots = 3, kSlots = kFastSlots + 1;      // the last slot serves long tasks
+// batch slots: the first kFastSlots serve ordinary tasks, the others tasks of more than LB2_FAST_ROWS rows (a batch lasts
+// as long as its longest task; long tasks are a tenth of the requests of SV reads but, with a single slot, were two
+// thirds of the time a read spent waiting)
+constexpr int kFastSlots = 3, kSlowSlots = 3, kSlots = kFastSlots + kSlowSlots;
 // chaining batches in flight at once: a batch lasts about as long as its slowest read (one warp walks a read), so a
 // request that arrives while one batch runs should not have to wait for it
 constexpr int kSdpThreads = 3;
@@ -224,9 +227,9 @@ void completer_main(Device* d, int k) {
     {
         // steady-state sizes up front (two sets: one batch being packed while the previous one is read back): growing
         // pinned or device buffers later would stall every slot for milliseconds.  Each slot's thread does its own.
-        const bool slow = k == kFastSlots;
+        const bool slow = k >= kFastSlots;
         for (int r = 0; r < 2; ++r)
-            if (lb2::ctx_reserve(s.ctx, slow ? 4096 : 16384, (size_t)(slow ? 64 : 16) << 20,
+            if (lb2::ctx_reserve(s.ctx, slow ? 4096 : 16384, (size_t)(slow ? 32 : 16) << 20,
                                  (size_t)(slow ? 1024 : 256) << 20, (size_t)(slow ? 8 : 4) << 20)) die("cannot size the batch buffers");
         { std::lock_guard<std::mutex> lk(d->mu); s.busy = false; }
         d->cv_submit.notify_one();
@@ -262,7 +265,9 @@ void submitter_main(Device* d) {
                 if (d->stop) return;
                 int free_fast = -1, busy_fast = 0;
                 for (int q = 0; q < kFastSlots; ++q) { if (!d->slot[q].busy) { if (free_fast < 0) free_fast = q; } else ++busy_fast; }
-                if (!d->pend_slow.empty() && !d->slot[kFastSlots].busy) { k = kFastSlots; slow = true; break; }
+                int free_slow = -1;
+                for (int q = kFastSlots; q < kSlots; ++q) if (!d->slot[q].busy) { free_slow = q; break; }
+                if (!d->pend_slow.empty() && free_slow >= 0) { k = free_slow; slow = true; break; }
                 if (!d->pend_fast.empty() && free_fast >= 0) {
                     const auto due = d->pend_fast_since + std::chrono::microseconds(gather_us);
                     if (busy_fast == 0 || d->pend_fast_tasks >= min_batch || Clock::now() >= due) { k = free_fast; break; }

@@ -7,7 +7,7 @@ Test infrastructure; only possible in the container that has /root/reference.
     python oracle/make_big_fixtures.py multi      # tests/golden/sam_multi/ (committed, xz members): 4 contigs, SVs
     python oracle/make_big_fixtures.py c3full     # bigfix/sam_c3full: BASELINE configs[2] at full size
     python oracle/make_big_fixtures.py c4full     # bigfix/sam_c4full: configs[3] at full read count
-    python oracle/make_big_fixtures.py c5s        # bigfix/sam_c5s: configs[4] scaled (24 contigs, 240 Mbp)
+    python oracle/make_big_fixtures.py c5s        # bigfix/sam_c5s: configs[4] scaled (24 contigs, 120 Mbp: what fits a gpurun snapshot; 20 k reads)
 """
 import os
 import shutil
@@ -157,7 +157,7 @@ if __name__ == "__main__":
             make(os.path.join(big, "sam_c4full"), [100_000_000], 20_000, 20_000, 0.05, seed=41, aln_opts=("-V", "10000"),
                  sv_every=15_000, sv_max=10_000)
         elif what == "c5s":
-            make(os.path.join(big, "sam_c5s"), [10_000_000] * 24, 20_000, 10_000, 0.15, seed=51, mix=(1.5, 9, 4.5), transloc=False)
+            make(os.path.join(big, "sam_c5s"), [5_000_000] * 24, 20_000, 10_000, 0.15, seed=51, mix=(1.5, 9, 4.5), transloc=False)
         elif what == "c4multi":
             make(os.path.join(big, "sam_c4multi"), [2_000_000] * 6, 1500, 20_000, 0.05, seed=61, aln_opts=("-V", "10000"),
                  sv_every=15_000, sv_max=10_000, transloc=True)
