@@ -515,14 +515,18 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     std::vector<uint64_t> zsz((size_t)n); std::vector<int32_t> ctmpw((size_t)n);
     uint8_t* hp = b->h_pool;
     DTask* ht = b->h_tasks;
+    const bool stream = pool > ((uint64_t)8 << 20);          // large staging: written once, read by the DMA engine only
     parallel_for(n, [&, hp, ht](int64_t a, int64_t e) {
         for (int64_t i = a; i < e; ++i) {
             PackedTask& p = pk[(size_t)i];
-            copy_sequences(tasks[i], p, hp, qoff[(size_t)i]);
+            copy_sequences(tasks[i], p, hp, qoff[(size_t)i], false, stream);
             ht[i] = p.d;
             b->flags[(size_t)i] = p.flags; cls[(size_t)i] = p.cls; bin[(size_t)i] = p.bin;
             zsz[(size_t)i] = p.zsz; ctmpw[(size_t)i] = p.ctmpw;
         }
+#if defined(__SSE2__)
+        if (stream) _mm_sfence();
+#endif
     });
     if (layout_waves(b, cls.data(), bin.data(), zsz.data(), ctmpw.data())) return 1;
     if (alloc_device(b)) return 1;

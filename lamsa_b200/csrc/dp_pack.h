@@ -11,6 +11,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "../../include/lamsa_b200.h"
 #include "dp_device.cuh"
@@ -46,11 +49,22 @@ inline int env_int(const char* name, int dflt) {
     return e && *e ? atoi(e) : dflt;
 }
 
+// largest / smallest entry of a scoring matrix (floored / capped at 0 like the reference's scans); tasks of a batch
+// share a handful of matrices, so the last one looked at is remembered per thread
+struct MatRange { int maxs, mins; };
+inline MatRange mat_range(int m, const int8_t* mat) {
+    thread_local const int8_t* last = nullptr; thread_local int last_m = 0; thread_local int8_t copy[64]; thread_local MatRange r{0, 0};
+    if (mat == last && m == last_m && !memcmp(copy, mat, (size_t)m * m)) return r;
+    r.maxs = 0; r.mins = 0;
+    for (int a = 0; a < m * m; ++a) { r.maxs = r.maxs > mat[a] ? r.maxs : mat[a]; r.mins = r.mins < mat[a] ? r.mins : mat[a]; }
+    last = mat; last_m = m; memcpy(copy, mat, (size_t)m * m);
+    return r;
+}
+
 // src/ksw.c:696-704 -- double division, truncation toward zero
 inline int extend_band(int w, int qlen, int m, const int8_t* mat, int end_bonus,
                        int o_del, int e_del, int o_ins, int e_ins) {
-    int best = 0;
-    for (int a = 0; a < m * m; ++a) best = best > mat[a] ? best : mat[a];
+    const int best = mat_range(m, mat).maxs;
     int lim = (int)((double)(qlen * best + end_bonus - o_ins) / e_ins + 1.);
     lim = lim > 1 ? lim : 1;
     w = w < lim ? w : lim;
@@ -62,8 +76,8 @@ inline int extend_band(int w, int qlen, int m, const int8_t* mat, int end_bonus,
 
 // Can every value of this task live in the packed-int16 domain of dp_fill16.cuh?
 inline bool fits_int16(const lb2_task& t, int w) {
-    int maxs = 0, mins = 0;
-    for (int a = 0; a < t.m * t.m; ++a) { maxs = std::max<int>(maxs, t.mat[a]); mins = std::min<int>(mins, t.mat[a]); }
+    const MatRange mr = mat_range(t.m, t.mat);
+    const int maxs = mr.maxs, mins = mr.mins;
     const long ncol = std::min<long>(t.qlen, 2L * w + 1);
     const long maxo = std::max(t.o_del, t.o_ins), maxe = std::max(t.e_del, t.e_ins);
     if (t.o_del < 0 || t.o_ins < 0 || maxe > 255 || maxo + maxe > 500) return false;
@@ -97,7 +111,7 @@ inline int pick_variant(const lb2_task& t, int w, long ncol, int logS) {
         const int sub_max = t.kind == LB2_KIND_EXTEND ? sub_max_ext : sub_max_glb;
         // wide bands in 8-lane groups with 8 columns per lane (64-column tiles): LB2_SUB_NP4_MIN_EXT / _GLB
         static const int sub4_ext = env_int("LB2_SUB_NP4_MIN_EXT", 160), sub4_glb = env_int("LB2_SUB_NP4_MIN_GLB", 100);
-        static const int sub16_ext = env_int("LB2_SUB16_NP4_MIN_EXT", 1000000);     // 16-lane groups, 128-column tiles
+        static const int sub16_ext = env_int("LB2_SUB16_NP4_MIN_EXT", 375);     // 16-lane groups, 128-column tiles: windows of 1024 slots halve the resident 8-lane groups
         static const int sub16_glb = env_int("LB2_SUB16_NP4_MIN_GLB", 1000000), sub16_glb_max = env_int("LB2_SUB16_NP4_MAX_GLB", 1000000);
         if (sub_l == 8 && t.kind == LB2_KIND_EXTEND && ncol < sub_max && ncol >= sub16_ext &&
             warp_smem_bytes16(S_) * 2 * 2 <= kMaxDynSmem) return 9;
@@ -191,22 +205,41 @@ inline int classify_task(const lb2_task& t, int64_t l_pac, PackedTask& o, char* 
     return 0;
 }
 
+// Sequence bytes into a 32-byte aligned, 32-byte padded pool slot.  `stream`: with non-temporal stores -- the pinned
+// staging of a large batch is written once and read by the DMA engine only, so the destination lines need not be
+// read into the cache first (a write-allocate copy moves the destination twice over the memory bus; with eight
+// processes packing a gigabyte each per step the host memory system is what bounds the end-to-end rate).
+inline void put_sequence(uint8_t* dst, const uint8_t* src, size_t len, size_t padded, bool rev, bool stream) {
+    if (rev) { std::reverse_copy(src, src + len, dst); memset(dst + len, 0, padded - len); return; }
+#if defined(__SSE2__)
+    if (stream && len >= 64) {
+        size_t k = 0;
+        for (; k + 16 <= len; k += 16)
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + k), _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + k)));
+        uint8_t tail[48];
+        memset(tail, 0, sizeof tail);
+        memcpy(tail, src + k, len - k);
+        for (size_t q = 0; k + q < padded; q += 16)
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + k + q), _mm_loadu_si128(reinterpret_cast<const __m128i*>(tail + q)));
+        return;
+    }
+#endif
+    if (len) memcpy(dst, src, len);
+    memset(dst + len, 0, padded - len);
+}
+
 // copy a task's sequences into a pool at byte offset `off` (32-byte aligned); returns the bytes used.
 // `rev`: store both sequences back to front (what ksw_extend_r does before its fill, src/ksw.c:826-830).
-inline uint64_t copy_sequences(const lb2_task& t, PackedTask& o, uint8_t* pool, uint64_t off, bool rev = false) {
+inline uint64_t copy_sequences(const lb2_task& t, PackedTask& o, uint8_t* pool, uint64_t off, bool rev = false, bool stream = false) {
     const bool tpac = (t.flags & LB2_FLAG_TARGET_PAC) != 0;
-    uint8_t* q = pool + off;
     const uint64_t qp = pool_bytes_query(t.qlen);
     o.d.q_off32 = (uint32_t)(off >> 5);
-    if (t.qlen) { if (rev) std::reverse_copy(t.query, t.query + t.qlen, q); else memcpy(q, t.query, (size_t)t.qlen); }
-    memset(q + t.qlen, 0, qp - (uint64_t)t.qlen);
+    put_sequence(pool + off, t.query, (size_t)t.qlen, (size_t)qp, rev, stream);
     uint64_t used = qp;
     if (!tpac) {
-        uint8_t* tt = pool + off + qp;
         const uint64_t tp = pool_bytes_target(t.tlen);
         o.d.t_off32 = (uint32_t)((off + qp) >> 5);
-        if (t.tlen) { if (rev) std::reverse_copy(t.target, t.target + t.tlen, tt); else memcpy(tt, t.target, (size_t)t.tlen); }
-        memset(tt + t.tlen, 0, tp - (uint64_t)t.tlen);
+        put_sequence(pool + off + qp, t.target, (size_t)t.tlen, (size_t)tp, rev, stream);
         used += tp;
     }
     return used;
