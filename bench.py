@@ -124,6 +124,11 @@ def pipeline_fixture():
     return None
 
 
+def pipeline_replicate(base, n_gpus):
+    """Weak scaling like the DP leg: the reads are taken `base` times per GPU."""
+    return base * max(1, n_gpus)
+
+
 def pipeline_leg(impl, n_gpus, repeat=2):
     """Whole `lamsa aln -N` on the pipeline fixture -> dict for the JSON line (never raises)."""
     try:
@@ -132,11 +137,12 @@ def pipeline_leg(impl, n_gpus, repeat=2):
         exe = pipeline.REFBIN if impl == "reference" else pipeline.PRODUCER
         if fx is None or not os.path.exists(exe):
             return {"unavailable": f"{'fixture' if fx is None else exe} not present (built where the reference tree is mounted)"}
-        work = pipeline.temp_workdir(fx[0], fx[1])
+        rep = pipeline_replicate(fx[1], n_gpus)
+        work = pipeline.temp_workdir(fx[0], rep)
         bases = pipeline.read_bases(work)
         exp = list(open(os.path.join(work, "expected.sam")))
         cores = os.cpu_count() or 1
-        in_flight = env_int("LB2_READS_IN_FLIGHT", 8192 * n_gpus)
+        in_flight = env_int("LB2_READS_IN_FLIGHT", min(8192 * n_gpus, 24576))
         env = {} if impl == "reference" else {"LB2_DEVICES": str(n_gpus), "LB2_READS_IN_FLIGHT": str(in_flight), "LB2_FIBER_STATS": "1",
                                               "LB2_READ_TRACE": os.path.join(work, "read_trace.txt")}
         best, steady = None, None
@@ -157,7 +163,7 @@ def pipeline_leg(impl, n_gpus, repeat=2):
                "definition": "sum of read lengths / wall seconds of the alignment stage (lamsa_aln_core), seeding and index loading excluded (SURVEY.md 8d); "
                              "the stage is bracketed by the program's own stderr lines 'Mapping reads to genome' / 'Mapping done'",
                "stage_s": best["stage_s"], "whole_process_s": best["wall_s"], "whole_process_mbp_per_s": bases / best["wall_s"] / 1e6,
-               "fixture": fx[2], "reads_bases": bases, "sam_records": len([l for l in best["sam"] if not l.startswith("@")]),
+               "fixture": fx[2] + (f"; x{n_gpus} for {n_gpus} GPUs (weak scaling: the same reads per GPU)" if n_gpus > 1 else ""), "reads_bases": bases, "sam_records": len([l for l in best["sam"] if not l.startswith("@")]),
                "sam_identical_to_reference": best["sam"] == exp, "runs": repeat, "host_cores": cores}
         if impl == "reference":
             out["program"] = f"unmodified reference lamsa aln -t {cores} -N (oracle/_ref/lamsa_ref)"
@@ -231,6 +237,9 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a CPU group for the wait during the whole-program leg: an NCCL barrier would keep the idle ranks spinning on
+        # the cores the leg's host threads need
+        cpu_group = dist.new_group(backend="gloo")
     dev = local if world > 1 else 0
     torch.cuda.set_device(dev)
 
@@ -355,7 +364,8 @@ def main():
     if rank == 0 and not a.no_pipeline:
         torch.cuda.empty_cache()
         pipe = pipeline_leg("b200", world)
-    barrier()
+    if dist is not None:
+        dist.barrier(group=cpu_group)
 
     traffic, traffic_note = None, "no ncu capture committed"
     try:        # dram bytes of the dominant kernel from the committed ncu capture, scaled to this task count

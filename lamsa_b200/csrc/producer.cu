@@ -378,6 +378,8 @@ std::vector<Device*>& devices() {
         Device* d = new Device();
         d->device = base + k;
         bool ok = true;
+        // this process runs ten device threads per GPU next to the workers: waits on the GPU should sleep, not spin
+        if (!env_i("LB2_SPIN_SYNC", 0)) { cudaSetDevice(d->device); cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync); }
         for (int q = 0; q < kSlots && ok; ++q) {
             ok = lb2_ctx_create(d->device, &d->slot[q].ctx) == 0;
             if (ok) lb2_ctx_set_scratch_limit(d->slot[q].ctx, scratch);

@@ -337,6 +337,8 @@ int lamsa_aln_core(const char *read_prefix, char *seed_result, seed_msg *s_msg,
 	if (AP->n_thread > n_workers) n_workers = AP->n_thread;
 	if (s_msg->read_all > 0 && n_workers > s_msg->read_all) n_workers = s_msg->read_all;
 	if (n_workers < 1) n_workers = 1;
+	/* a worker's stack and its guard page are two mappings; stay well below vm.max_map_count (65530 by default) */
+	if (n_workers > 24576) n_workers = 24576;
 	P.ring_n = 4 * n_workers;
 	P.ring = (out_slot *)calloc(P.ring_n, sizeof(out_slot));
 
