@@ -372,6 +372,30 @@ int lb2_fiber_selftest(int n, int yields, int threads);
  * start-up overlaps the caller's own start-up (index loading).  Optional. */
 void lb2_dropin_warmup(void);
 
+/* ------------------------------------------- 5. alignment record statistics -- */
+/*
+ * The reference-touching half of lamsa_res_aux (src/frag_check.c:793-853): a record's CIGAR walked
+ * against its read and the resident 2-bit reference (lb2_ctx_set_reference), giving the counts from which NM and AS
+ * follow (:835-838: NM = mismatches + inserted + deleted bases; AS = matches*match - mismatches*mis - gap costs).
+ * CIGAR operators other than M / I / D / S are reported as ref_used = -(op+1) (the reference exits there).
+ */
+typedef struct {
+    const cigar32_t *cigar; int32_t n_cigar;
+    int32_t read_len;
+    const uint8_t *read;          /* codes 0..4, in the orientation the record is reported in             */
+    int64_t ref_pac;              /* forward pac coordinate of the record's first reference base           */
+} lb2_aux_task;
+typedef struct {
+    int32_t n_match, n_mismatch, n_ins_open, n_ins_ext, n_del_open, n_del_ext;
+    int32_t read_used, ref_used;  /* read / reference bases the CIGAR consumed                             */
+} lb2_aux_result;
+int  lb2_aux_run(lb2_ctx *ctx, int64_t n, const lb2_aux_task *tasks, lb2_aux_result *results);
+/* The same for callers inside the batch producer's worker fibers: parks the request; all parked requests of all
+ * workers are served as one launch (producer.cu).  lb2_producer_set_reference hands the producer the reference
+ * once (the pointer must stay valid; it is uploaded to the GPUs that serve these requests). */
+int  lb2_worker_aux_counts(int64_t n, const lb2_aux_task *tasks, lb2_aux_result *results);
+void lb2_producer_set_reference(const uint8_t *pac, int64_t l_pac);
+
 /* field offsets / sizes of the library's restatements of the reference structs (ref_abi.h), in the
  * order of oracle/sdp_ref_shim.c:ref_sdp_offsets / ref_sdp_sizes; returns the count */
 int  lb2_ref_abi_offsets(int *out);

@@ -20,6 +20,7 @@
 #include "dp_fill16d.cuh"
 #include "dp_trace.cuh"
 #include "int_peak.cuh"
+#include "aux_scan.cuh"
 #include "ctx_internal.h"
 #include "dp_pack.h"
 
@@ -94,6 +95,8 @@ struct lb2_ctx {
     int32_t* d_ctmp = nullptr; size_t ctmp_cap = 0;     // per-task reversed CIGAR scratch (words)
     uint8_t* d_gwin = nullptr; size_t gwin_cap = 0;     // eh[] windows too large for shared memory
     uint8_t* d_pac = nullptr;  int64_t l_pac = 0;       // resident 2-bit forward reference (lb2_ctx_set_reference)
+    // grow-only staging of lb2_aux_run (pinned host + device): records, CIGAR words, read bytes, results
+    uint8_t* aux_h = nullptr; uint8_t* aux_d = nullptr; size_t aux_cap = 0;
     int occ[kNumClass] = {0};                           // resident blocks per SM, filled lazily
     // side streams: the launch classes of a wave run concurrently, so the drain of one
     // class (few long tasks left) is filled by the blocks of the next
@@ -185,6 +188,8 @@ extern "C" void lb2_ctx_destroy(lb2_ctx* c) {
     if (c->d_ctmp) cudaFree(c->d_ctmp);
     if (c->d_gwin) cudaFree(c->d_gwin);
     if (c->d_pac) cudaFree(c->d_pac);
+    if (c->aux_h) cudaFreeHost(c->aux_h);
+    if (c->aux_d) cudaFree(c->aux_d);
     for (auto& p : c->parked) if (p.valid) p.release();
     if (c->copy) cudaStreamDestroy(c->copy);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -951,6 +956,54 @@ extern "C" int lb2_ctx_last_run_kernel_ms(const lb2_ctx* ctx, float* fill_ms, fl
     if (!ctx) return fail("ctx is NULL");
     if (fill_ms) *fill_ms = ctx->run_fill_ms;
     if (trace_ms) *trace_ms = ctx->run_trace_ms;
+    return 0;
+}
+
+// ---- alignment record statistics (include/lamsa_b200.h section 5, aux_scan.cuh) ----------------------------------
+extern "C" int lb2_aux_run(lb2_ctx* c, int64_t n, const lb2_aux_task* tasks, lb2_aux_result* results) {
+    if (!c || n < 0 || (n > 0 && (!tasks || !results))) return fail("lb2_aux_run: bad argument");
+    if (!c->d_pac) return fail("lb2_aux_run: no resident reference (lb2_ctx_set_reference)");
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    // one staging block: [AuxRec n][cigar words][read bytes][results n], each part 16-byte aligned
+    size_t words = 0, bytes = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (tasks[i].n_cigar < 0 || tasks[i].read_len < 0 || (tasks[i].n_cigar && !tasks[i].cigar) || (tasks[i].read_len && !tasks[i].read))
+            return fail("lb2_aux_run: task %lld is malformed", (long long)i);
+        words += (size_t)tasks[i].n_cigar; bytes += ((size_t)tasks[i].read_len + 15) & ~(size_t)15;
+    }
+    auto up = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t o_rec = 0, o_cig = up(sizeof(AuxRec) * (size_t)n), o_rd = o_cig + up(words * 4), o_res = o_rd + up(bytes),
+                 total = o_res + sizeof(lb2_aux_result) * (size_t)n;
+    if (c->aux_cap < total) {
+        const size_t cap = grown(total, c->aux_cap, (size_t)1 << 20);
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFreeHost(c->aux_h); cudaFree(c->aux_d); c->aux_h = nullptr; c->aux_d = nullptr; c->aux_cap = 0;
+        CU(cudaMallocHost(&c->aux_h, cap)); CU(cudaMalloc(&c->aux_d, cap)); c->aux_cap = cap;
+    }
+    AuxRec* rec = reinterpret_cast<AuxRec*>(c->aux_h + o_rec);
+    int32_t* cg = reinterpret_cast<int32_t*>(c->aux_h + o_cig);
+    uint8_t* rd = c->aux_h + o_rd;
+    size_t w = 0, b = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const lb2_aux_task& t = tasks[i];
+        if (t.ref_pac < 0) return fail("lb2_aux_run: task %lld: negative reference coordinate", (long long)i);
+        rec[i] = AuxRec{(uint32_t)w, (uint32_t)t.n_cigar, (uint32_t)b, (uint32_t)t.read_len, (uint64_t)t.ref_pac};
+        if (t.n_cigar) memcpy(cg + w, t.cigar, (size_t)t.n_cigar * 4);
+        if (t.read_len) memcpy(rd + b, t.read, (size_t)t.read_len);
+        w += (size_t)t.n_cigar; b += ((size_t)t.read_len + 15) & ~(size_t)15;
+    }
+    cudaStream_t s = c->stream;
+    CU(cudaMemcpyAsync(c->aux_d, c->aux_h, o_res, cudaMemcpyHostToDevice, s));
+    const int wpb = 4;
+    aux_scan_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, s>>>(
+        reinterpret_cast<const AuxRec*>(c->aux_d + o_rec), (int)n, reinterpret_cast<const int32_t*>(c->aux_d + o_cig),
+        c->aux_d + o_rd, c->d_pac, (long long)c->l_pac, reinterpret_cast<lb2_aux_result*>(c->aux_d + o_res));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->aux_h + o_res, c->aux_d + o_res, sizeof(lb2_aux_result) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    memcpy(results, c->aux_h + o_res, sizeof(lb2_aux_result) * (size_t)n);
     return 0;
 }
 

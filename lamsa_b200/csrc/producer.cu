@@ -96,6 +96,12 @@ struct DpGroup {
     std::vector<lb2::DpRequest*> reqs;
     std::vector<Fiber*> owners;
 };
+struct AuxRequest { int64_t n; const lb2_aux_task* tasks; lb2_aux_result* results; };
+struct AuxGroup {
+    Clock::time_point t_first;
+    std::vector<AuxRequest*> reqs;
+    std::vector<Fiber*> owners;
+};
 struct SdpGroup {
     Clock::time_point t_first;
     std::vector<lb2::SdpRequest*> reqs;
@@ -115,7 +121,7 @@ struct Worker {                          // one OS thread
     std::deque<Fiber*> resumed, fresh;   // run queue: fibers with a served request first, then fibers not started yet
     std::mutex in_mu; std::condition_variable in_cv; std::vector<Fiber*> inbox;
     std::atomic<int> inbox_n{0};
-    DpGroup* fast = nullptr; DpGroup* slow = nullptr; SdpGroup* sdp = nullptr;
+    DpGroup* fast = nullptr; DpGroup* slow = nullptr; SdpGroup* sdp = nullptr; AuxGroup* aux = nullptr;
     size_t live = 0;
     int64_t switches = 0, handovers = 0, dp_n = 0, sdp_n = 0;
     double dev_wait_s = 0, idle_s = 0, fiber_s = 0, pack_s = 0, dp_lat_s = 0, sdp_lat_s = 0, dp_lat_max = 0;
@@ -141,15 +147,17 @@ struct Device {
     int device = 0;
     bool loopback = false;                       // self test: no GPU, requests are handed straight back
     lb2_ctx* sdp_ctx[kSdpThreads] = {nullptr};
+    lb2_ctx* aux_ctx = nullptr;                  // record statistics (lb2_aux_run): holds the resident reference
     std::mutex mu;
-    std::condition_variable cv_submit, cv_slot, cv_sdp;
+    std::condition_variable cv_submit, cv_slot, cv_sdp, cv_aux;
     std::vector<DpGroup*> pend_fast, pend_slow;
     int64_t pend_fast_tasks = 0, pend_slow_tasks = 0;
     Clock::time_point pend_fast_since;           // arrival of the oldest pending group
     std::vector<SdpGroup*> pend_sdp;
+    std::vector<AuxGroup*> pend_aux;
     Slot slot[kSlots];
     bool stop = false;
-    std::thread submitter, sdp_thread[kSdpThreads];
+    std::thread submitter, sdp_thread[kSdpThreads], aux_thread;
     // statistics (under mu)
     std::vector<int> batch_tasks;
     int64_t dp_tasks = 0, slow_batches = 0, slow_tasks = 0, sdp_reqs = 0, sdp_batches = 0;
@@ -341,6 +349,38 @@ void sdp_main(Device* d, int k) {
     }
 }
 
+// the reference for lb2_aux_run, given once by the host program (lb2_producer_set_reference)
+const uint8_t* g_ref_pac = nullptr; int64_t g_ref_l_pac = 0;
+
+void aux_main(Device* d) {
+    cudaSetDevice(d->device);
+    bool have_ref = false;
+    for (;;) {
+        std::vector<AuxGroup*> take;
+        {
+            std::unique_lock<std::mutex> lk(d->mu);
+            d->cv_aux.wait(lk, [&] { return d->stop || !d->pend_aux.empty(); });
+            if (d->pend_aux.empty()) return;
+            take.swap(d->pend_aux);
+        }
+        if (!have_ref) {
+            if (!g_ref_pac || lb2_ctx_set_reference(d->aux_ctx, g_ref_pac, g_ref_l_pac)) die("record statistics need the reference (lb2_producer_set_reference)");
+            have_ref = true;
+        }
+        std::vector<lb2_aux_task> tasks; std::vector<lb2_aux_result> results; std::vector<Fiber*> owners;
+        for (AuxGroup* g : take) for (AuxRequest* q : g->reqs) tasks.insert(tasks.end(), q->tasks, q->tasks + q->n);
+        results.resize(tasks.size());
+        if (lb2_aux_run(d->aux_ctx, (int64_t)tasks.size(), tasks.data(), results.data())) die("record statistics failed");
+        size_t at = 0;
+        for (AuxGroup* g : take) {
+            for (AuxRequest* q : g->reqs) { std::copy(results.begin() + (long)at, results.begin() + (long)(at + (size_t)q->n), q->results); at += (size_t)q->n; }
+            owners.insert(owners.end(), g->owners.begin(), g->owners.end());
+            delete g;
+        }
+        route_home(owners);
+    }
+}
+
 // self test: the "device" hands every request straight back from another thread
 void loopback_main(Device* d) {
     for (;;) {
@@ -373,25 +413,36 @@ std::vector<Device*>& devices() {
     const auto t0 = Clock::now();
     const int ndev = std::max(1, env_i("LB2_DEVICES", 1)), base = env_i("LB2_DEVICE", 0);
     const uint64_t scratch = (uint64_t)env_i("LB2_SLOT_SCRATCH_MB", 8192) << 20;
-    std::vector<Device*> opened;
-    for (int k = 0; k < ndev; ++k) {
-        Device* d = new Device();
-        d->device = base + k;
-        bool ok = true;
-        // this process runs ten device threads per GPU next to the workers: waits on the GPU should sleep, not spin
-        if (!env_i("LB2_SPIN_SYNC", 0)) { cudaSetDevice(d->device); cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync); }
-        for (int q = 0; q < kSlots && ok; ++q) {
-            ok = lb2_ctx_create(d->device, &d->slot[q].ctx) == 0;
-            if (ok) lb2_ctx_set_scratch_limit(d->slot[q].ctx, scratch);
-        }
-        for (int q = 0; q < kSdpThreads && ok; ++q) ok = lb2_ctx_create(d->device, &d->sdp_ctx[q]) == 0;
-        if (!ok) { g_dev_error = lb2_last_error(); return g_devices; }      // g_devices stays empty
-        opened.push_back(d);
+    // one opener thread per GPU: creating a device's primary context takes of the order of a second
+    std::vector<Device*> opened((size_t)ndev, nullptr);
+    std::vector<std::string> errs((size_t)ndev);
+    {
+        std::vector<std::thread> openers;
+        for (int k = 0; k < ndev; ++k)
+            openers.emplace_back([&, k] {
+                Device* d = new Device();
+                d->device = base + k;
+                bool ok = true;
+                // this process runs ten device threads per GPU next to the workers: waits on the GPU should sleep, not spin
+                if (!env_i("LB2_SPIN_SYNC", 0)) { cudaSetDevice(d->device); cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync); }
+                for (int q = 0; q < kSlots && ok; ++q) {
+                    ok = lb2_ctx_create(d->device, &d->slot[q].ctx) == 0;
+                    if (ok) lb2_ctx_set_scratch_limit(d->slot[q].ctx, scratch);
+                }
+                for (int q = 0; q < kSdpThreads && ok; ++q) ok = lb2_ctx_create(d->device, &d->sdp_ctx[q]) == 0;
+                ok = ok && lb2_ctx_create(d->device, &d->aux_ctx) == 0;
+                if (!ok) errs[(size_t)k] = lb2_last_error();        // lb2_last_error is per thread
+                else opened[(size_t)k] = d;
+            });
+        for (auto& t : openers) t.join();
     }
+    for (int k = 0; k < ndev; ++k)
+        if (!opened[(size_t)k]) { g_dev_error = errs[(size_t)k]; return g_devices; }      // g_devices stays empty
     const double t_ctx = secs(t0, Clock::now());
     for (Device* d : opened) {
         d->submitter = std::thread(submitter_main, d);
         for (int q = 0; q < kSdpThreads; ++q) d->sdp_thread[q] = std::thread(sdp_main, d, q);
+        d->aux_thread = std::thread(aux_main, d);
         for (int q = 0; q < kSlots; ++q) d->slot[q].completer = std::thread(completer_main, d, q);
     }
     g_devices = opened;
@@ -466,6 +517,18 @@ void hand_over_sdp(Worker* w) {
     d->cv_sdp.notify_one();
 }
 
+void hand_over_aux(Worker* w) {
+    if (!w->aux || w->aux->reqs.empty()) return;
+    bind_device(w);
+    Device* d = w->dev;
+    {
+        std::lock_guard<std::mutex> lk(d->mu);
+        d->pend_aux.push_back(w->aux);
+    }
+    w->aux = nullptr;
+    d->cv_aux.notify_one();
+}
+
 void worker_main(Worker* w) {
     tl_worker = w;
     static const size_t flush_dp = (size_t)env_i("LB2_FLUSH_TASKS", 256), flush_sdp = (size_t)env_i("LB2_FLUSH_READS", 32);
@@ -493,11 +556,13 @@ void worker_main(Worker* w) {
             if ((w->fast && (w->fast->reqs.size() >= flush_dp || tf1 - w->fast->t_first > flush_wait)) ||
                 (w->slow && (w->slow->reqs.size() >= flush_dp / 8 + 1 || tf1 - w->slow->t_first > flush_wait))) hand_over_dp(w);
             if (w->sdp && (w->sdp->reqs.size() >= flush_sdp || tf1 - w->sdp->t_first > flush_wait)) hand_over_sdp(w);
+            if (w->aux && (w->aux->reqs.size() >= flush_sdp || tf1 - w->aux->t_first > flush_wait)) hand_over_aux(w);
             continue;
         }
         if (w->live == 0) break;
         hand_over_dp(w);
         hand_over_sdp(w);
+        hand_over_aux(w);
         const auto t0 = Clock::now();
         std::unique_lock<std::mutex> lk(w->in_mu);
         w->in_cv.wait(lk, [&] { return !w->inbox.empty(); });
@@ -614,6 +679,22 @@ extern "C" void lb2_fiber_main(void* p) {                 // entered once per fi
     abort();
 }
 #endif
+
+extern "C" void lb2_producer_set_reference(const uint8_t* pac, int64_t l_pac) { g_ref_pac = pac; g_ref_l_pac = l_pac; }
+
+// lb2_aux_run for a worker fiber: parks; all parked requests of all workers are one launch
+extern "C" int lb2_worker_aux_counts(int64_t n, const lb2_aux_task* tasks, lb2_aux_result* results) {
+    Worker* w = tl_worker;
+    if (!w || !w->cur) return lb2::set_error("lb2_worker_aux_counts: not called from a worker of the batch producer");
+    if (n <= 0) return 0;
+    AuxRequest r{n, tasks, results};
+    if (!w->aux) { w->aux = new AuxGroup(); w->aux->t_first = Clock::now(); }
+    w->aux->reqs.push_back(&r); w->aux->owners.push_back(w->cur);
+    const auto t1 = Clock::now();
+    yield_to_scheduler();
+    tl_worker->cur->parked_s += secs(t1, Clock::now());
+    return 0;
+}
 
 // Seconds the calling worker has spent parked on DP / chaining requests so far (statistics of a host pipeline).
 extern "C" double lb2_worker_parked_seconds(void) {

@@ -45,6 +45,9 @@ extern int lb2_worker_join(pthread_t id, void **ret);
 extern void lb2_worker_yield(void);
 extern double lb2_worker_parked_seconds(void);
 extern void lb2_dropin_warmup(void);
+#ifdef LB2_CORE_RES_AUX
+extern void lb2_producer_set_reference(const uint8_t *pac, int64_t l_pac);   /* res_aux.c: record statistics on the GPU */
+#endif
 
 /* non-static parts of the reference's src/lamsa_aln.c that its header does not declare */
 typedef struct { lamsa_aln_per_para *APP; map_msg *m_msg; aln_res *a_res; } lamsa_seq_t;   /* src/lamsa_aln.c:782-794 */
@@ -321,6 +324,9 @@ int lamsa_aln_core(const char *read_prefix, char *seed_result, seed_msg *s_msg,
 	pipeline_t P;
 	memset(&P, 0, sizeof P);
 	P.AP = AP; P.bwt = bwt; P.bns = bns; P.pac = pac; P.s_msg = s_msg;
+#ifdef LB2_CORE_RES_AUX
+	lb2_producer_set_reference(pac, bns->l_pac);
+#endif
 	gzFile readfp;
 	if ((P.seed_mapfp = fopen(seed_result, "r")) == NULL) { fprintf(stderr, "\n[lamsa_aln_core] Can't open seed-result file %s.\n", seed_result); exit(1); }
 	if ((readfp = gzopen(read_prefix, "r")) == NULL) { fprintf(stderr, "\n[lamsa_aln_core] Can't open read file %s.\n", read_prefix); exit(1); }

@@ -76,6 +76,24 @@ class Context:
         weakref.finalize(cig, self.lib.lb2_free, pool.value)
         return res, cig
 
+    def aux_counts(self, cigars, reads, ref_pacs):
+        """lb2_aux_run (include/lamsa_b200.h section 5): per record (CIGAR words, read codes, pac coordinate) ->
+        array of (n_match, n_mismatch, n_ins_open, n_ins_ext, n_del_open, n_del_ext, read_used, ref_used)."""
+        from ._lib import AuxTask
+        n = len(cigars)
+        tasks = (AuxTask * max(n, 1))()
+        keep = []
+        for i in range(n):
+            c = np.ascontiguousarray(cigars[i], dtype=np.int32); r = np.ascontiguousarray(reads[i], dtype=np.uint8)
+            keep += [c, r]
+            tasks[i].cigar = c.ctypes.data if len(c) else None; tasks[i].n_cigar = len(c)
+            tasks[i].read = r.ctypes.data if len(r) else None; tasks[i].read_len = len(r)
+            tasks[i].ref_pac = int(ref_pacs[i])
+        out = np.zeros((n, 8), dtype=np.int32)
+        if self.lib.lb2_aux_run(self.handle, n, tasks, out.ctypes.data):
+            raise _err(self.lib, "lb2_aux_run")
+        return out
+
     def set_chunk_tasks(self, n):
         if self.lib.lb2_ctx_set_chunk_tasks(self.handle, int(n)):
             raise _err(self.lib, "lb2_ctx_set_chunk_tasks")

@@ -20,7 +20,10 @@ EXES = {"dp": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin"),
         "dp+sdp": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin_sdp"),
         # + the alignment stage replaced by this repo's read pipeline (lamsa_b200/host/aln_core.c): reads as worker
         # fibers, every DP / chaining call served in batches gathered over all reads (`make -C oracle producer`)
-        "producer": os.path.join(ROOT, "oracle", "_ref", "lamsa_b200_aln")}
+        "producer": os.path.join(ROOT, "oracle", "_ref", "lamsa_b200_aln"),
+        # + lamsa_res_aux (NM / AS of every record) walking the CIGARs on the GPU over the resident reference
+        # (lamsa_b200/host/res_aux.c, `make -C oracle producer_aux`): the NM:i / AS:i tags must not move
+        "producer+aux": os.path.join(ROOT, "oracle", "_ref", "lamsa_b200_aln_aux")}
 FIXTURES = [
     ("small", os.path.join(ROOT, "tests", "golden", "sam_small")),
     # 4 contigs; donor with deletions / insertions / inversions / duplications and translocations BETWEEN contigs
@@ -45,7 +48,7 @@ def stage(src, dst):
 
 @pytest.mark.parametrize("name,src", FIXTURES, ids=[f[0] for f in FIXTURES])
 @pytest.mark.parametrize("threads", [1, 4])
-@pytest.mark.parametrize("link", ["dp", "dp+sdp", "producer"])
+@pytest.mark.parametrize("link", ["dp", "dp+sdp", "producer", "producer+aux"])
 def test_dropin_sam_identical_to_reference(tmp_path, name, src, threads, link):
     EXE = EXES[link]
     if not os.path.exists(EXE):
@@ -53,7 +56,7 @@ def test_dropin_sam_identical_to_reference(tmp_path, name, src, threads, link):
     if not os.path.isdir(src):
         pytest.skip(f"fixture {src} not present")
     env = dict(os.environ)
-    if link == "producer":
+    if link.startswith("producer"):
         # reads in flight: the default (thousands), or fewer workers than reads with an odd count
         if threads == 1:
             env["LB2_READS_IN_FLIGHT"] = "37"
