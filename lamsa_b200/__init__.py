@@ -8,13 +8,13 @@ and raises when the shared library or a GPU is missing.
 """
 from ._lib import (LIB_PATH, LibraryMissing, load_library, TASK_DTYPE, RESULT_DTYPE,
                    AlnPara, KIND_GLOBAL, KIND_EXTEND, FLAG_CIGAR, FLAG_TARGET_PAC, FLAG_TARGET_REV)
-from .ksw import (Context, Batch, make_tasks, default_matrix,
+from .ksw import (Context, Batch, make_tasks, default_matrix, pinned_pool,
                   ksw_global2, ksw_global, ksw_extend2, ksw_extend, ksw_extend_core,
                   ksw_extend_c, ksw_extend_r, ksw_bi_extend)
 
 __all__ = [
     "LIB_PATH", "LibraryMissing", "load_library", "TASK_DTYPE", "RESULT_DTYPE", "AlnPara",
-    "KIND_GLOBAL", "KIND_EXTEND", "FLAG_CIGAR", "FLAG_TARGET_PAC", "FLAG_TARGET_REV", "Context", "Batch", "make_tasks", "default_matrix",
+    "KIND_GLOBAL", "KIND_EXTEND", "FLAG_CIGAR", "FLAG_TARGET_PAC", "FLAG_TARGET_REV", "Context", "Batch", "make_tasks", "default_matrix", "pinned_pool",
     "ksw_global2", "ksw_global", "ksw_extend2", "ksw_extend", "ksw_extend_core",
     "ksw_extend_c", "ksw_extend_r", "ksw_bi_extend",
 ]

@@ -83,8 +83,8 @@ PARA_FIELDS = [
 EXPORTS = [
     "ksw_global2", "ksw_global", "ksw_extend2", "ksw_extend", "ksw_extend_core", "ksw_extend_c",
     "ksw_extend_r", "ksw_bi_extend", "sw_mid_fix",
-    "lb2_ctx_create", "lb2_ctx_destroy", "lb2_last_error", "lb2_ctx_set_scratch_limit", "lb2_ctx_set_reference", "lb2_ctx_last_run_stats", "lb2_ctx_last_run_kernel_ms", "lb2_ctx_set_chunk_tasks", "lb2_dp_run",
-    "lb2_batch_create", "lb2_batch_upload", "lb2_batch_compute", "lb2_batch_compute_async", "lb2_batch_compute_done", "lb2_batch_compute_wait", "lb2_batch_download", "lb2_batch_download_view", "lb2_batch_stats", "lb2_batch_set_class_timing", "lb2_batch_class_stats",
+    "lb2_ctx_create", "lb2_ctx_destroy", "lb2_last_error", "lb2_ctx_set_scratch_limit", "lb2_ctx_set_reference", "lb2_ctx_last_run_stats", "lb2_ctx_last_run_kernel_ms", "lb2_ctx_set_chunk_tasks", "lb2_dp_run", "lb2_dp_run_pool", "lb2_pool_pack", "lb2_host_alloc", "lb2_host_free",
+    "lb2_batch_create", "lb2_batch_create_pool", "lb2_batch_upload", "lb2_batch_compute", "lb2_batch_compute_async", "lb2_batch_compute_done", "lb2_batch_compute_wait", "lb2_batch_download", "lb2_batch_download_view", "lb2_batch_stats", "lb2_batch_set_class_timing", "lb2_batch_class_stats",
     "lb2_batch_destroy", "lb2_free", "lb2_int_peak",
     "lb2_sdp_create", "lb2_sdp_reset", "lb2_sdp_run_bcc", "lb2_sdp_run_remain", "lb2_sdp_stats", "lb2_sdp_destroy", "lb2_sdp_get_tracked", "lb2_sdp_set_tracked",
     "lb2_aux_run", "lb2_worker_aux_counts", "lb2_producer_set_reference", "lb2_ref_abi_offsets", "lb2_ref_abi_sizes", "lb2_worker_spawn", "lb2_worker_join", "lb2_worker_yield", "lb2_worker_parked_seconds", "lb2_dropin_warmup", "lb2_fiber_selftest",
@@ -118,6 +118,13 @@ def load_library():
     lib.lb2_ctx_last_run_stats.argtypes = [P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64)]
     lib.lb2_dp_run.argtypes = [P, I64, P, P, C.POINTER(P), C.POINTER(I64)]
     lib.lb2_batch_create.argtypes = [P, I64, P, C.POINTER(P)]
+    lib.lb2_batch_create_pool.argtypes = [P, P, I64, I64, P, C.POINTER(P)]
+    lib.lb2_dp_run_pool.argtypes = [P, P, I64, I64, P, P, C.POINTER(P), C.POINTER(I64)]
+    lib.lb2_pool_pack.argtypes = [I64, P, P, I64, C.POINTER(I64)]
+    lib.lb2_ctx_last_run_kernel_ms.argtypes = [P, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.lb2_host_alloc.argtypes = [C.c_size_t, C.POINTER(P)]
+    lib.lb2_host_free.argtypes = [P]
+    lib.lb2_host_free.restype = None
     lib.lb2_batch_upload.argtypes = [P]
     lib.lb2_batch_compute.argtypes = [P, C.POINTER(C.c_float)]
     lib.lb2_batch_compute_async.argtypes = [P]

@@ -3,6 +3,7 @@
 // kernels class by class, and unpacks results.  No DP arithmetic happens here.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -83,7 +84,8 @@ struct Buffers {
 struct lb2_ctx {
     int device = 0;
     std::mutex mu;
-    Buffers parked[2];                                  // buffers of the last destroyed batches (two: lb2_dp_run pipelines)
+    static constexpr int kParked = 3;
+    Buffers parked[kParked];                            // buffers of the last destroyed batches (lb2_dp_run keeps two chunks enqueued while it drains a third)
     cudaStream_t copy = nullptr;                        // H2D of batch k+1 overlaps the kernels of batch k
     int64_t run_h2d = 0, run_d2h = 0, run_launches = 0; // counters of the last lb2_dp_run
     float run_fill_ms = 0, run_trace_ms = 0;
@@ -93,6 +95,11 @@ struct lb2_ctx {
     uint64_t scratch_limit = 0;
     uint8_t* d_z = nullptr;    size_t z_cap = 0;        // direction nibbles (+ row bands)
     int32_t* d_ctmp = nullptr; size_t ctmp_cap = 0;     // per-task reversed CIGAR scratch (words)
+    // second scratch set + compute stream: lb2_dp_run alternates its chunks between the two, so the fills of chunk
+    // k+1 start on the SMs the tail of chunk k leaves idle and run beside chunk k's traceback
+    uint8_t* d_z1 = nullptr;    size_t z1_cap = 0;
+    int32_t* d_ctmp1 = nullptr; size_t ctmp1_cap = 0;
+    cudaStream_t stream1 = nullptr;
     uint8_t* d_gwin = nullptr; size_t gwin_cap = 0;     // eh[] windows too large for shared memory
     uint8_t* d_pac = nullptr;  int64_t l_pac = 0;       // resident 2-bit forward reference (lb2_ctx_set_reference)
     // grow-only staging of lb2_aux_run (pinned host + device): records, CIGAR words, read bytes, results
@@ -186,6 +193,9 @@ extern "C" void lb2_ctx_destroy(lb2_ctx* c) {
     cudaSetDevice(c->device);
     if (c->d_z) cudaFree(c->d_z);
     if (c->d_ctmp) cudaFree(c->d_ctmp);
+    if (c->d_z1) cudaFree(c->d_z1);
+    if (c->d_ctmp1) cudaFree(c->d_ctmp1);
+    if (c->stream1) cudaStreamDestroy(c->stream1);
     if (c->d_gwin) cudaFree(c->d_gwin);
     if (c->d_pac) cudaFree(c->d_pac);
     if (c->aux_h) cudaFreeHost(c->aux_h);
@@ -254,6 +264,8 @@ struct lb2_batch {
     int64_t h2d_bytes = 0, d2h_bytes = 0, launches = 0;
     float fill_ms = 0, trace_ms = 0;
     bool uploaded = false, enqueued = false, computed = false;
+    int slot = 0;                                                // which scratch set / compute stream of the context (0, 1)
+    const uint8_t* raw_src = nullptr; size_t raw_bytes = 0;      // pooled batch: the range of the caller's pool its tasks use
     std::vector<cudaEvent_t> wave_ev;      // only when scratch forces several waves
     bool class_timing = false;             // lb2_batch_set_class_timing: classes one after the other, each with its own events
     struct ClassRun { int cls; int tasks; cudaEvent_t t0, t1; float ms; };
@@ -305,21 +317,21 @@ static size_t grown(size_t need, size_t old_cap, size_t floor_) {
 
 // ---- the three steps every batch creator shares ------------------------------------------------
 // (1) pinned host staging for n tasks and pool_bytes of sequences (grow-only, taken from the context's parked set)
-static int alloc_host(lb2_batch* b, size_t pool_bytes) {
+static int alloc_host(lb2_batch* b, size_t pool_bytes, bool host_pool = true) {
     lb2_ctx* ctx = b->ctx;
     b->pool_bytes = pool_bytes + 64;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         // prefer the parked set whose pinned pool is large enough
         int pick = -1;
-        for (int k = 0; k < 2; ++k)
+        for (int k = 0; k < lb2_ctx::kParked; ++k)
             if (ctx->parked[k].valid && (pick < 0 || ctx->parked[k].h_pool_cap >= b->pool_bytes)) pick = k;
         if (pick >= 0) { b->B = ctx->parked[pick]; ctx->parked[pick] = Buffers(); }
     }
     Buffers& B = b->B;
     B.valid = true;
     const size_t n1c = (size_t)std::max<int64_t>(b->n, 1);
-    if (B.h_pool_cap < b->pool_bytes) {
+    if (host_pool && B.h_pool_cap < b->pool_bytes) {
         const size_t cap = grown(b->pool_bytes, B.h_pool_cap, (size_t)1 << 20);
         cudaFreeHost(B.h_pool); B.h_pool = nullptr; B.h_pool_cap = 0;
         CU(cudaMallocHost(&B.h_pool, cap)); B.h_pool_cap = cap;
@@ -365,7 +377,9 @@ static int layout_waves(lb2_batch* b, const int16_t* cls, const uint8_t* bin, co
     b->cls.assign(cls, cls + n);
     for (auto& wv : b->waves) {
         // classes in use are few: histogram only those (a producer submits thousands of small batches)
-        std::vector<int32_t> keys((size_t)wv.count);
+        thread_local std::vector<int32_t> keys_tl;
+        if (keys_tl.size() < (size_t)wv.count + 1) keys_tl.resize((size_t)wv.count + 1);
+        int32_t* const keys = keys_tl.data();
         parallel_for(wv.count, [&](int64_t lo_i, int64_t hi_i) {
             for (int64_t k = lo_i; k < hi_i; ++k) keys[(size_t)k] = (int32_t)cls[wv.first + k] * kCostBins + bin[wv.first + k];
         });
@@ -440,36 +454,54 @@ static int alloc_device(lb2_batch* b) {
     // (lb2_dp_run pipelines chunks): wait for them explicitly rather than rely on cudaFree's implicit barrier.
     uint64_t zmax = 16, cmax = 16;
     for (auto& wv : b->waves) { zmax = std::max(zmax, wv.z_bytes); cmax = std::max(cmax, wv.ctmp_words); }
-    if (ctx->z_cap < zmax || ctx->ctmp_cap < cmax) {
+    if (b->slot && !ctx->stream1) CU(cudaStreamCreateWithFlags(&ctx->stream1, cudaStreamNonBlocking));
+    uint8_t*& dz = b->slot ? ctx->d_z1 : ctx->d_z;          size_t& zcap = b->slot ? ctx->z1_cap : ctx->z_cap;
+    int32_t*& dct = b->slot ? ctx->d_ctmp1 : ctx->d_ctmp;   size_t& ccap = b->slot ? ctx->ctmp1_cap : ctx->ctmp_cap;
+    if (zcap < zmax || ccap < cmax) {
         std::lock_guard<std::mutex> lk(ctx->mu);
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaStreamSynchronize(b->slot ? ctx->stream1 : ctx->stream));
         for (int q = 0; q < lb2_ctx::kAux; ++q) CU(cudaStreamSynchronize(ctx->aux[q]));
-        if (ctx->z_cap < zmax) {
-            const size_t cap = grown(zmax, ctx->z_cap, (size_t)16 << 20);
-            if (ctx->d_z) CU(cudaFree(ctx->d_z));
-            ctx->d_z = nullptr; ctx->z_cap = 0;
-            CU(cudaMalloc(&ctx->d_z, cap + 64)); ctx->z_cap = cap;
+        if (zcap < zmax) {
+            const size_t cap = grown(zmax, zcap, (size_t)16 << 20);
+            if (dz) CU(cudaFree(dz));
+            dz = nullptr; zcap = 0;
+            CU(cudaMalloc(&dz, cap + 64)); zcap = cap;
         }
-        if (ctx->ctmp_cap < cmax) {
-            const size_t cap = grown(cmax, ctx->ctmp_cap, (size_t)1 << 20);
-            if (ctx->d_ctmp) CU(cudaFree(ctx->d_ctmp));
-            ctx->d_ctmp = nullptr; ctx->ctmp_cap = 0;
-            CU(cudaMalloc(&ctx->d_ctmp, (cap + 16) * 4)); ctx->ctmp_cap = cap;
+        if (ccap < cmax) {
+            const size_t cap = grown(cmax, ccap, (size_t)1 << 20);
+            if (dct) CU(cudaFree(dct));
+            dct = nullptr; ccap = 0;
+            CU(cudaMalloc(&dct, (cap + 16) * 4)); ccap = cap;
         }
     }
     return 0;
 }
 
-extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_batch** out) {
+// `pool` != nullptr: every sequence of `tasks` lies inside [pool, pool + pool_bytes) (lb2_batch_create_pool); the range
+// of the pool the tasks use is then uploaded as it lies and the kernels read it in place (DTask offsets in bytes,
+// kRawOff) instead of a 32-byte aligned, padded copy made here.
+static int batch_create_impl(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, const uint8_t* upool, int64_t upool_bytes, lb2_batch** out, int slot = 0) {
     if (!ctx || !out || (n > 0 && !tasks)) return fail("lb2_batch_create: NULL argument");
     if (n < 0 || n > (int64_t)1 << 30) return fail("lb2_batch_create: n=%lld out of range", (long long)n);
     CU(cudaSetDevice(ctx->device));
     lb2_batch* b = new lb2_batch();
-    b->ctx = ctx; b->n = n;
+    b->ctx = ctx; b->n = n; b->slot = slot;
     struct Guard { lb2_batch* b; bool ok = false; ~Guard() { if (!ok) lb2_batch_destroy(b); } } guard{b};
 
     // ---- pass 1 (parallel): validate, final band, kernel variant, sizes
-    std::vector<PackedTask> pk((size_t)n);
+    // host scratch of this function is kept per calling thread (a run of equally sized chunks re-uses it: fresh vectors
+    // of tens of megabytes per chunk cost more in page faults than the classification itself)
+    thread_local std::vector<PackedTask> pk_tl;
+    thread_local std::vector<uint64_t> qoff_tl, zsz_tl;
+    thread_local std::vector<int16_t> cls_tl; thread_local std::vector<uint8_t> bin_tl; thread_local std::vector<int32_t> ctmpw_tl;
+    if (pk_tl.size() < (size_t)n + 1) {
+        pk_tl.resize((size_t)n + 1); qoff_tl.resize((size_t)n + 1); zsz_tl.resize((size_t)n + 1); cls_tl.resize((size_t)n + 1);
+        bin_tl.resize((size_t)n + 1); ctmpw_tl.resize((size_t)n + 1);
+    }
+    // plain pointers: the worker threads of parallel_for must see THIS thread's vectors
+    PackedTask* const pk = pk_tl.data(); uint64_t* const qoff = qoff_tl.data(); uint64_t* const zsz = zsz_tl.data();
+    int16_t* const cls = cls_tl.data(); uint8_t* const bin = bin_tl.data(); int32_t* const ctmpw = ctmpw_tl.data();
+    uint64_t raw_min = UINT64_MAX, raw_max = 0;
     std::vector<std::vector<int8_t>> mats;           // distinct matrices, each 64 entries (8x8, zero padded)
     std::mutex mats_mu;
     std::mutex err_mu; int64_t err_i = -1; std::string err_msg;
@@ -486,9 +518,20 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
     parallel_for(n, [&](int64_t lo_i, int64_t hi_i) {
         const int8_t* last_mat = nullptr; int last_m = 0, last_id = -1;     // per-thread cache: tasks share matrices
         char msg[200];
+        uint64_t my_min = UINT64_MAX, my_max = 0;
         for (int64_t i = lo_i; i < hi_i; ++i) {
             const lb2_task& t = tasks[i];
             int bad = classify_task(t, l_pac, pk[(size_t)i], msg, sizeof msg);
+            if (!bad && upool) {        // the range of the caller's pool this batch reads
+                const bool tp = (t.flags & LB2_FLAG_TARGET_PAC) != 0;
+                for (int q = 0; q < (tp ? 1 : 2) && !bad; ++q) {
+                    const int len = q ? t.tlen : t.qlen;
+                    if (!len) continue;
+                    const uint8_t* ptr = q ? t.target : t.query;
+                    if (ptr < upool || ptr + len > upool + upool_bytes) { snprintf(msg, sizeof msg, "%s lies outside the pool", q ? "target" : "query"); bad = 1; break; }
+                    my_min = std::min<uint64_t>(my_min, (uint64_t)(ptr - upool)); my_max = std::max<uint64_t>(my_max, (uint64_t)(ptr - upool) + len);
+                }
+            }
             if (!bad && (t.mat != last_mat || t.m != last_m)) {
                 last_id = matrix_id(t); last_mat = t.mat; last_m = t.m;
                 if (last_id < 0) { snprintf(msg, sizeof msg, "more than %d distinct scoring matrices in one batch", kMaxMats); bad = 1; }
@@ -500,9 +543,10 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
             }
             pk[(size_t)i].d.mat_id = (uint8_t)last_id;
         }
+        std::lock_guard<std::mutex> lk(err_mu);
+        raw_min = std::min(raw_min, my_min); raw_max = std::max(raw_max, my_max);
     });
     if (err_i >= 0) return fail("%s", err_msg.c_str());
-    std::vector<uint64_t> qoff((size_t)n);
     uint64_t pool = 0;
     for (int64_t i = 0; i < n; ++i) {
         qoff[(size_t)i] = pool;
@@ -510,21 +554,35 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
         if (!(tasks[i].flags & LB2_FLAG_TARGET_PAC)) pool += pool_bytes_target(tasks[i].tlen);
     }
     if (pool >> 37) return fail("sequence pool of %llu bytes is too large for one batch", (unsigned long long)pool);
-    if (alloc_host(b, pool)) return 1;
+    if (alloc_host(b, pool, upool == nullptr)) return 1;
     for (size_t k = 0; k < mats.size(); ++k)
         for (int r = 0; r < 8; ++r) memcpy(&b->h_mats[k * 8 + r], mats[k].data() + r * 8, 8);
+    uint64_t raw_lo = 0;
+    if (upool) {
+        // tasks in pool order give one tight range per chunk
+        uint64_t lo = raw_min, hi = raw_max;
+        if (lo > hi) { lo = 0; hi = 0; }
+        raw_lo = lo & ~uint64_t(15);
+        b->raw_src = upool + raw_lo; b->raw_bytes = (size_t)(hi - raw_lo);
+        if (b->raw_bytes >> 32) return fail("a pooled batch may span at most 4 GiB of its pool (this one spans %llu bytes): lower lb2_ctx_set_chunk_tasks or order the pool like the tasks", (unsigned long long)b->raw_bytes);
+        b->pool_bytes = b->raw_bytes + 64;           // what alloc_device sizes the device pool by
+    }
 
     // ---- pass 2: descriptors and sequences into the pinned staging (parallel)
     b->flags.resize((size_t)n);
-    std::vector<int16_t> cls((size_t)n); std::vector<uint8_t> bin((size_t)n);
-    std::vector<uint64_t> zsz((size_t)n); std::vector<int32_t> ctmpw((size_t)n);
     uint8_t* hp = b->h_pool;
     DTask* ht = b->h_tasks;
     const bool stream = pool > ((uint64_t)8 << 20);          // large staging: written once, read by the DMA engine only
     parallel_for(n, [&, hp, ht](int64_t a, int64_t e) {
         for (int64_t i = a; i < e; ++i) {
             PackedTask& p = pk[(size_t)i];
-            copy_sequences(tasks[i], p, hp, qoff[(size_t)i], false, stream);
+            if (upool) {
+                const lb2_task& t = tasks[i];
+                p.d.want_dir |= kRawOff;
+                p.d.q_off32 = t.qlen ? (uint32_t)((uint64_t)(t.query - upool) - raw_lo) : 0u;
+                if (!(t.flags & LB2_FLAG_TARGET_PAC)) p.d.t_off32 = t.tlen ? (uint32_t)((uint64_t)(t.target - upool) - raw_lo) : 0u;
+            } else
+                copy_sequences(tasks[i], p, hp, qoff[(size_t)i], false, stream);
             ht[i] = p.d;
             b->flags[(size_t)i] = p.flags; cls[(size_t)i] = p.cls; bin[(size_t)i] = p.bin;
             zsz[(size_t)i] = p.zsz; ctmpw[(size_t)i] = p.ctmpw;
@@ -533,12 +591,28 @@ extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, 
         if (stream) _mm_sfence();
 #endif
     });
-    if (layout_waves(b, cls.data(), bin.data(), zsz.data(), ctmpw.data())) return 1;
+    if (layout_waves(b, cls, bin, zsz, ctmpw)) return 1;
     if (alloc_device(b)) return 1;
     guard.ok = true;
     *out = b;
     return 0;
 }
+
+extern "C" int lb2_batch_create(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_batch** out) {
+    return batch_create_impl(ctx, n, tasks, nullptr, 0, out);
+}
+extern "C" int lb2_batch_create_pool(lb2_ctx* ctx, const uint8_t* pool, int64_t pool_bytes, int64_t n, const lb2_task* tasks, lb2_batch** out) {
+    if (!pool || pool_bytes < 0) return fail("lb2_batch_create_pool: NULL pool");
+    return batch_create_impl(ctx, n, tasks, pool, pool_bytes, out);
+}
+// page-locked host memory for pools handed to lb2_batch_create_pool / lb2_dp_run_pool (DMA reads it in place)
+extern "C" int lb2_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail("lb2_host_alloc: out is NULL");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return 0;
+}
+extern "C" void lb2_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // The batch producer's creator: tasks arrive classified and copied by the threads that parked them
 // (dp_pack.h: TaskBlob); this only concatenates the blobs into the pinned staging and lays out the launch.
@@ -601,12 +675,13 @@ extern "C" int lb2_batch_upload(lb2_batch* b) {
     CU(cudaSetDevice(c->device));
     const int64_t n1 = std::max<int64_t>(b->n, 1);
     cudaStream_t s = c->copy;
-    CU(cudaMemcpyAsync(b->d_pool, b->h_pool, b->pool_bytes, cudaMemcpyHostToDevice, s));
+    if (!b->raw_src) CU(cudaMemcpyAsync(b->d_pool, b->h_pool, b->pool_bytes, cudaMemcpyHostToDevice, s));
+    else if (b->raw_bytes) CU(cudaMemcpyAsync(b->d_pool, b->raw_src, b->raw_bytes, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(b->d_tasks, b->h_tasks, sizeof(DTask) * n1, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(b->d_order, b->h_order, sizeof(int32_t) * n1, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(b->d_mats, b->h_mats, sizeof(uint2) * kMaxMats * 8, cudaMemcpyHostToDevice, s));
     CU(cudaEventRecord(b->B.up_ev, s));
-    b->h2d_bytes = (int64_t)b->pool_bytes + (int64_t)(sizeof(DTask) + 4) * n1 + (int64_t)sizeof(uint2) * kMaxMats * 8;
+    b->h2d_bytes = (int64_t)(b->raw_src ? b->raw_bytes : b->pool_bytes) + (int64_t)(sizeof(DTask) + 4) * n1 + (int64_t)sizeof(uint2) * kMaxMats * 8;
     b->uploaded = true;
     return 0;
 }
@@ -617,7 +692,9 @@ static int compute_enqueue(lb2_batch* b) {
     if (!b->uploaded) return fail("lb2_batch_compute before lb2_batch_upload");
     lb2_ctx* c = b->ctx;
     CU(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
+    cudaStream_t s = b->slot ? c->stream1 : c->stream;
+    uint8_t* const d_z = b->slot ? c->d_z1 : c->d_z;
+    int32_t* const d_ctmp = b->slot ? c->d_ctmp1 : c->d_ctmp;
     CU(cudaStreamWaitEvent(s, b->B.up_ev, 0));
     CU(cudaMemsetAsync(b->d_cursor, 0, sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned int) * b->n_counters, s));
@@ -678,7 +755,7 @@ static int compute_enqueue(lb2_batch* b) {
             // global-window classes share one scratch: keep them all on aux[0] (in order)
             cudaStream_t ls_ = fan ? c->aux[var == kVarGmem ? 0 : nlaunch++ % lb2_ctx::kAux] : s;
             fill_table(kind, var)<<<grid, wpb * 32, smem, ls_>>>(b->d_tasks, b->d_order + wv.first + wv.cls_off[k], cnt,
-                                                             b->d_pool, c->d_pac, c->d_z, b->d_results, b->d_mats,
+                                                             b->d_pool, c->d_pac, d_z, b->d_results, b->d_mats,
                                                              b->d_counters + wi * kNumClass + k, 1 << ls, c->d_gwin);
             if (b->class_timing && !class_timing) { cudaEventRecord(t1, s); b->class_runs.push_back({k, cnt, t0, t1, 0.f}); }
             if (class_timing) {
@@ -705,7 +782,7 @@ static int compute_enqueue(lb2_batch* b) {
         CU(cudaEventRecord(one_wave ? b->ev[2] : b->wave_ev[wi * 3 + 1], s));
         if (wv.ctmp_words) {
             trace_kernel<<<(wv.count + 127) / 128, 128, 0, s>>>(b->d_tasks, b->d_order + wv.first, wv.count,
-                                                                c->d_z, b->d_results, c->d_ctmp, b->d_cdense,
+                                                                d_z, b->d_results, d_ctmp, b->d_cdense,
                                                                 b->d_cursor, b->dense_cap, b->d_err);
             CU(cudaGetLastError());
             ++b->launches;
@@ -893,17 +970,27 @@ extern "C" int lb2_batch_class_stats(const lb2_batch* b, lb2_class_stat* out, in
 // One-shot run.  Large batches are cut into chunks and pipelined: while the GPU
 // runs chunk k, the host packs chunk k+1 and its H2D copy goes out on the copy
 // stream; results and CIGAR words are appended in task order.
-extern "C" int lb2_dp_run(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_result* results,
-                          cigar32_t** cigar_pool, int64_t* cigar_pool_n) {
+static int dp_run_impl(lb2_ctx* ctx, const uint8_t* upool, int64_t upool_bytes, int64_t n, const lb2_task* tasks, lb2_result* results,
+                       cigar32_t** cigar_pool, int64_t* cigar_pool_n) {
     if (!ctx) return fail("ctx is NULL");
     static const int64_t chunk_env = env_int("LB2_CHUNK_TASKS", 0);
     const int64_t chunk_min = chunk_env > 0 ? chunk_env : ctx->chunk_tasks;
     int64_t K = chunk_min > 0 ? n / chunk_min : 1;
     K = std::max<int64_t>(1, std::min<int64_t>(K, 16));
+    // chunk boundaries: the first chunk is a quarter of the others, so the GPU starts early (the pipeline's fill time is
+    // the host work + H2D of chunk 0), and the last one half, so little is left to read back once the kernels are done
+    std::vector<double> wgt((size_t)K, 1.0);
+    if (K >= 2) wgt[0] = 0.25;
+    if (K >= 3) wgt[(size_t)K - 1] = 0.5;
+    double wsum = 0; for (double x : wgt) wsum += x;
+    std::vector<int64_t> cut((size_t)K + 1, 0);
+    { double acc = 0; for (int64_t k = 0; k < K; ++k) { acc += wgt[(size_t)k]; cut[(size_t)k + 1] = (int64_t)((double)n * acc / wsum); } }
+    cut[(size_t)K] = n;
     ctx->run_h2d = ctx->run_d2h = ctx->run_launches = 0;
     ctx->run_fill_ms = ctx->run_trace_ms = 0;
     cigar32_t* pool = nullptr; int64_t pool_n = 0, pool_cap = 0;
-    lb2_batch* prev = nullptr; int64_t prev_lo = 0;
+    struct InFlight { lb2_batch* b; int64_t lo; };
+    std::vector<InFlight> fly;          // enqueued, not yet drained (oldest first)
     int rc = 0;
     auto drain = [&](lb2_batch* b, int64_t lo) -> int {       // finish + download chunk starting at task `lo`
         if (compute_finish(b, nullptr)) return 1;
@@ -928,20 +1015,70 @@ extern "C" int lb2_dp_run(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_re
         pool_n += used;
         return 0;
     };
+    static const int trace = env_int("LB2_RUN_TRACE", 0), overlap = env_int("LB2_RUN_OVERLAP", 1);
+    // chunks kept enqueued while an older one is read back: with two, the GPU always has the next chunk's kernels queued
+    // when a chunk ends (chunk k and k+2 share a scratch set and a compute stream, so they are ordered by the stream)
+    const size_t ahead = overlap ? 2 : 1;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     for (int64_t k = 0; k < K && !rc; ++k) {
-        const int64_t lo = n * k / K, hi = n * (k + 1) / K;
+        const int64_t lo = cut[(size_t)k], hi = cut[(size_t)k + 1];
         lb2_batch* b = nullptr;
-        if (lb2_batch_create(ctx, hi - lo, tasks + lo, &b)) { rc = 1; break; }      // host packing
+        const double t0 = now();
+        if (batch_create_impl(ctx, hi - lo, tasks + lo, upool, upool_bytes, &b, overlap ? (int)(k & 1) : 0)) { rc = 1; break; }      // host packing
+        const double t1 = now();
         if (lb2_batch_upload(b) || compute_enqueue(b)) { lb2_batch_destroy(b); rc = 1; break; }
-        if (prev) { rc = drain(prev, prev_lo); lb2_batch_destroy(prev); prev = nullptr; }
-        if (rc) { lb2_batch_destroy(b); break; }
-        prev = b; prev_lo = lo;
+        const double t2 = now();
+        fly.push_back({b, lo});
+        if (fly.size() > ahead) { rc = drain(fly.front().b, fly.front().lo); lb2_batch_destroy(fly.front().b); fly.erase(fly.begin()); }
+        if (trace) fprintf(stderr, "[lb2 run] chunk %lld: %lld tasks; at %.1f ms create %.1f, upload+enqueue %.1f, drain of an earlier one %.1f ms\n",
+                           (long long)k, (long long)(hi - lo), (t0 - t_begin) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (now() - t2) * 1e3);
     }
-    if (prev) { if (!rc) rc = drain(prev, prev_lo); lb2_batch_destroy(prev); }
+    const double t_last = now();
+    for (auto& f : fly) { if (!rc) rc = drain(f.b, f.lo); lb2_batch_destroy(f.b); }
+    fly.clear();
+    if (trace) fprintf(stderr, "[lb2 run] last drains %.1f ms; total %.1f ms; kernels fill %.1f + trace %.1f ms (sums of per-chunk event times: chunks overlap)\n", (now() - t_last) * 1e3, (now() - t_begin) * 1e3, ctx->run_fill_ms, ctx->run_trace_ms);
     if (rc) { free(pool); return 1; }
     if (cigar_pool) *cigar_pool = pool ? pool : (cigar32_t*)malloc(sizeof(cigar32_t));
     if (cigar_pool_n) *cigar_pool_n = pool_n;
     return 0;
+}
+
+// Copies the sequences of `tasks` into `pool` in task order (query, then target; 16-byte granular) and re-points
+// the records at the copies: the layout under which every chunk of lb2_dp_run_pool uploads one tight range.
+extern "C" int lb2_pool_pack(int64_t n, lb2_task* tasks, uint8_t* pool, int64_t pool_bytes, int64_t* used) {
+    if (n < 0 || (n > 0 && (!tasks || !pool))) return fail("lb2_pool_pack: NULL argument");
+    std::vector<int64_t> off((size_t)n + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        if (tasks[i].qlen < 0 || tasks[i].tlen < 0) return fail("lb2_pool_pack: task %lld has a negative length", (long long)i);
+        const int64_t t = (tasks[i].flags & LB2_FLAG_TARGET_PAC) ? 0 : tasks[i].tlen;
+        off[(size_t)i + 1] = off[(size_t)i] + (((int64_t)tasks[i].qlen + t + 15) & ~(int64_t)15);
+    }
+    if (used) *used = off[(size_t)n];
+    if (off[(size_t)n] > pool_bytes) return fail("lb2_pool_pack: pool of %lld bytes, %lld needed", (long long)pool_bytes, (long long)off[(size_t)n]);
+    parallel_for(n, [&](int64_t a, int64_t e) {
+        for (int64_t i = a; i < e; ++i) {
+            lb2_task& t = tasks[i];
+            uint8_t* q = pool + off[(size_t)i];
+            if (t.qlen) memcpy(q, t.query, (size_t)t.qlen);
+            t.query = q;
+            if (!(t.flags & LB2_FLAG_TARGET_PAC)) {
+                if (t.tlen) memcpy(q + t.qlen, t.target, (size_t)t.tlen);
+                t.target = q + t.qlen;
+            }
+        }
+    });
+    return 0;
+}
+
+extern "C" int lb2_dp_run(lb2_ctx* ctx, int64_t n, const lb2_task* tasks, lb2_result* results,
+                          cigar32_t** cigar_pool, int64_t* cigar_pool_n) {
+    return dp_run_impl(ctx, nullptr, 0, n, tasks, results, cigar_pool, cigar_pool_n);
+}
+extern "C" int lb2_dp_run_pool(lb2_ctx* ctx, const uint8_t* pool, int64_t pool_bytes, int64_t n, const lb2_task* tasks,
+                               lb2_result* results, cigar32_t** cigar_pool, int64_t* cigar_pool_n) {
+    if (!pool || pool_bytes < 0) return fail("lb2_dp_run_pool: NULL pool");
+    return dp_run_impl(ctx, pool, pool_bytes, n, tasks, results, cigar_pool, cigar_pool_n);
 }
 
 extern "C" int lb2_ctx_last_run_stats(const lb2_ctx* ctx, int64_t* h2d, int64_t* d2h, int64_t* launches) {
@@ -1032,8 +1169,8 @@ int ctx_reserve(lb2_ctx* ctx, int64_t n_tasks, size_t pool_bytes, size_t z_bytes
     b->ctx = ctx; b->n = n_tasks;
     struct Guard { lb2_batch* b; ~Guard() { lb2_batch_destroy(b); } } guard{b};
     // take no parked set: this call is there to CREATE one
-    Buffers keep[2];
-    { std::lock_guard<std::mutex> lk(ctx->mu); for (int k = 0; k < 2; ++k) { keep[k] = ctx->parked[k]; ctx->parked[k] = Buffers(); } }
+    Buffers keep[lb2_ctx::kParked];
+    { std::lock_guard<std::mutex> lk(ctx->mu); for (int k = 0; k < lb2_ctx::kParked; ++k) { keep[k] = ctx->parked[k]; ctx->parked[k] = Buffers(); } }
     int rc = alloc_host(b, pool_bytes);
     if (!rc) {
         Wave wv; memset(&wv, 0, sizeof wv);
@@ -1048,7 +1185,7 @@ int ctx_reserve(lb2_ctx* ctx, int64_t n_tasks, size_t pool_bytes, size_t z_bytes
         if (cudaMallocHost(&b->B.h_cigar, cigar_words * sizeof(cigar32_t)) != cudaSuccess) rc = fail("ctx_reserve: pinned CIGAR buffer");
         else b->B.h_cigar_cap = cigar_words;
     }
-    { std::lock_guard<std::mutex> lk(ctx->mu); for (int k = 0; k < 2; ++k) if (keep[k].valid) ctx->parked[k] = keep[k]; }
+    { std::lock_guard<std::mutex> lk(ctx->mu); for (int k = 0; k < lb2_ctx::kParked; ++k) if (keep[k].valid) ctx->parked[k] = keep[k]; }
     return rc;          // the guard parks the new set in a free place (or releases it when both are taken)
 }
 int batch_wait_blocking(lb2_batch* b) {

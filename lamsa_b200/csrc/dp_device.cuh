@@ -16,19 +16,20 @@ constexpr int kMaxMats = 16;             // distinct scoring matrices per batch
 constexpr int kKindGlobal = 0;
 constexpr int kKindExtend = 1;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kWantDir = 1, kTargetPac = 2, kTargetRev = 4;    // bits of DTask::want_dir
+constexpr int kWantDir = 1, kTargetPac = 2, kTargetRev = 4, kRawOff = 8;    // bits of DTask::want_dir
 
 // One DP task as the kernels see it.  Sequences live in one pooled byte array
 // (`pool`), every sequence starting on a 32-byte boundary and padded so that a
 // whole column chunk can always be fetched with one aligned vector load.
 struct __align__(16) DTask {
-    uint32_t q_off32, t_off32;   // offsets into pool, in 32-byte units (t_off32: pac coordinate when kTargetPac)
+    uint32_t q_off32, t_off32;   // offsets into pool, in 32-byte units -- in BYTES with kRawOff (pooled batches: the caller's bytes as they lie, any
+                                 // alignment, no padding: what follows a sequence is readable but arbitrary) (t_off32: pac coordinate when kTargetPac)
     int32_t qlen, tlen;
     int32_t w;                   // FINAL band: after src/ksw.c:549 resp. :696-704
     int32_t h0;
     int32_t o_del, e_del, o_ins, e_ins;
     int32_t end_bonus, zdrop;
-    uint8_t kind, want_dir /* bit0 directions, kTargetPac, kTargetRev */, mat_id, cshift;   // cshift = log2(G), G = columns per lane per tile
+    uint8_t kind, want_dir /* bit0 directions, kTargetPac, kTargetRev, kRawOff */, mat_id, cshift;   // cshift = log2(G), G = columns per lane per tile
     int32_t row_chunks;          // tiles (32*G columns) of direction nibbles stored per row
     uint64_t z_off;              // byte offset of this task's direction scratch
     uint64_t ctmp_end;           // word offset one past this task's CIGAR scratch
@@ -80,10 +81,16 @@ __host__ __device__ constexpr size_t warp_smem_bytes(int S) { return (size_t)S *
 // ... of the packed-int16 kernels (h16, e16, one selector per pair, + 8 staged matrix rows)
 __host__ __device__ constexpr size_t warp_smem_bytes16(int S) { return (size_t)S * 5 + 64; }
 
+// start of the task's query codes; two adjacent codes (alignment-free: pooled batches keep the caller's layout)
+__device__ __forceinline__ const uint8_t* query_ptr(const DTask& T, const uint8_t* pool) {
+    return pool + (size_t)T.q_off32 * ((T.want_dir & kRawOff) ? 1 : 32);
+}
+__device__ __forceinline__ uint32_t ld_pair(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
 __device__ __forceinline__ TargetSrc make_target(const DTask& T, const uint8_t* pool, const uint8_t* pac) {
     TargetSrc t;
     const bool p = (T.want_dir & kTargetPac) != 0;
-    t.bytes = pool + (p ? 0 : (size_t)T.t_off32 * 32);
+    t.bytes = pool + (p ? 0 : (size_t)T.t_off32 * ((T.want_dir & kRawOff) ? 1 : 32));
     t.pac = p ? pac : nullptr;
     t.coor = T.t_off32;
     t.tlen = T.tlen; t.tpad = (T.tlen + 31) & ~31; t.rev = (T.want_dir & kTargetRev) ? 1 : 0;

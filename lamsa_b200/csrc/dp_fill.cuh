@@ -99,7 +99,7 @@ __device__ void fill_task(const DTask& T, const uint8_t* __restrict__ pool, cons
     const int qlen = T.qlen, tlen = T.tlen, w = T.w, h0 = T.h0;
     const int o_del = T.o_del, e_del = T.e_del, o_ins = T.o_ins, e_ins = T.e_ins;
     const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
-    const uint8_t* __restrict__ qseq = pool + (size_t)T.q_off32 * 32;
+    const uint8_t* __restrict__ qseq = query_ptr(T, pool);
     const TargetSrc tsrc = make_target(T, pool, pac);
     const bool want = (T.want_dir & kWantDir) != 0;
     const int RT = T.row_chunks;                        // tiles per stored row

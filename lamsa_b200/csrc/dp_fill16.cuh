@@ -142,7 +142,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
     const uint32_t one = (uint32_t)S >> (31 - __clz(S));
     const int qlen = T.qlen, tlen = T.tlen, w = T.w, h0 = T.h0;
     const int o_del = T.o_del, e_del = T.e_del, o_ins = T.o_ins, e_ins = T.e_ins;
-    const uint8_t* __restrict__ qseq = pool + (size_t)T.q_off32 * 32;
+    const uint8_t* __restrict__ qseq = query_ptr(T, pool);
     const TargetSrc tsrc = make_target(T, pool, pac);
     const bool want = (T.want_dir & kWantDir) != 0;
     int2* __restrict__ rowmeta = reinterpret_cast<int2*>(zbase + T.z_off);
@@ -177,13 +177,13 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
         const int want_q = w + 66 < qpad ? w + 66 : qpad;
         while (q_hi < want_q) {
             if (lane < 16) {
-                const uint32_t cc = *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * lane);
+                const uint32_t cc = ld_pair(qseq + q_hi + 2 * lane);
                 qb[((q_hi >> 1) + lane) & SMQ] = (uint16_t)sel_for_pair(cc & 0xffu, cc >> 8);
             }
             q_hi += 32;
         }
     }
-    uint32_t qpre = (q_hi < qpad && lane < 16) ? *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * lane) : 0u;
+    uint32_t qpre = (q_hi < qpad && lane < 16) ? ld_pair(qseq + q_hi + 2 * lane) : 0u;
     uint32_t tcur = 0u;
     uint32_t tnext = tsrc.at(lane);
 
@@ -198,7 +198,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
             if (i && q_hi < qpad) {
                 if (lane < 16) qb[((q_hi >> 1) + lane) & SMQ] = (uint16_t)sel_for_pair(qpre & 0xffu, qpre >> 8);
                 q_hi += 32;
-                qpre = (q_hi < qpad && lane < 16) ? *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * lane) : 0u;
+                qpre = (q_hi < qpad && lane < 16) ? ld_pair(qseq + q_hi + 2 * lane) : 0u;
             }
         }
         const int tb = __shfl_sync(kFull, (int)tcur, i & 31) & 7;

@@ -95,7 +95,7 @@ __device__ void fill_bundle16_dyn(const DTask* __restrict__ tasks, const int32_t
                 const DTask T = tasks[idx];
                 qlen = T.qlen; tlen = T.tlen; w = T.w; h0 = T.h0;
                 o_del = T.o_del; e_del = T.e_del; o_ins = T.o_ins; e_ins = T.e_ins; zdrop = T.zdrop; end_bonus = T.end_bonus;
-                qseq = pool + (size_t)T.q_off32 * 32;
+                qseq = query_ptr(T, pool);
                 tsrc = make_target(T, pool, pac);
                 want = got && (T.want_dir & kWantDir) != 0;
                 rowmeta = reinterpret_cast<int2*>(zbase + T.z_off);
@@ -124,13 +124,13 @@ __device__ void fill_bundle16_dyn(const DTask* __restrict__ tasks, const int32_t
                     const int want_q = w + 66 < qpad ? w + 66 : qpad;
                     while (q_hi < want_q) {
                         if (gl < QR / 2) {
-                            const uint32_t cc = *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * gl);
+                            const uint32_t cc = ld_pair(qseq + q_hi + 2 * gl);
                             qb[((q_hi >> 1) + gl) & SMQ] = (uint16_t)sel_for_pair(cc & 0xffu, cc >> 8);
                         }
                         q_hi += QR;
                     }
                 }
-                qpre = (q_hi < qpad && gl < QR / 2) ? *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * gl) : 0u;
+                qpre = (q_hi < qpad && gl < QR / 2) ? ld_pair(qseq + q_hi + 2 * gl) : 0u;
                 tcur = 0u;
                 tnext = tsrc.at(gl);
                 beg = 0; end = qlen;
@@ -153,7 +153,7 @@ __device__ void fill_bundle16_dyn(const DTask* __restrict__ tasks, const int32_t
         if ((i & (QR - 1)) == 0 && i && q_hi < qpad) {    // next QR selectors (pad region is readable)
             if (gl < QR / 2) qb[((q_hi >> 1) + gl) & SMQ] = (uint16_t)sel_for_pair(qpre & 0xffu, qpre >> 8);
             q_hi += QR;
-            qpre = (q_hi < qpad && gl < QR / 2) ? *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * gl) : 0u;
+            qpre = (q_hi < qpad && gl < QR / 2) ? ld_pair(qseq + q_hi + 2 * gl) : 0u;
         }
         const int tb = __shfl_sync(kFull, (int)tcur, i & (L - 1), L) & 7;
         const int send = i + w + 1 < qlen ? i + w + 1 : qlen;

@@ -48,7 +48,7 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
     uint2* __restrict__ mrw = reinterpret_cast<uint2*>(qb + (S >> 1));
     const int qlen = T.qlen, tlen = T.tlen, w = T.w, h0 = T.h0;
     const int o_del = T.o_del, e_del = T.e_del, o_ins = T.o_ins, e_ins = T.e_ins;
-    const uint8_t* __restrict__ qseq = pool + (size_t)T.q_off32 * 32;
+    const uint8_t* __restrict__ qseq = query_ptr(T, pool);
     const TargetSrc tsrc = make_target(T, pool, pac);
     const bool want = have && (T.want_dir & kWantDir) != 0;
     int2* __restrict__ rowmeta = reinterpret_cast<int2*>(zbase + T.z_off);
@@ -81,13 +81,13 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
         const int want_q = w + 66 < qpad ? w + 66 : qpad;
         while (q_hi < want_q) {
             if (gl < QR / 2) {
-                const uint32_t cc = *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * gl);
+                const uint32_t cc = ld_pair(qseq + q_hi + 2 * gl);
                 qb[((q_hi >> 1) + gl) & SMQ] = (uint16_t)sel_for_pair(cc & 0xffu, cc >> 8);
             }
             q_hi += QR;
         }
     }
-    uint32_t qpre = (q_hi < qpad && gl < QR / 2) ? *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * gl) : 0u;
+    uint32_t qpre = (q_hi < qpad && gl < QR / 2) ? ld_pair(qseq + q_hi + 2 * gl) : 0u;
     uint32_t tcur = 0u;
     uint32_t tnext = tsrc.at(gl);
 
@@ -106,7 +106,7 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
         if ((i & (QR - 1)) == 0 && i && q_hi < qpad) {    // next QR selectors (pad region is readable)
             if (gl < QR / 2) qb[((q_hi >> 1) + gl) & SMQ] = (uint16_t)sel_for_pair(qpre & 0xffu, qpre >> 8);
             q_hi += QR;
-            qpre = (q_hi < qpad && gl < QR / 2) ? *reinterpret_cast<const uint16_t*>(qseq + q_hi + 2 * gl) : 0u;
+            qpre = (q_hi < qpad && gl < QR / 2) ? ld_pair(qseq + q_hi + 2 * gl) : 0u;
         }
         const int tb = __shfl_sync(kFull, (int)tcur, i & (L - 1), L) & 7;
         const int send = i + w + 1 < qlen ? i + w + 1 : qlen;

@@ -76,6 +76,22 @@ class Context:
         weakref.finalize(cig, self.lib.lb2_free, pool.value)
         return res, cig
 
+    def run_pool(self, tasks, pool):
+        """lb2_dp_run_pool: as run(), with every sequence of `tasks` inside the uint8 array `pool` (see pinned_pool /
+        workload.pool_tasks): no host copy of the sequences, the pool range is uploaded as it lies."""
+        tasks = np.ascontiguousarray(tasks, dtype=TASK_DTYPE)
+        res = np.zeros(len(tasks), dtype=RESULT_DTYPE)
+        out, pn = C.c_void_p(), C.c_int64()
+        if self.lib.lb2_dp_run_pool(self.handle, pool.ctypes.data, pool.nbytes, len(tasks), tasks.ctypes.data,
+                                    res.ctypes.data, C.byref(out), C.byref(pn)):
+            raise _err(self.lib, "lb2_dp_run_pool")
+        if not pn.value:
+            self.lib.lb2_free(out)
+            return res, np.zeros(0, dtype=np.int32)
+        cig = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_int32)), shape=(pn.value,))
+        weakref.finalize(cig, self.lib.lb2_free, out.value)
+        return res, cig
+
     def aux_counts(self, cigars, reads, ref_pacs):
         """lb2_aux_run (include/lamsa_b200.h section 5): per record (CIGAR words, read codes, pac coordinate) ->
         array of (n_match, n_mismatch, n_ins_open, n_ins_ext, n_del_open, n_del_ext, read_used, ref_used)."""
@@ -103,6 +119,11 @@ class Context:
         self.lib.lb2_ctx_last_run_stats(self.handle, C.byref(a), C.byref(b), C.byref(c))
         return {"h2d_bytes": a.value, "d2h_bytes": b.value, "launches": c.value}
 
+    def last_run_kernel_ms(self):
+        f, t = C.c_float(), C.c_float()
+        self.lib.lb2_ctx_last_run_kernel_ms(self.handle, C.byref(f), C.byref(t))
+        return {"fill_ms": f.value, "trace_ms": t.value}
+
     def close(self):
         if self.handle:
             self.lib.lb2_ctx_destroy(self.handle)
@@ -115,17 +136,32 @@ class Context:
             pass
 
 
-class Batch:
-    """Staged batch (lb2_batch): create=pack, upload=H2D, compute=kernels, download=D2H."""
+def pinned_pool(nbytes):
+    """uint8 array over page-locked host memory (lb2_host_alloc); freed when the array goes away."""
+    lib = load_library()
+    p = C.c_void_p()
+    if lib.lb2_host_alloc(int(nbytes), C.byref(p)):
+        raise _err(lib, "lb2_host_alloc")
+    arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(int(nbytes), 1),))
+    weakref.finalize(arr, lib.lb2_host_free, p.value)
+    return arr[:int(nbytes)] if nbytes else arr[:0]
 
-    def __init__(self, ctx, tasks, keep=()):
+
+class Batch:
+    """Staged batch (lb2_batch): create=pack, upload=H2D, compute=kernels, download=D2H.  With `pool` (the uint8
+    array holding every sequence of `tasks`): lb2_batch_create_pool."""
+
+    def __init__(self, ctx, tasks, keep=(), pool=None):
         self.ctx, self.lib = ctx, ctx.lib
         tasks = np.ascontiguousarray(tasks, dtype=TASK_DTYPE)
         self.n = len(tasks)
-        self._keep = (tasks, keep)
+        self._keep = (tasks, keep, pool)
         h = C.c_void_p()
-        if self.lib.lb2_batch_create(ctx.handle, self.n, tasks.ctypes.data, C.byref(h)):
-            raise _err(self.lib, "lb2_batch_create")
+        if pool is None:
+            if self.lib.lb2_batch_create(ctx.handle, self.n, tasks.ctypes.data, C.byref(h)):
+                raise _err(self.lib, "lb2_batch_create")
+        elif self.lib.lb2_batch_create_pool(ctx.handle, pool.ctypes.data, pool.nbytes, self.n, tasks.ctypes.data, C.byref(h)):
+            raise _err(self.lib, "lb2_batch_create_pool")
         self.handle = h
 
     def upload(self):

@@ -84,6 +84,23 @@ def gen_microbench(n, seed=20260101, qmin=50, qmax=1000, wmin=10, wmax=200, max_
     return np.concatenate(parts), keep
 
 
+def pool_tasks(tasks, keep=(), alloc=None):
+    """Copy every sequence of `tasks` into ONE pool, in task order, and re-point the records at it (lb2_pool_pack)
+    -> (tasks', pool).  `alloc(nbytes)` returns the pool's uint8 array (lamsa_b200.pinned_pool for page-locked
+    memory; default a plain numpy array).  Matrices keep their own buffers."""
+    import ctypes as C
+    from ._lib import load_library
+    lib = load_library()
+    t = np.ascontiguousarray(tasks, dtype=TASK_DTYPE).copy()
+    pac = (t["flags"] & 2) != 0
+    total = int(((t["qlen"].astype(np.int64) + np.where(pac, 0, t["tlen"]).astype(np.int64) + 15) & ~15).sum()) + 64
+    pool = alloc(total) if alloc is not None else np.zeros(total, dtype=np.uint8)
+    used = C.c_int64()
+    if lib.lb2_pool_pack(len(t), t.ctypes.data, pool.ctypes.data, pool.nbytes, C.byref(used)):
+        raise RuntimeError("lb2_pool_pack: " + lib.lb2_last_error().decode())
+    return t, pool
+
+
 def gen_edge_cases(seed=7):
     """Small adversarial tasks: empty sequences, band beyond the length difference,
     all-N reads, dying first rows, z-drop, end-bonus ties, narrow and huge bands."""

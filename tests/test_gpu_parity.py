@@ -45,6 +45,27 @@ def test_gpu_matches_oracle_random(ctx, seed, n, kw):
     assert not bad, "\n".join(bad)
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_gpu_pooled_run_matches_oracle(ctx, pinned):
+    """lb2_dp_run_pool: sequences uploaded as they lie in one host pool (odd alignments, a short chunk size so that
+    several chunks with their own pool ranges are pipelined) and re-laid out on the device."""
+    tasks, keep = workload.gen_microbench(9000, seed=206, qmin=1, qmax=300)
+    edge, ekeep = workload.gen_edge_cases(seed=9)
+    tasks = np.concatenate((tasks, edge))
+    ptasks, pool = workload.pool_tasks(tasks, alloc=lamsa_b200.pinned_pool if pinned else None)
+    c2 = lamsa_b200.Context(0)
+    c2.set_chunk_tasks(2000)
+    res, cig = c2.run_pool(ptasks, pool)
+    st = c2.last_run_stats()
+    c2.close()
+    assert st["h2d_bytes"] < 1.2 * pool.nbytes + 200 * len(tasks)
+    ores, ocig, _ = _oracle.oracle_run(tasks)
+    bad = _oracle.compare(tasks, res, cig, ores, ocig, what="gpu-pooled-vs-oracle", check_cells=True)
+    assert not bad, "\n".join(bad)
+    with pytest.raises(RuntimeError, match="outside the pool"):
+        ctx.run_pool(tasks[:50], pool)          # the original pointers are not inside the pool
+
+
 def test_gpu_multi_wave_equals_single_wave(ctx):
     tasks, keep = workload.gen_microbench(3000, seed=205, qmax=500)
     a = run_gpu(ctx, tasks, keep)

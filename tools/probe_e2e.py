@@ -21,3 +21,10 @@ for it in range(3):
 for it in range(3):
     t0 = time.perf_counter(); res, cig = ctx.run(tasks, keep); dt = time.perf_counter() - t0
     print(f"lb2_dp_run (pipelined) iter {it}: {dt:.3f} s -> {int(res['cells'].sum())/dt/1e9:.1f} GCUPS e2e; {ctx.last_run_stats()}", flush=True)
+
+ptasks, pool = workload.pool_tasks(tasks, keep, lamsa_b200.pinned_pool)
+for chunk in (100000, 131072, 200000):
+    ctx.set_chunk_tasks(chunk)
+    for it in range(3):
+        t0 = time.perf_counter(); res, cig = ctx.run_pool(ptasks, pool); dt = time.perf_counter() - t0
+        print(f"lb2_dp_run_pool chunk {chunk} iter {it}: {dt:.3f} s -> {int(res['cells'].sum())/dt/1e9:.1f} GCUPS e2e; {ctx.last_run_stats()} {ctx.last_run_kernel_ms()}", flush=True)
