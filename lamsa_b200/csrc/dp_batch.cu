@@ -241,6 +241,7 @@ extern "C" int lb2_ctx_set_scratch_limit(lb2_ctx* c, uint64_t bytes) {
 struct Wave {
     int cls_off[kNumClass + 1];      // ranges inside `order`, by class
     int first, count;                // range inside `order`
+    int long_count;                  // tasks walked by trace_long_kernel: order[n + first .. + long_count)
     uint64_t z_bytes, ctmp_words;
 };
 
@@ -342,7 +343,7 @@ static int alloc_host(lb2_batch* b, size_t pool_bytes, bool host_pool = true) {
         B.h_tasks = nullptr; B.h_results = nullptr; B.h_order = nullptr; B.h_n_cap = 0;
         CU(cudaMallocHost(&B.h_tasks, sizeof(DTask) * cap));
         CU(cudaMallocHost(&B.h_results, sizeof(DResult) * cap));
-        CU(cudaMallocHost(&B.h_order, sizeof(int32_t) * cap));
+        CU(cudaMallocHost(&B.h_order, sizeof(int32_t) * cap * 2));       // second half: the tasks of trace_long_kernel, per wave
         B.h_n_cap = cap;
     }
     if (!B.h_mats) CU(cudaMallocHost(&B.h_mats, sizeof(uint2) * kMaxMats * 8));
@@ -400,6 +401,11 @@ static int layout_waves(lb2_batch* b, const int16_t* cls, const uint8_t* bin, co
         }
         int32_t* ord = b->h_order + wv.first;
         for (int k = 0; k < wv.count; ++k) ord[hist[(size_t)keys[(size_t)k]]++] = wv.first + k;
+        wv.long_count = 0;
+        for (int k = 0; k < wv.count; ++k) {
+            const DTask& d = b->h_tasks[wv.first + k];
+            if ((d.want_dir & kWantDir) && d.qlen + d.tlen >= kLongTrace) b->h_order[n + wv.first + wv.long_count++] = wv.first + k;
+        }
         uint64_t z = 0, cw = 0;
         for (int k = 0; k < wv.count; ++k) {          // scratch offsets follow the original order
             const int64_t a = wv.first + k;
@@ -428,7 +434,7 @@ static int alloc_device(lb2_batch* b) {
         B.d_tasks = nullptr; B.d_results = nullptr; B.d_order = nullptr; B.d_n_cap = 0;
         CU(cudaMalloc(&B.d_tasks, sizeof(DTask) * cap));
         CU(cudaMalloc(&B.d_results, sizeof(DResult) * cap));
-        CU(cudaMalloc(&B.d_order, sizeof(int32_t) * cap));
+        CU(cudaMalloc(&B.d_order, sizeof(int32_t) * cap * 2));
         B.d_n_cap = cap;
     }
     if (!B.d_mats) CU(cudaMalloc(&B.d_mats, sizeof(uint2) * kMaxMats * 8));
@@ -679,6 +685,11 @@ extern "C" int lb2_batch_upload(lb2_batch* b) {
     else if (b->raw_bytes) CU(cudaMemcpyAsync(b->d_pool, b->raw_src, b->raw_bytes, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(b->d_tasks, b->h_tasks, sizeof(DTask) * n1, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(b->d_order, b->h_order, sizeof(int32_t) * n1, cudaMemcpyHostToDevice, s));
+    {
+        int64_t any_long = 0;
+        for (const auto& wv : b->waves) any_long += wv.long_count;
+        if (any_long) CU(cudaMemcpyAsync(b->d_order + b->n, b->h_order + b->n, sizeof(int32_t) * n1, cudaMemcpyHostToDevice, s));
+    }
     CU(cudaMemcpyAsync(b->d_mats, b->h_mats, sizeof(uint2) * kMaxMats * 8, cudaMemcpyHostToDevice, s));
     CU(cudaEventRecord(b->B.up_ev, s));
     b->h2d_bytes = (int64_t)(b->raw_src ? b->raw_bytes : b->pool_bytes) + (int64_t)(sizeof(DTask) + 4) * n1 + (int64_t)sizeof(uint2) * kMaxMats * 8;
@@ -781,11 +792,22 @@ static int compute_enqueue(lb2_batch* b) {
         }
         CU(cudaEventRecord(one_wave ? b->ev[2] : b->wave_ev[wi * 3 + 1], s));
         if (wv.ctmp_words) {
-            trace_kernel<<<(wv.count + 127) / 128, 128, 0, s>>>(b->d_tasks, b->d_order + wv.first, wv.count,
-                                                                d_z, b->d_results, d_ctmp, b->d_cdense,
-                                                                b->d_cursor, b->dense_cap, b->d_err);
-            CU(cudaGetLastError());
-            ++b->launches;
+            static const int long_trace = env_int("LB2_LONG_TRACE", 1);
+            const int nlong = long_trace ? wv.long_count : 0;
+            if (nlong) {          // the long walks first: they are what the wave waits for
+                trace_long_kernel<<<(nlong + kTraceWarps - 1) / kTraceWarps, kTraceWarps * 32, 0, s>>>(
+                    b->d_tasks, b->d_order + b->n + wv.first, nlong, d_z, b->d_results, d_ctmp, b->d_cdense,
+                    b->d_cursor, b->dense_cap, b->d_err);
+                CU(cudaGetLastError());
+                ++b->launches;
+            }
+            if (nlong < wv.count) {
+                trace_kernel<<<(wv.count + 127) / 128, 128, 0, s>>>(b->d_tasks, b->d_order + wv.first, wv.count,
+                                                                    d_z, b->d_results, d_ctmp, b->d_cdense,
+                                                                    b->d_cursor, b->dense_cap, b->d_err, nlong ? 1 : 0);
+                CU(cudaGetLastError());
+                ++b->launches;
+            }
         }
         if (!one_wave) CU(cudaEventRecord(b->wave_ev[wi * 3 + 2], s));
     }

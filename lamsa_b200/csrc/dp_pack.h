@@ -106,8 +106,12 @@ inline int pick_variant(const lb2_task& t, int w, long ncol, int logS) {
     // (1 M-task C2: 437 vs 423 GCUPS, tools/kernel_probe.py)
     static const int sub_l = env_int("LB2_SUBWARP", 8), sub_max_ext = env_int("LB2_SUBWARP_MAX_EXT", 410),
                      sub_max_glb = env_int("LB2_SUBWARP_MAX_GLB", 200);
+    // long tasks: what matters is the time of ONE row on ONE warp (a batch lasts as long as its longest task), not lanes kept
+    // busy -- one task per warp (no group bookkeeping in the row loop) instead of the lane groups
+    static const int long_rows = env_int("LB2_LONG_ROWS", 1200), long_var = env_int("LB2_LONG_VAR", 3);
     if (use16 && fits_int16(t, w)) {
         const bool wide = ncol >= (t.kind == LB2_KIND_EXTEND ? np4_min_ext : np4_min);
+        if (t.tlen >= long_rows && ncol < 2000 && long_var >= 0) return ncol >= 1000 ? 4 : long_var;
         const int sub_max = t.kind == LB2_KIND_EXTEND ? sub_max_ext : sub_max_glb;
         // wide bands in 8-lane groups with 8 columns per lane (64-column tiles): LB2_SUB_NP4_MIN_EXT / _GLB
         static const int sub4_ext = env_int("LB2_SUB_NP4_MIN_EXT", 160), sub4_glb = env_int("LB2_SUB_NP4_MIN_GLB", 100);

@@ -9,15 +9,19 @@
 
 namespace lb2 {
 
+// tasks whose path is at least this long (qlen + tlen) are walked by a whole warp (trace_long_kernel)
+constexpr int kLongTrace = 1536;
+
 struct CigarWriter {
     int32_t* top;      // next free word is top[-1]; words are written downwards
     int32_t* floor;    // lowest usable address
     int n;
     int op, len;
     bool overflow;
+    bool writer = true;    // warp-uniform walks: every lane keeps the state, one lane stores
     __device__ void flush() {
         if (len > 0) {
-            if (top > floor) { *--top = (int32_t)((uint32_t)len << 4 | (uint32_t)op); ++n; }
+            if (top > floor) { --top; if (writer) *top = (int32_t)((uint32_t)len << 4 | (uint32_t)op); ++n; }
             else overflow = true;
         }
     }
@@ -32,13 +36,14 @@ trace_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order,
              const uint8_t* __restrict__ zbase, DResult* __restrict__ results,
              int32_t* __restrict__ ctmp, int32_t* __restrict__ cdense,
              unsigned long long* __restrict__ cursor, unsigned long long dense_cap,
-             int* __restrict__ err)
+             int* __restrict__ err, int skip_long)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int idx = order[t];
     const DTask T = tasks[idx];
     if (!(T.want_dir & kWantDir)) return;
+    if (skip_long && T.qlen + T.tlen >= kLongTrace) return;       // trace_long_kernel's
     DResult* R = results + idx;
     int i = R->ti, k = R->tk;
     const int w = T.w, G = 1 << T.cshift, gs = T.cshift;
@@ -98,6 +103,104 @@ trace_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ order,
     for (int a = 0; a < W.n; ++a) cdense[off + a] = W.top[a];
     R->n_cigar = W.n;
     R->cigar_off = (long long)off;
+}
+
+// The same walk for LONG tasks, one warp per task.  A single thread pays one dependent L2/HBM access per row (the row's
+// band, then the cell's nibble: about 0.6 us per row, 3 ms for a 5 000-row extension, and a batch lasts as long as its
+// longest task).  Here the warp stages sixteen rows at a time -- lane pair (2l, 2l+1) loads row i-l's band and the two
+// 16-byte pieces of its direction nibbles that end at the path's current column -- into shared memory and then walks
+// them there, every lane in step (lane 0 stores the CIGAR words).  A path that leaves the staged window (a long
+// insertion run) simply stages again from where it stands.
+constexpr int kTraceRows = 16;
+constexpr int kTraceWarps = 4;
+
+__global__ void __launch_bounds__(kTraceWarps * 32)
+trace_long_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ list, int nlist,
+                  const uint8_t* __restrict__ zbase, DResult* __restrict__ results,
+                  int32_t* __restrict__ ctmp, int32_t* __restrict__ cdense,
+                  unsigned long long* __restrict__ cursor, unsigned long long dense_cap,
+                  int* __restrict__ err)
+{
+    __shared__ __align__(16) uint4 sdir[kTraceWarps][kTraceRows][2];
+    __shared__ int4 smeta[kTraceWarps][kTraceRows];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int t = blockIdx.x * kTraceWarps + wid;
+    if (t >= nlist) return;
+    const int idx = list[t];
+    const DTask T = tasks[idx];
+    DResult* R = results + idx;
+    int i = R->ti, k = R->tk;
+    const int w = T.w, G = 1 << T.cshift;
+    const bool ext = T.kind == kKindExtend;
+    const int2* __restrict__ rowmeta = reinterpret_cast<const int2*>(zbase + T.z_off);
+    const uint8_t* __restrict__ zdir = zbase + T.z_off + (ext ? ext_meta_bytes(T.tlen) : 0);
+    const int lb = G >= 2 ? G / 2 : 1;
+    const size_t zrow_bytes = (size_t)T.row_chunks * 32 * lb;
+    const int cs = G >= 2 ? 5 : 4;                 // log2(cells per 16-byte piece): a nibble per cell, a byte when G == 1
+
+    CigarWriter W;
+    W.top = ctmp + T.ctmp_end; W.floor = W.top - T.ctmp_cap;
+    W.n = 0; W.op = -1; W.len = 0; W.overflow = false; W.writer = lane == 0;
+
+    int which = 0;
+    while (i >= 0 && k >= 0) {
+        {   // ---- stage rows i .. i-15
+            const int l = lane >> 1, h = lane & 1;
+            const int r = i - l;
+            int rb = 0, re = 0, base = 0, c = 0;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (r >= 0) {
+                if (ext) { const int2 mm = rowmeta[r]; rb = mm.x; re = mm.y; }
+                else { rb = r > w ? r - w : 0; re = r + w + 1 < T.qlen ? r + w + 1 : T.qlen; }
+                base = rb & ~(G - 1);
+                const int relk = k - base;             // the path's column in this row is never right of k
+                c = relk >= 0 ? relk >> cs : 0;
+                const int piece = c - 1 + h;
+                if (piece >= 0 && (size_t)piece * 16 < zrow_bytes)
+                    v = *reinterpret_cast<const uint4*>(zdir + (size_t)r * zrow_bytes + (size_t)piece * 16);
+            }
+            sdir[wid][l][h] = v;
+            if (h == 0) smeta[wid][l] = make_int4(rb, re, base, c);
+        }
+        __syncwarp();
+        const int i0 = i;
+        while (i >= 0 && k >= 0 && i > i0 - kTraceRows) {
+            const int4 mt = smeta[wid][i0 - i];
+            if (k >= mt.x && k < mt.y) {
+                const int rel = k - mt.z;
+                const int piece = (rel >> cs) - (mt.w - 1);
+                if (piece < 0 || piece > 1) break;     // left of the staged window: stage again from (i, k)
+                const uint8_t* bytes = reinterpret_cast<const uint8_t*>(&sdir[wid][i0 - i][0]);
+                uint32_t nib;
+                if (G == 1) nib = bytes[piece * 16 + (rel & 15)] & 15u;
+                else nib = (bytes[piece * 16 + ((rel & 31) >> 1)] >> (4 * (rel & 1))) & 15u;
+                if (T.dir_fmt == 1) {
+                    const uint32_t b0 = nib & 1u, b1 = (nib >> 1) & 1u;
+                    const uint32_t pe = ext ? b0 : b0 ^ 1u, pf = ext ? b1 : b1 ^ 1u;
+                    nib = (pf ? 2u : pe) | ((~nib) & 12u);
+                }
+                if (which == 0) which = nib & 3;
+                else if (which == 1) which = (nib >> 2) & 1;
+                else if (which == 2) which = (nib & 8) ? 2 : 0;
+                else which = 0;
+            } else which = 3;
+            if (which == 0) { W.push(0, 1); --i; --k; }
+            else if (which == 1) { W.push(2, 1); --i; }
+            else { W.push(1, 1); --k; }
+        }
+        __syncwarp();
+    }
+    if (i >= 0) W.push(2, i + 1);
+    if (k >= 0) W.push(1, k + 1);
+    W.flush();
+    if (W.overflow) { if (lane == 0) { atomicExch(err, 1); R->n_cigar = 0; } return; }
+    unsigned long long off = 0;
+    if (lane == 0) off = atomicAdd(cursor, (unsigned long long)W.n);
+    off = __shfl_sync(kFull, off, 0);
+    if (off + W.n > dense_cap) { if (lane == 0) { atomicExch(err, 2); R->n_cigar = 0; } return; }
+    __syncwarp();
+    for (int a = lane; a < W.n; a += 32) cdense[off + a] = W.top[a];
+    if (lane == 0) { R->n_cigar = W.n; R->cigar_off = (long long)off; }
 }
 
 }  // namespace lb2

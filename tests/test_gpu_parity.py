@@ -117,6 +117,61 @@ def test_dropin_entry_points(ctx):
         assert rc == (0 if qle == ql else 1 if tle == tl else 2)
 
 
+def test_gpu_long_tasks(ctx):
+    """Tasks of thousands of rows: one task per warp in the fill (dp_pack.h LB2_LONG_ROWS) and the warp-cooperative
+    traceback (dp_trace.cuh trace_long_kernel), with indel runs that push the path out of a staged window, packed
+    and int32 kernels (match score 2 keeps a task out of the int16 domain), both kinds; a 20 kbp extension with the
+    SV band of SURVEY appendix C (w 2458)."""
+    rng = np.random.default_rng(77)
+    mats = {1: lamsa_b200.default_matrix(1, 3), 2: lamsa_b200.default_matrix(2, 4)}
+    keep, rows = list(mats.values()), []
+
+    def add(kind, q, t, w, h0=0, zdrop=0, pen=(5, 2, 5, 2), end_bonus=5, match=1):
+        qb = np.concatenate((q, np.zeros(8, np.uint8))).astype(np.uint8)
+        tb = np.concatenate((t, np.zeros(8, np.uint8))).astype(np.uint8)
+        keep.extend([qb, tb])
+        r = np.zeros(1, dtype=lamsa_b200.TASK_DTYPE)
+        r["kind"], r["flags"], r["qlen"], r["tlen"] = kind, 1, len(q), len(t)
+        r["query"], r["target"], r["w"], r["h0"] = qb.ctypes.data, tb.ctypes.data, w, h0
+        r["o_del"], r["e_del"], r["o_ins"], r["e_ins"] = pen
+        r["end_bonus"], r["zdrop"], r["m"], r["mat"] = end_bonus, zdrop, 5, mats[match].ctypes.data
+        rows.append(r)
+
+    def indels(q, n, maxlen):
+        """copy of q with n indel runs of up to maxlen bases and 3 % substitutions"""
+        out, at = [], 0
+        for cut in sorted(rng.integers(1, len(q) - 1, size=n)):
+            out.append(q[at:cut])
+            L = int(rng.integers(1, maxlen + 1))
+            if rng.random() < 0.5:
+                out.append(rng.integers(0, 4, size=L, dtype=np.uint8)); at = cut
+            else:
+                at = min(len(q), cut + L)
+        out.append(q[at:])
+        t = np.concatenate(out).astype(np.uint8)
+        sub = rng.random(len(t)) < 0.03
+        t[sub] = (t[sub] + rng.integers(1, 4, size=int(sub.sum()), dtype=np.uint8)) & 3
+        return t
+
+    for ql in (1600, 3000, 4700, 7000):
+        q = rng.integers(0, 4, size=ql, dtype=np.uint8)
+        for maxlen, w in ((3, 10), (40, 60), (90, 120)):
+            t = indels(q, 12, maxlen)
+            for match in (1, 2):
+                add(1, q, t, w, h0=100, zdrop=100, match=match)
+                add(1, q, t, w, h0=19, zdrop=0, pen=(2, 1, 2, 1), end_bonus=0, match=match)
+                add(0, q, t, w, match=match)
+                add(0, q, t, w, pen=(1, 1, 1, 1), match=match)
+    q = rng.integers(0, 4, size=19982, dtype=np.uint8)
+    add(1, q, indels(q, 30, 60), 2458, h0=190, zdrop=100)          # SURVEY appendix C: the longest task seen, its band
+    add(1, q[:9000], indels(q[:9000], 6, 200), 2458, h0=190, zdrop=0)
+    tasks = np.concatenate(rows)
+    res, cig = ctx.run(tasks, keep)
+    ores, ocig, _ = _oracle.oracle_run(tasks, 4)
+    bad = _oracle.compare(tasks, res, cig, ores, ocig, what="long", check_cells=True)
+    assert not bad, "\n".join(bad)
+
+
 def test_gpu_huge_windows(ctx):
     """Bands of ~10^4 columns (`-V 10000` gaps): windows beyond shared memory run the
     global-memory-window variant; a 32768-slot packed window still fits shared memory."""
