@@ -417,6 +417,47 @@ void lb2_producer_set_reference(const uint8_t *pac, int64_t l_pac);
 int  lb2_ref_abi_offsets(int *out);
 int  lb2_ref_abi_sizes(int *out);
 
+/* ---------------------------------- 6. local split mapping: seeds and line -- */
+/*
+ * The seed-and-chain half of the reference's hash_split_map (src/split_mapping.c:634-686): k-mer index of a
+ * reference window (init_hash :181-208), look-up of the read's k-mers (:654-675, at most 50 hits per k-mer) and
+ * the chaining of the hits into one line (hash_main_line :492-602).  One warp per request (hash_line.cuh).
+ * The line comes back as 3 ints per node: read position, diagonal (window position - read position), relation to
+ * the previous node (F_MATCH 0, F_MISMATCH 2, F_LONG_MISMATCH 3, F_INSERT 4, F_DELETE 5; src/lamsa_aln.h:101-113).
+ * The stitching of the line with DP calls (:688-821) is the drop-in `hash_split_map` below.
+ */
+typedef struct {
+    const uint8_t *ref;  int32_t ref_len;       /* reference window, codes 0..3 (4 hashes as 2, src/bntseq.c:78) */
+    const uint8_t *read; int32_t read_len;      /* read piece, codes 0..4                                        */
+    int32_t ref_offset;                          /* hash_split_map's ref_offset (> 0: duplication window)         */
+    int32_t hash_len, hash_step, split_len;      /* lamsa_aln_para: hash_len (<= 15), hash_step, split_len        */
+    int32_t head, tail;                          /* _head, _tail                                                  */
+    int32_t *line; int32_t line_cap;             /* out: 3 ints per node; capacity in nodes, at least
+                                                    (read_len - hash_len) / hash_step + 1                         */
+    int32_t m_len;                               /* out: nodes on the line (hash_main_line's return value)        */
+    int32_t n_hits;                              /* out: k-mer hits that entered the chaining                     */
+} lb2_hash_task;
+int lb2_hash_line_run(lb2_ctx *ctx, int64_t n, lb2_hash_task *tasks);
+
+/* drop-in replacements of src/split_mapping.c:181 and :634 (same signatures).  init_hash no longer builds the host
+ * index (it only leaves the arrays its callers free in a freeable state); hash_split_map sends the pair to the GPU
+ * for the line and stitches it with this library's ksw_global2 / ksw_bi_extend / ksw_extend_core.  The reference's
+ * own definitions are marked weak when split_mapping.c is compiled. */
+int init_hash(uint8_t *ref_seq, int ref_len, int hash_len, uint32_t **hash_num, uint64_t ***hash_node,
+              int ***hash_node_num, int32_t **hash_pos, int key_len, int hash_size);
+int hash_split_map(cigar32_t **split_cigar, int *split_clen, int *split_m,
+                   uint8_t *ref_seq, int ref_len, int ref_offset, uint8_t *read_seq, int read_len,
+                   lamsa_aln_para *AP, uint32_t *hash_num, uint64_t **hash_node, int **hash_node_num,
+                   int32_t *hash_pos, int _head, int _tail);
+/* the same two under library names, for a program that keeps its own (weak) init_hash / hash_split_map and forwards
+ * to these from one of its own objects (lamsa_b200/host/split_map.c; oracle/Makefile `producer_hash`) */
+int lb2_init_hash(uint8_t *ref_seq, int ref_len, int hash_len, uint32_t **hash_num, uint64_t ***hash_node,
+                  int ***hash_node_num, int32_t **hash_pos, int key_len, int hash_size);
+int lb2_hash_split_map(cigar32_t **split_cigar, int *split_clen, int *split_m,
+                       uint8_t *ref_seq, int ref_len, int ref_offset, uint8_t *read_seq, int read_len,
+                       lamsa_aln_para *AP, uint32_t *hash_num, uint64_t **hash_node, int **hash_node_num,
+                       int32_t *hash_pos, int _head, int _tail);
+
 #ifdef __cplusplus
 }
 #endif

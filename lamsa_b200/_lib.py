@@ -64,6 +64,13 @@ class AuxTask(C.Structure):
     _fields_ = [("cigar", C.c_void_p), ("n_cigar", C.c_int32), ("read_len", C.c_int32), ("read", C.c_void_p), ("ref_pac", C.c_int64)]
 
 
+class HashTask(C.Structure):
+    """lb2_hash_task"""
+    _fields_ = [("ref", C.c_void_p), ("ref_len", C.c_int32), ("read", C.c_void_p), ("read_len", C.c_int32), ("ref_offset", C.c_int32),
+                ("hash_len", C.c_int32), ("hash_step", C.c_int32), ("split_len", C.c_int32), ("head", C.c_int32), ("tail", C.c_int32),
+                ("line", C.c_void_p), ("line_cap", C.c_int32), ("m_len", C.c_int32), ("n_hits", C.c_int32)]
+
+
 class ClassStat(C.Structure):
     """lb2_class_stat"""
     _fields_ = [("class_id", C.c_int32), ("kind", C.c_int32), ("variant", C.c_int32), ("window_slots", C.c_int32),
@@ -87,7 +94,7 @@ EXPORTS = [
     "lb2_batch_create", "lb2_batch_create_pool", "lb2_batch_upload", "lb2_batch_compute", "lb2_batch_compute_async", "lb2_batch_compute_done", "lb2_batch_compute_wait", "lb2_batch_download", "lb2_batch_download_view", "lb2_batch_stats", "lb2_batch_set_class_timing", "lb2_batch_class_stats",
     "lb2_batch_destroy", "lb2_free", "lb2_int_peak",
     "lb2_sdp_create", "lb2_sdp_reset", "lb2_sdp_run_bcc", "lb2_sdp_run_remain", "lb2_sdp_stats", "lb2_sdp_destroy", "lb2_sdp_get_tracked", "lb2_sdp_set_tracked",
-    "lb2_aux_run", "lb2_worker_aux_counts", "lb2_producer_set_reference", "lb2_ref_abi_offsets", "lb2_ref_abi_sizes", "lb2_worker_spawn", "lb2_worker_join", "lb2_worker_yield", "lb2_worker_parked_seconds", "lb2_dropin_warmup", "lb2_fiber_selftest",
+    "lb2_aux_run", "lb2_hash_line_run", "init_hash", "hash_split_map", "lb2_init_hash", "lb2_hash_split_map", "lb2_worker_aux_counts", "lb2_producer_set_reference", "lb2_ref_abi_offsets", "lb2_ref_abi_sizes", "lb2_worker_spawn", "lb2_worker_join", "lb2_worker_yield", "lb2_worker_parked_seconds", "lb2_dropin_warmup", "lb2_fiber_selftest",
     "frag_line_BCC", "frag_line_remain", "node_init_score", "node_free_score", "cover_rate",
     "build_node_max_heap", "build_node_min_heap", "build_node_minpos_heap",
 ]
@@ -138,6 +145,7 @@ def load_library():
     lib.lb2_batch_class_stats.argtypes = [P, C.POINTER(ClassStat), I]
     lib.lb2_batch_destroy.argtypes = [P]
     lib.lb2_aux_run.argtypes = [P, I64, C.POINTER(AuxTask), P]
+    lib.lb2_hash_line_run.argtypes = [P, I64, C.POINTER(HashTask)]
     lib.lb2_batch_destroy.restype = None
     lib.lb2_free.argtypes = [P]
     lib.lb2_free.restype = None

@@ -49,5 +49,7 @@ void dropin_submit_sdp(std::vector<SdpRequest*>& batch);
 bool fiber_active();
 void fiber_wait_dp(DpRequest* r);
 void fiber_wait_sdp(SdpRequest* r);
+// lb2_hash_line_run for a worker fiber (producer.cu): parks; all parked requests of all workers are one launch
+int worker_hash_line(lb2_hash_task* t);
 
 }  // namespace lb2

@@ -96,7 +96,7 @@ struct DpGroup {
     std::vector<lb2::DpRequest*> reqs;
     std::vector<Fiber*> owners;
 };
-struct AuxRequest { int64_t n; const lb2_aux_task* tasks; lb2_aux_result* results; };
+struct AuxRequest { int64_t n; const lb2_aux_task* tasks; lb2_aux_result* results; lb2_hash_task* hash; };   // hash != nullptr: one lb2_hash_line_run request
 struct AuxGroup {
     Clock::time_point t_first;
     std::vector<AuxRequest*> reqs;
@@ -160,7 +160,7 @@ struct Device {
     std::thread submitter, sdp_thread[kSdpThreads], aux_thread;
     // statistics (under mu)
     std::vector<int> batch_tasks;
-    int64_t dp_tasks = 0, slow_batches = 0, slow_tasks = 0, sdp_reqs = 0, sdp_batches = 0;
+    int64_t dp_tasks = 0, slow_batches = 0, slow_tasks = 0, sdp_reqs = 0, sdp_batches = 0, hash_n = 0, hash_batches = 0;
     double pack_s = 0, deliver_s = 0, sdp_s = 0, kernel_ms = 0;
 };
 
@@ -363,17 +363,28 @@ void aux_main(Device* d) {
             if (d->pend_aux.empty()) return;
             take.swap(d->pend_aux);
         }
-        if (!have_ref) {
-            if (!g_ref_pac || lb2_ctx_set_reference(d->aux_ctx, g_ref_pac, g_ref_l_pac)) die("record statistics need the reference (lb2_producer_set_reference)");
-            have_ref = true;
-        }
         std::vector<lb2_aux_task> tasks; std::vector<lb2_aux_result> results; std::vector<Fiber*> owners;
-        for (AuxGroup* g : take) for (AuxRequest* q : g->reqs) tasks.insert(tasks.end(), q->tasks, q->tasks + q->n);
-        results.resize(tasks.size());
-        if (lb2_aux_run(d->aux_ctx, (int64_t)tasks.size(), tasks.data(), results.data())) die("record statistics failed");
+        std::vector<lb2_hash_task> hashes; std::vector<lb2_hash_task*> hash_home;
+        for (AuxGroup* g : take) for (AuxRequest* q : g->reqs) {
+            if (q->hash) { hashes.push_back(*q->hash); hash_home.push_back(q->hash); }
+            else tasks.insert(tasks.end(), q->tasks, q->tasks + q->n);
+        }
+        if (!tasks.empty()) {
+            if (!have_ref) {
+                if (!g_ref_pac || lb2_ctx_set_reference(d->aux_ctx, g_ref_pac, g_ref_l_pac)) die("record statistics need the reference (lb2_producer_set_reference)");
+                have_ref = true;
+            }
+            results.resize(tasks.size());
+            if (lb2_aux_run(d->aux_ctx, (int64_t)tasks.size(), tasks.data(), results.data())) die("record statistics failed");
+        }
+        if (!hashes.empty()) {      // the seed-and-chain requests of hash_split_map (hash_dropin.cu): one launch
+            if (lb2_hash_line_run(d->aux_ctx, (int64_t)hashes.size(), hashes.data())) { fprintf(stderr, "[lamsa_b200] %s\n", lb2_last_error()); die("split-mapping lines failed"); }
+            for (size_t k = 0; k < hashes.size(); ++k) { hash_home[k]->m_len = hashes[k].m_len; hash_home[k]->n_hits = hashes[k].n_hits; }
+            d->hash_n += (int64_t)hashes.size(); ++d->hash_batches;
+        }
         size_t at = 0;
         for (AuxGroup* g : take) {
-            for (AuxRequest* q : g->reqs) { std::copy(results.begin() + (long)at, results.begin() + (long)(at + (size_t)q->n), q->results); at += (size_t)q->n; }
+            for (AuxRequest* q : g->reqs) if (!q->hash) { std::copy(results.begin() + (long)at, results.begin() + (long)(at + (size_t)q->n), q->results); at += (size_t)q->n; }
             owners.insert(owners.end(), g->owners.begin(), g->owners.end());
             delete g;
         }
@@ -625,6 +636,7 @@ void run_all(std::vector<Fiber*>& fibers) {
                             "%lld chaining requests in %lld batches; submitter packing %.3f s, completers %.3f s, kernels %.3f s, chaining thread %.3f s\n",
                     d->device, (long long)d->dp_tasks, bt.size(), med, mx, (long long)d->slow_tasks, (long long)d->slow_batches,
                     (long long)d->sdp_reqs, (long long)d->sdp_batches, d->pack_s, d->deliver_s, d->kernel_ms * 1e-3, d->sdp_s);
+            if (d->hash_n) fprintf(stderr, "[lamsa_b200] GPU %d: %lld split-mapping lines (k-mer index + chaining of a window) in %lld launches\n", d->device, (long long)d->hash_n, (long long)d->hash_batches);
         }
     }
     for (Fiber* f : fibers) delete f;
@@ -687,7 +699,20 @@ extern "C" int lb2_worker_aux_counts(int64_t n, const lb2_aux_task* tasks, lb2_a
     Worker* w = tl_worker;
     if (!w || !w->cur) return lb2::set_error("lb2_worker_aux_counts: not called from a worker of the batch producer");
     if (n <= 0) return 0;
-    AuxRequest r{n, tasks, results};
+    AuxRequest r{n, tasks, results, nullptr};
+    if (!w->aux) { w->aux = new AuxGroup(); w->aux->t_first = Clock::now(); }
+    w->aux->reqs.push_back(&r); w->aux->owners.push_back(w->cur);
+    const auto t1 = Clock::now();
+    yield_to_scheduler();
+    tl_worker->cur->parked_s += secs(t1, Clock::now());
+    return 0;
+}
+
+// lb2_hash_line_run for a worker fiber (hash_dropin.cu): parks; all parked requests of all workers are one launch
+int lb2::worker_hash_line(lb2_hash_task* t) {
+    Worker* w = tl_worker;
+    if (!w || !w->cur) return lb2::set_error("worker_hash_line: not called from a worker of the batch producer");
+    AuxRequest r{0, nullptr, nullptr, t};
     if (!w->aux) { w->aux = new AuxGroup(); w->aux->t_first = Clock::now(); }
     w->aux->reqs.push_back(&r); w->aux->owners.push_back(w->cur);
     const auto t1 = Clock::now();

@@ -35,7 +35,7 @@ def lib():
 def test_exports_every_declared_symbol(lib):
     hdr = open(os.path.join(ROOT, "include", "lamsa_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b((?:ksw|lb2|sw|frag_line|node|build_node)_[A-Za-z0-9_]+|cover_rate)\s*\(", hdr))
+    declared = set(re.findall(r"\b((?:ksw|lb2|sw|frag_line|node|build_node)_[A-Za-z0-9_]+|cover_rate|init_hash|hash_split_map)\s*\(", hdr))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     abi = open(os.path.join(ROOT, "lamsa_b200", "csrc", "ref_abi.h")).read()
     declared_abi = set(re.findall(r"\b((?:heap|node)_[a-z_]+)\s*\(lb2_ref_node_score", abi))

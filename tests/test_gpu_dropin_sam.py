@@ -23,7 +23,10 @@ EXES = {"dp": os.path.join(ROOT, "oracle", "_ref", "lamsa_dropin"),
         "producer": os.path.join(ROOT, "oracle", "_ref", "lamsa_b200_aln"),
         # + lamsa_res_aux (NM / AS of every record) walking the CIGARs on the GPU over the resident reference
         # (lamsa_b200/host/res_aux.c, `make -C oracle producer_aux`): the NM:i / AS:i tags must not move
-        "producer+aux": os.path.join(ROOT, "oracle", "_ref", "lamsa_b200_aln_aux")}
+        "producer+aux": os.path.join(ROOT, "oracle", "_ref", "lamsa_b200_aln_aux"),
+        # + init_hash / hash_split_map of the local split mapping: k-mer index of the window, look-up and chaining of the
+        # hits on the GPU (hash_line.cuh, lamsa_b200/host/split_map.c, `make -C oracle producer_hash`)
+        "producer+hash": os.path.join(ROOT, "oracle", "_ref", "lamsa_b200_aln_hash")}
 FIXTURES = [
     ("small", os.path.join(ROOT, "tests", "golden", "sam_small")),
     # 4 contigs; donor with deletions / insertions / inversions / duplications and translocations BETWEEN contigs
@@ -48,7 +51,7 @@ def stage(src, dst):
 
 @pytest.mark.parametrize("name,src", FIXTURES, ids=[f[0] for f in FIXTURES])
 @pytest.mark.parametrize("threads", [1, 4])
-@pytest.mark.parametrize("link", ["dp", "dp+sdp", "producer", "producer+aux"])
+@pytest.mark.parametrize("link", ["dp", "dp+sdp", "producer", "producer+aux", "producer+hash"])
 def test_dropin_sam_identical_to_reference(tmp_path, name, src, threads, link):
     EXE = EXES[link]
     if not os.path.exists(EXE):
@@ -57,6 +60,7 @@ def test_dropin_sam_identical_to_reference(tmp_path, name, src, threads, link):
         pytest.skip(f"fixture {src} not present")
     env = dict(os.environ)
     if link.startswith("producer"):
+        env["LB2_FIBER_STATS"] = "1"
         # reads in flight: the default (thousands), or fewer workers than reads with an odd count
         if threads == 1:
             env["LB2_READS_IN_FLIGHT"] = "37"
@@ -74,3 +78,5 @@ def test_dropin_sam_identical_to_reference(tmp_path, name, src, threads, link):
     assert len(got) == len(exp), (len(got), len(exp))
     diff = [(i, a, b) for i, (a, b) in enumerate(zip(got, exp)) if a != b]
     assert not diff, f"{len(diff)} differing SAM lines; first: {diff[0][1][:300]!r} vs {diff[0][2][:300]!r}"
+    if link == "producer+hash" and name in ("multi_contig_sv", "c4_reduced_sv"):
+        assert b"split-mapping lines" in r.stderr or "LB2_FIBER_STATS" not in env      # the SV fixtures do reach the GPU path
