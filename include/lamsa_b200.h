@@ -417,6 +417,39 @@ void lb2_producer_set_reference(const uint8_t *pac, int64_t l_pac);
 int  lb2_ref_abi_offsets(int *out);
 int  lb2_ref_abi_sizes(int *out);
 
+/* ------------------------------------------- 7. local Smith-Waterman (ksw_align) -- */
+/* src/ksw.h:15-20, :62-63; src/ksw.c:68 (ksw_qinit), :116 (ksw_u8), :237 (ksw_i16), :344 (ksw_align2), :373 (ksw_align).
+ * No caller inside LAMSA; exported because the reference's header declares them.  kswq_t stays opaque
+ * (callers pass it back and free() it).  Results equal the SSE2 code's, including its dependence on the profile
+ * width (16 byte lanes / 8 word lanes), the padding columns in the row maxima, and score 255 on byte overflow. */
+#define LB2_KSW_XBYTE  0x10000
+#define LB2_KSW_XSTOP  0x20000
+#define LB2_KSW_XSUBO  0x40000
+#define LB2_KSW_XSTART 0x80000
+#ifndef LAMSA_B200_NO_PARA_TYPE
+struct _kswq_t;
+typedef struct _kswq_t kswq_t;
+typedef struct { int score; int te, qe; int score2, te2; int tb, qb; } kswr_t;
+kswq_t *ksw_qinit(int size, int qlen, const uint8_t *query, int m, const int8_t *mat);
+kswr_t ksw_u8(kswq_t *q, int tlen, const uint8_t *target, int o_del, int e_del, int o_ins, int e_ins, int xtra);
+kswr_t ksw_i16(kswq_t *q, int tlen, const uint8_t *target, int o_del, int e_del, int o_ins, int e_ins, int xtra);
+kswr_t ksw_align2(int qlen, uint8_t *query, int tlen, uint8_t *target, int m, const int8_t *mat,
+                  int o_del, int e_del, int o_ins, int e_ins, int xtra, kswq_t **qry);
+kswr_t ksw_align(int qlen, uint8_t *query, int tlen, uint8_t *target, int m, const int8_t *mat,
+                 int gapo, int gape, int xtra, kswq_t **qry);
+#endif
+/* batch form: one warp per pair (sw_local.cuh); size 1 = byte profile (ksw_u8), 2 = word profile (ksw_i16);
+ * xtra as in src/ksw.h (KSW_XSTART is the caller's second pass, see ksw_align2); tb/qb come back -1 */
+typedef struct {
+    const uint8_t *query; int32_t qlen;
+    const uint8_t *target; int32_t tlen;
+    int32_t m; const int8_t *mat;
+    int32_t o_del, e_del, o_ins, e_ins;
+    int32_t xtra, size;
+} lb2_sw_task;
+typedef struct { int32_t score, te, qe, score2, te2, tb, qb; } lb2_sw_result;
+int lb2_sw_run(lb2_ctx *ctx, int64_t n, const lb2_sw_task *tasks, lb2_sw_result *results);
+
 /* ---------------------------------- 6. local split mapping: seeds and line -- */
 /*
  * The seed-and-chain half of the reference's hash_split_map (src/split_mapping.c:634-686): k-mer index of a

@@ -89,7 +89,7 @@ PARA_FIELDS = [
 # every symbol include/lamsa_b200.h declares
 EXPORTS = [
     "ksw_global2", "ksw_global", "ksw_extend2", "ksw_extend", "ksw_extend_core", "ksw_extend_c",
-    "ksw_extend_r", "ksw_bi_extend", "sw_mid_fix",
+    "ksw_extend_r", "ksw_bi_extend", "sw_mid_fix", "ksw_qinit", "ksw_u8", "ksw_i16", "ksw_align2", "ksw_align", "lb2_sw_run",
     "lb2_ctx_create", "lb2_ctx_destroy", "lb2_last_error", "lb2_ctx_set_scratch_limit", "lb2_ctx_set_reference", "lb2_ctx_last_run_stats", "lb2_ctx_last_run_kernel_ms", "lb2_ctx_set_chunk_tasks", "lb2_dp_run", "lb2_dp_run_pool", "lb2_pool_pack", "lb2_host_alloc", "lb2_host_free",
     "lb2_batch_create", "lb2_batch_create_pool", "lb2_batch_upload", "lb2_batch_compute", "lb2_batch_compute_async", "lb2_batch_compute_done", "lb2_batch_compute_wait", "lb2_batch_download", "lb2_batch_download_view", "lb2_batch_stats", "lb2_batch_set_class_timing", "lb2_batch_class_stats",
     "lb2_batch_destroy", "lb2_free", "lb2_int_peak",
