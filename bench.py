@@ -112,8 +112,8 @@ def pipeline_fixture():
     """(dir, replicate, description) of the C3-shaped fixture the pipeline leg runs, or None.  The fixtures are outputs
     of the unmodified reference (oracle/make_sam_fixtures.py); the larger ones live under oracle/_ref/ (not in git,
     shipped with the snapshot), the committed small one is the fall-back."""
-    cands = [(os.path.join(ROOT, "oracle", "_ref", "sam_c3m"), 4,
-              "C3 shape: 4 Mbp random reference, 2 000 x 10 kbp reads at 15 % error (1.5/9/4.5 sub/ins/del), `-T pacbio`, reads taken 4 times = 8 000 reads, 84 Mbp"),
+    cands = [(os.path.join(ROOT, "oracle", "_ref", "sam_c3m"), 10,
+              "C3 shape at BASELINE configs[2]'s read count: 4 Mbp random reference, 2 000 x 10 kbp reads at 15 % error (1.5/9/4.5 sub/ins/del), `-T pacbio`, reads taken 10 times = 20 000 reads, 209 Mbp"),
              (os.path.join(ROOT, "oracle", "_ref", "sam_c3s"), 16,
               "C3 shape, reduced: 1 Mbp reference, 100 x 10 kbp reads at 15 % error, `-T pacbio`, reads taken 16 times"),
              (os.path.join(ROOT, "tests", "golden", "sam_small"), 64,

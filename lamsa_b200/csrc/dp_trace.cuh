@@ -9,8 +9,12 @@
 
 namespace lb2 {
 
-// tasks whose path is at least this long (qlen + tlen) are walked by a whole warp (trace_long_kernel)
-constexpr int kLongTrace = 1536;
+// tasks whose path is at least this long (qlen + tlen) are walked by a whole warp (trace_long_kernel): a matter of
+// LATENCY (a batch lasts as long as its longest task).  For throughput one thread per task is better -- a million
+// 500-row walks keep every SM busy at a thirty-second of the issue slots a warp per walk would take; measured on the
+// C2 batch with the threshold at 1536: traceback 14.8 -> 25.6 ms -- so the threshold sits above that workload's tasks
+// (the same 1200 rows at which the fill goes to one task per warp, dp_pack.h).
+constexpr int kLongTrace = 2400;
 
 struct CigarWriter {
     int32_t* top;      // next free word is top[-1]; words are written downwards

@@ -252,6 +252,10 @@ void remaining_regions(const lb2_sdp_para& P, int read_len, const lb2_sdp_reg* r
     }
     std::vector<int> ord(n_reg);
     std::iota(ord.begin(), ord.end(), 0);
+    // TIE ORDER: the reference sorts with qsort(reg_comp) (src/lamsa_aln.c:476), whose order of records with equal `beg` is
+    // whatever the C library's qsort does: glibc up to 2.36 merge-sorts (stable, the order reproduced here and by the
+    // oracle); glibc >= 2.37 uses an introsort that is not stable.  Records with equal `beg` are therefore the one place
+    // where a reference binary built against another libc may legitimately differ; ties are broken by input order here.
     std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return regs[a].beg < regs[b].beg; });
     std::vector<Aligned> A;
     for (int k = 0; k < n_reg; ++k) {

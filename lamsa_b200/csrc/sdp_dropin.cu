@@ -126,6 +126,7 @@ void push_pts(lb2_ref_reg* r, int bn, const lb2_ref_reg_b* b, int en, const lb2_
     }
 }
 void sort_merge_regions(lb2_ref_aln_reg* a, int thd) {
+    // ties (equal `beg`) keep input order: see the note on qsort's tie order in sdp_batch.cu (remaining_regions)
     std::stable_sort(a->reg, a->reg + a->reg_n, [](const lb2_ref_reg& x, const lb2_ref_reg& y) { return x.beg < y.beg; });
     int cur = 0;
     for (int i = 1; i < a->reg_n; ++i) {
@@ -251,7 +252,9 @@ extern "C" int frag_line_remain(lb2_ref_aln_reg* a_reg, lb2_ref_map_msg* m_msg, 
         const lb2_ref_reg& g = a_reg->reg[k];
         // get_reg (src/lamsa_aln.c:608-616) hands one begin and one end point per record; records that a
         // caller already merged are passed as one record per point pair
-        const int n = std::max(g.beg_n, g.end_n);
+        // a record without a begin or without an end point has no interval on the reference to report (push_reg allows
+        // such records; get_reg never produces them): it takes part in the in-place merge below, not in the request
+        const int n = (g.beg_n > 0 && g.end_n > 0) ? std::max(g.beg_n, g.end_n) : 0;
         for (int t = 0; t < n; ++t) {
             const lb2_ref_reg_b& pb = g.ref_beg[std::min(t, g.beg_n - 1)];
             const lb2_ref_reg_b& pe = g.ref_end[std::min(t, g.end_n - 1)];
