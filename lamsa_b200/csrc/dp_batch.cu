@@ -19,6 +19,7 @@
 #include "dp_fill16.cuh"
 #include "dp_fill16s.cuh"
 #include "dp_fill16d.cuh"
+#include "dp_fill_lean.cuh"
 #include "dp_trace.cuh"
 #include "int_peak.cuh"
 #include "aux_scan.cuh"
@@ -44,7 +45,7 @@ extern "C" void lb2_free(void* p) { free(p); }
 // ----------------------------------------------------------------- context --
 // launch classes, variants and the per-task classification live in dp_pack.h
 static inline int class_warps(int var, int logS) {   // warps per block
-    if (var == kVarGmem) return 4;
+    if (var == kVarGmem || var == kVarBlock) return 4;
     int wpb = 8;
     while (wpb > 1 && (size_t)wpb * var_warp_smem(var, 1 << logS) > 160 * 1024) wpb >>= 1;
     return wpb;
@@ -115,6 +116,7 @@ struct lb2_ctx {
 typedef void (*fill_fn)(const DTask*, const int32_t*, int, const uint8_t*, const uint8_t*, uint8_t*, DResult*,
                         const uint2*, unsigned int*, int, uint8_t*);
 static fill_fn fill_table(int kind, int var) {
+    if (var == kVarBlock) return fill_lean_kernel;
     // group kernels with dynamic refill (dp_fill16d.cuh) unless LB2_DYN=0
     static const bool dyn = [] { const char* e = getenv("LB2_DYN"); return !(e && *e == '0'); }();
     if (dyn && var >= 6) {
@@ -737,7 +739,7 @@ static int compute_enqueue(lb2_batch* b) {
             if (!cnt) continue;
             const int kind = class_kind(k), var = class_var(k), ls = class_logS(k);
             const int wpb = class_warps(var, ls);
-            const size_t smem = var == kVarGmem ? 0 : (size_t)wpb * var_warp_smem(var, 1 << ls);
+            const size_t smem = (var == kVarGmem || var == kVarBlock) ? 0 : (size_t)wpb * var_warp_smem(var, 1 << ls);
             if (!c->occ[k]) {
                 // first launch of this kernel through this context: opt in to the large dynamic shared memory, then
                 // ask how many blocks fit (both load the kernel's module on demand)
@@ -950,10 +952,10 @@ extern "C" int lb2_batch_stats(const lb2_batch* b, int64_t* h2d, int64_t* d2h, i
 static const char* kernel_name(int kind, int var) {
     static const char* g[] = {"fill_kernel<1,global>", "fill_kernel<2,global>", "fill_kernel<4,global>", "fill16_kernel<2,global>", "fill16_kernel<4,global>",
                               "fill_kernel<4,global,gmem window>", "fill16d_kernel<2,global,16>", "fill16d_kernel<2,global,8>", "fill16d_kernel<4,global,8>",
-                              "fill16d_kernel<4,global,16>", "fill_long_kernel<global>"};
+                              "fill16d_kernel<4,global,16>", "fill_lean_kernel"};
     static const char* e[] = {"fill_kernel<1,extend>", "fill_kernel<2,extend>", "fill_kernel<4,extend>", "fill16_kernel<2,extend>", "fill16_kernel<4,extend>",
                               "fill_kernel<4,extend,gmem window>", "fill16d_kernel<2,extend,16>", "fill16d_kernel<2,extend,8>", "fill16d_kernel<4,extend,8>",
-                              "fill16d_kernel<4,extend,16>", "fill_long_kernel<extend>"};
+                              "fill16d_kernel<4,extend,16>", "fill_lean_kernel<extend>"};
     return (kind == kKindGlobal ? g : e)[var];
 }
 

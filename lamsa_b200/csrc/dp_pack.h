@@ -24,7 +24,7 @@ namespace lb2 {
 // variants: 0..2 int32 lanes with G = 1,2,4 columns per lane; 3,4 packed int16 with NP = 2,4 pairs
 // per lane; 5 = int32 G=4 with the window in global memory (does not fit shared memory);
 // 6,7 = packed NP=2 in sub-warp groups of L = 16 / 8 lanes per task (dp_fill16d.cuh); 8, 9 = packed NP=4, L = 8 / 16;
-// 10 = one thread block per task (dp_fill_long.cuh: long tasks, rows cut into per-warp column segments).
+// 10 = extensions of many rows inside a band of at most 15: one task per warp, the window in registers (dp_fill_lean.cuh).
 constexpr int kMinLogS = 6, kMaxLogS = 18;          // 64 .. 262144 slots per warp
 constexpr int kNumLogS = kMaxLogS - kMinLogS + 1;
 constexpr int kNumVar = 11;
@@ -37,7 +37,7 @@ inline int class_id(int kind, int var, int logS) { return (kind * kNumVar + var)
 inline int class_kind(int c) { return c / (kNumVar * kNumLogS); }
 inline int class_var(int c) { return (c / kNumLogS) % kNumVar; }
 inline int class_logS(int c) { return c % kNumLogS + kMinLogS; }
-inline int var_gshift(int var) { return var == kVarBlock ? 2 : var >= 8 ? 3 : var == kVarGmem || var >= 6 ? 2 : var < 3 ? var : var - 1; }     // log2(columns per lane)
+inline int var_gshift(int var) { return var == kVarBlock ? 0 : var >= 8 ? 3 : var == kVarGmem || var >= 6 ? 2 : var < 3 ? var : var - 1; }     // log2(columns per lane)
 inline bool var_packed(int var) { return var == 3 || var == 4 || (var >= 6 && var <= 9); }
 inline int var_tasks_per_warp(int var) { return var == 6 || var == 9 ? 2 : (var >= 7 && var <= 8) ? 4 : 1; }
 inline size_t var_warp_smem(int var, int S) {
@@ -96,6 +96,9 @@ inline bool fits_int16(const lb2_task& t, int w) {
 // kernel variant from the widest band a row can have
 inline int pick_variant(const lb2_task& t, int w, long ncol, int logS) {
     const int S_ = 1 << logS;
+    // long extensions inside a narrow band: the latency of one row on one warp is what counts (dp_fill_lean.cuh)
+    static const int lean_rows = env_int("LB2_LEAN_ROWS", 192);
+    if (lean_rows > 0 && t.kind == LB2_KIND_EXTEND && w <= 15 && t.tlen >= lean_rows) return kVarBlock;
     static const int force_gmem = env_int("LB2_FORCE_GMEM", 0);              // test hook
     if (force_gmem || warp_smem_bytes16(S_) > kMaxDynSmem) return kVarGmem;   // window beyond shared memory
     static const int use16 = env_int("LB2_P16", 1), p16_min = env_int("LB2_P16_MIN", 37),

@@ -168,6 +168,29 @@ trace_long_kernel(const DTask* __restrict__ tasks, const int32_t* __restrict__ l
         }
         __syncwarp();
         const int i0 = i;
+        if (which == 0) {
+            // runs of diagonal steps -- most of an alignment -- are taken at once: lane l looks at cell (i-l, k-l) of the
+            // staged rows, the run is the number of leading lanes whose cell was computed and came from the diagonal
+            const int l = lane, rr = i - l, kk = k - l;
+            bool is_m = false;
+            if (l < kTraceRows && rr >= 0 && kk >= 0) {
+                const int4 mt = smeta[wid][l];
+                const int rel = kk - mt.z, piece = (rel >> cs) - (mt.w - 1);
+                if (kk >= mt.x && kk < mt.y && (piece == 0 || piece == 1)) {
+                    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(&sdir[wid][l][0]);
+                    uint32_t nib;
+                    if (G == 1) nib = bytes[piece * 16 + (rel & 15)] & 15u;
+                    else nib = (bytes[piece * 16 + ((rel & 31) >> 1)] >> (4 * (rel & 1))) & 15u;
+                    if (T.dir_fmt == 1) {           // raw predicates: H came from the diagonal iff neither E nor F won
+                        const uint32_t b0 = nib & 1u, b1 = (nib >> 1) & 1u;
+                        is_m = ext ? (b0 == 0u && b1 == 0u) : (b0 == 1u && b1 == 1u);
+                    } else is_m = (nib & 3u) == 0u;
+                }
+            }
+            const unsigned bal = __ballot_sync(kFull, is_m);
+            const int run = __ffs(~bal) - 1;        // leading ones (at most kTraceRows: lanes beyond never vote)
+            if (run > 0) { W.push(0, run); i -= run; k -= run; }
+        }
         while (i >= 0 && k >= 0 && i > i0 - kTraceRows) {
             const int4 mt = smeta[wid][i0 - i];
             if (k >= mt.x && k < mt.y) {
