@@ -44,6 +44,7 @@
 #include "ctx_internal.h"
 #include "dp_pack.h"
 #include "dropin_internal.h"
+namespace lb2 { extern std::atomic<long long> g_sdp_ns[5]; }      // sdp_dropin.cu: where the chaining batches' time goes
 
 namespace {
 
@@ -316,6 +317,18 @@ void sdp_main(Device* d, int k) {
             std::unique_lock<std::mutex> lk(d->mu);
             d->cv_sdp.wait(lk, [&] { return d->stop || !d->pend_sdp.empty(); });
             if (d->pend_sdp.empty()) return;
+            // a batch costs a dozen driver calls whatever its size: give the other worker threads a moment to add theirs
+            static const int min_reads = env_i("LB2_SDP_MIN_BATCH", 64), gather_us = env_i("LB2_SDP_GATHER_US", 200);
+            if (gather_us > 0) {
+                const auto due = Clock::now() + std::chrono::microseconds(gather_us);
+                for (;;) {
+                    size_t have = 0;
+                    for (SdpGroup* g : d->pend_sdp) have += g->reqs.size();
+                    if (d->stop || have >= (size_t)min_reads || d->pend_sdp.empty()) break;
+                    if (d->cv_sdp.wait_until(lk, due) == std::cv_status::timeout) break;
+                }
+                if (d->pend_sdp.empty()) continue;          // another chaining thread took them
+            }
             take.swap(d->pend_sdp);
         }
         const auto t0 = Clock::now();
@@ -636,6 +649,8 @@ void run_all(std::vector<Fiber*>& fibers) {
                             "%lld chaining requests in %lld batches; submitter packing %.3f s, completers %.3f s, kernels %.3f s, chaining thread %.3f s\n",
                     d->device, (long long)d->dp_tasks, bt.size(), med, mx, (long long)d->slow_tasks, (long long)d->slow_batches,
                     (long long)d->sdp_reqs, (long long)d->sdp_batches, d->pack_s, d->deliver_s, d->kernel_ms * 1e-3, d->sdp_s);
+            fprintf(stderr, "[lamsa_b200] chaining batches, seconds summed over the threads: flattening the requests %.3f, loading the batch (H2D) %.3f, stage incl. read-back %.3f (kernels alone %.3f), handing back %.3f\n",
+                    lb2::g_sdp_ns[0] * 1e-9, lb2::g_sdp_ns[1] * 1e-9, lb2::g_sdp_ns[2] * 1e-9, lb2::g_sdp_ns[3] * 1e-9, lb2::g_sdp_ns[4] * 1e-9);
             if (d->hash_n) fprintf(stderr, "[lamsa_b200] GPU %d: %lld split-mapping lines (k-mer index + chaining of a window) in %lld launches\n", d->device, (long long)d->hash_n, (long long)d->hash_batches);
         }
     }

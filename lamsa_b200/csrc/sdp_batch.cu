@@ -13,6 +13,7 @@
 #include "../../include/lamsa_b200.h"
 #include "ctx_internal.h"
 #include "sdp_kernel.cuh"
+#include <chrono>
 
 using namespace lb2;
 using namespace lb2::sdp;
@@ -34,21 +35,56 @@ template <class T> struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !view) cudaFree(p); p = nullptr; cap = 0; }
+    bool view = false;                         // p points into another buffer (the upload arena)
+    void point_at(void* q) { view = true; p = static_cast<T*>(q); cap = 0; }
 };
+// page-locked host staging, grow-only.  Every copy of a chaining batch goes through one: copies from or to pageable
+// memory are staged by the driver in pieces, each piece waited for -- with the producer's sleeping waits
+// (cudaDeviceScheduleBlockingSync) that made the H2D of a batch of a few hundred kilobytes cost milliseconds, ten times
+// its kernels (LB2_FIBER_STATS: 4.6 s of loading and 6.3 s of stages around 0.3 s of kernels on 20 000 reads).
+struct PinBuf {
+    uint8_t* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        const size_t want = std::max(std::max(n + n / 4, cap * 2), (size_t)1 << 16);
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+size_t up64(size_t x) { return (x + 63) & ~(size_t)63; }
+// Wait for everything queued on `st`: poll an event for a few hundred microseconds (the chaining kernels of a batch
+// last that long; a sleeping wait costs a wake-up on top), then sleep.
+cudaError_t wait_stream(cudaStream_t st, cudaEvent_t ev) {
+    cudaError_t e = cudaEventRecord(ev, st);
+    if (e != cudaSuccess) return e;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int spin = 0;; ++spin) {
+        e = cudaEventQuery(ev);
+        if (e != cudaErrorNotReady) return e;
+        if ((spin & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(400)) break;
+    }
+    return cudaEventSynchronize(ev);
+}
 }  // namespace
 
 struct lb2_sdp_batch {
     lb2_ctx* ctx = nullptr;
     lb2_sdp_para para{};
     int64_t n = 0, n_hits = 0, n_seeds = 0;
-    std::vector<DRead> reads;
-    std::vector<int32_t> order;
+    DRead* reads = nullptr;                   // in `up` (page-locked)
+    PinBuf up, up2, down, flags_pin;          // uploads of a reset / of a remain stage, read-backs of a stage, tracked flags
+    cudaEvent_t ev_wait = nullptr;
+    DevBuf<uint8_t> d_up;                     // device copy of the page-locked arena `up`: ONE copy per load; the next eight point into it
     DevBuf<DRead> d_reads; DevBuf<int32_t> d_order, d_seed_id, d_map_n, d_hoff, d_hseed, d_rflat;
     DevBuf<lb2_sdp_hit> d_hits;
     DevBuf<int> d_scratch, d_dense; DevBuf<DOut> d_outs; DevBuf<unsigned int> d_counter; DevBuf<long long> d_off;
     DevBuf<DRegion> d_regions; DevBuf<DPoint> d_pts; DevBuf<uint8_t> d_flags;
-    std::vector<int32_t> stream; std::vector<int64_t> off; std::vector<DOut> outs;
+    const int32_t* stream = nullptr; std::vector<int64_t> off; const DOut* outs = nullptr;     // stream / outs: in `down`
     int64_t pairs = 0, h2d = 0, d2h = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -56,11 +92,13 @@ struct lb2_sdp_batch {
 extern "C" void lb2_sdp_destroy(lb2_sdp_batch* b) {
     if (!b) return;
     cudaSetDevice(ctx_device(b->ctx));
-    b->d_reads.release(); b->d_order.release(); b->d_seed_id.release(); b->d_map_n.release(); b->d_hoff.release();
+    b->d_up.release(); b->d_reads.release(); b->d_order.release(); b->d_seed_id.release(); b->d_map_n.release(); b->d_hoff.release();
     b->d_hseed.release(); b->d_rflat.release(); b->d_hits.release(); b->d_scratch.release(); b->d_dense.release();
     b->d_outs.release(); b->d_counter.release(); b->d_off.release(); b->d_regions.release(); b->d_pts.release(); b->d_flags.release();
+    b->up.release(); b->up2.release(); b->down.release(); b->flags_pin.release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->ev_wait) cudaEventDestroy(b->ev_wait);
     delete b;
 }
 
@@ -76,6 +114,7 @@ extern "C" int lb2_sdp_create(lb2_ctx* ctx, const lb2_sdp_para* para, int64_t n_
     b->ctx = ctx;
     cudaError_t e = cudaEventCreate(&b->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_wait, cudaEventDisableTiming);
     if (e != cudaSuccess) { lb2_sdp_destroy(b); return set_error("lb2_sdp_create: %s", cudaGetErrorString(e)); }
     if (lb2_sdp_reset(b, para, n_reads, reads, seed_id, map_n, hits)) { lb2_sdp_destroy(b); return 1; }
     *out = b;
@@ -95,8 +134,8 @@ extern "C" int lb2_sdp_reset(lb2_sdp_batch* b, const lb2_sdp_para* para, int64_t
     CU(cudaSetDevice(ctx_device(ctx)));
     b->para = *para; b->n = n_reads;
     b->h2d = b->d2h = b->pairs = 0;
-    b->reads.resize(n_reads);
-    int64_t n_seeds = 0, n_hits = 0, scratch = 0;
+    // pass 1: validate, count
+    int64_t n_seeds = 0, n_hits = 0;
     for (int64_t r = 0; r < n_reads; ++r) {
         const lb2_sdp_read& rd = reads[r];
         if (rd.seed_out < 0 || rd.seed_first < 0 || rd.hit_first < 0) return set_error("lb2_sdp_reset: read %lld: negative field", (long long)r);
@@ -108,21 +147,33 @@ extern "C" int lb2_sdp_reset(lb2_sdp_batch* b, const lb2_sdp_para* para, int64_t
             H += m;
         }
         if (H > (1 << 26)) return set_error("lb2_sdp_reset: read %lld has %lld hits", (long long)r, (long long)H);
-        DRead& d = b->reads[r];
-        d.seed_out = rd.seed_out; d.seed_all = rd.seed_all; d.read_len = rd.read_len; d.n_hits = (int32_t)H;
-        d.n_region = 0; d.pad = 0; d.region_first = 0;
-        d.seed_base = n_seeds; d.hoff_base = n_seeds + r; d.hit_base = n_hits; d.scratch = scratch;
         n_seeds += rd.seed_out; n_hits += H;
-        scratch += make_layout((int)H, rd.seed_out, para->ske_max).total;
     }
     b->n_seeds = n_seeds; b->n_hits = n_hits;
-    // packed copies: seeds / hits of the reads in batch order, plus the derived index arrays
-    std::vector<int32_t> h_sid(n_seeds), h_mn(n_seeds), h_hoff(n_seeds + n_reads), h_hseed(n_hits), h_rflat(n_hits);
-    std::vector<lb2_sdp_hit> h_hits(n_hits);
+    // the page-locked arena of this load: read descriptors, launch order, seeds / hits of the reads in batch order and
+    // the derived index arrays.  It stays untouched until the next reset, so nothing below waits for the copies.
+    const size_t o_reads = 0, o_order = o_reads + up64(sizeof(DRead) * (size_t)n_reads), o_sid = o_order + up64(4 * (size_t)n_reads),
+                 o_mn = o_sid + up64(4 * (size_t)n_seeds), o_hoff = o_mn + up64(4 * (size_t)n_seeds),
+                 o_hseed = o_hoff + up64(4 * (size_t)(n_seeds + n_reads)), o_rflat = o_hseed + up64(4 * (size_t)n_hits),
+                 o_hits = o_rflat + up64(4 * (size_t)n_hits), o_end = o_hits + up64(sizeof(lb2_sdp_hit) * (size_t)n_hits);
+    {
+        cudaError_t e0 = b->up.reserve(o_end + 64);
+        if (e0 != cudaSuccess) return set_error("lb2_sdp_reset: pinned staging: %s", cudaGetErrorString(e0));
+    }
+    b->reads = reinterpret_cast<DRead*>(b->up.p + o_reads);
+    int32_t* h_order = reinterpret_cast<int32_t*>(b->up.p + o_order);
+    int32_t* h_sid = reinterpret_cast<int32_t*>(b->up.p + o_sid); int32_t* h_mn = reinterpret_cast<int32_t*>(b->up.p + o_mn);
+    int32_t* h_hoff = reinterpret_cast<int32_t*>(b->up.p + o_hoff); int32_t* h_hseed = reinterpret_cast<int32_t*>(b->up.p + o_hseed);
+    int32_t* h_rflat = reinterpret_cast<int32_t*>(b->up.p + o_rflat);
+    lb2_sdp_hit* h_hits = reinterpret_cast<lb2_sdp_hit*>(b->up.p + o_hits);
+    int64_t at_seed = 0, at_hit = 0, scratch = 0;
     for (int64_t r = 0; r < n_reads; ++r) {
         const lb2_sdp_read& rd = reads[r];
-        const DRead& d = b->reads[r];
-        int32_t* hoff = h_hoff.data() + d.hoff_base;
+        DRead& d = b->reads[r];
+        d.seed_out = rd.seed_out; d.seed_all = rd.seed_all; d.read_len = rd.read_len;
+        d.n_region = 0; d.pad = 0; d.region_first = 0;
+        d.seed_base = at_seed; d.hoff_base = at_seed + r; d.hit_base = at_hit; d.scratch = scratch;
+        int32_t* hoff = h_hoff + d.hoff_base;
         int acc = 0;
         for (int i = 0; i < rd.seed_out; ++i) {
             h_sid[d.seed_base + i] = seed_id[rd.seed_first + i];
@@ -133,35 +184,33 @@ extern "C" int lb2_sdp_reset(lb2_sdp_batch* b, const lb2_sdp_para* para, int64_t
             acc += m;
         }
         hoff[rd.seed_out] = acc;
-        if (acc) memcpy(h_hits.data() + d.hit_base, hits + rd.hit_first, (size_t)acc * sizeof(lb2_sdp_hit));
+        d.n_hits = acc;
+        if (acc) memcpy(h_hits + d.hit_base, hits + rd.hit_first, (size_t)acc * sizeof(lb2_sdp_hit));
         // scan order of the predecessor loops (src/lamsa_dp_con.c:713-714): seeds descending, hits ascending
         int q = 0;
         for (int i = rd.seed_out - 1; i >= 0; --i)
             for (int p = hoff[i]; p < hoff[i + 1]; ++p) h_rflat[d.hit_base + q++] = p;
+        at_seed += rd.seed_out; at_hit += acc;
+        scratch += make_layout(acc, rd.seed_out, para->ske_max).total;
     }
-    b->order.resize(n_reads);
-    std::iota(b->order.begin(), b->order.end(), 0);
-    std::stable_sort(b->order.begin(), b->order.end(), [&](int32_t x, int32_t y) { return b->reads[x].n_hits > b->reads[y].n_hits; });
+    std::iota(h_order, h_order + n_reads, 0);
+    std::stable_sort(h_order, h_order + n_reads, [&](int32_t x, int32_t y) { return b->reads[x].n_hits > b->reads[y].n_hits; });
 
     cudaStream_t st = ctx_stream(ctx);
-#define UP(dst, src, cnt) do { auto e1_ = (dst).reserve(cnt); if (e1_ != cudaSuccess) return set_error("lb2_sdp_reset: cudaMalloc: %s", cudaGetErrorString(e1_)); \
-        if ((cnt) > 0) { auto e2_ = cudaMemcpyAsync((dst).p, (src), (size_t)(cnt) * sizeof(*(dst).p), cudaMemcpyHostToDevice, st); \
-        if (e2_ != cudaSuccess) return set_error("lb2_sdp_reset: H2D: %s", cudaGetErrorString(e2_)); \
-        b->h2d += (int64_t)(cnt) * sizeof(*(dst).p); } } while (0)
-    UP(b->d_reads, b->reads.data(), n_reads);
-    UP(b->d_order, b->order.data(), n_reads);
-    UP(b->d_seed_id, h_sid.data(), n_seeds);
-    UP(b->d_map_n, h_mn.data(), n_seeds);
-    UP(b->d_hoff, h_hoff.data(), n_seeds + n_reads);
-    UP(b->d_hseed, h_hseed.data(), n_hits);
-    UP(b->d_rflat, h_rflat.data(), n_hits);
-    UP(b->d_hits, h_hits.data(), n_hits);
-#undef UP
-    cudaError_t e = b->d_scratch.reserve((size_t)scratch);
+    cudaError_t e = b->d_up.reserve(o_end + 64);
+    if (e != cudaSuccess) return set_error("lb2_sdp_reset: cudaMalloc: %s", cudaGetErrorString(e));
+    b->d_reads.point_at(b->d_up.p + o_reads); b->d_order.point_at(b->d_up.p + o_order); b->d_seed_id.point_at(b->d_up.p + o_sid);
+    b->d_map_n.point_at(b->d_up.p + o_mn); b->d_hoff.point_at(b->d_up.p + o_hoff); b->d_hseed.point_at(b->d_up.p + o_hseed);
+    b->d_rflat.point_at(b->d_up.p + o_rflat); b->d_hits.point_at(b->d_up.p + o_hits);
+    if (o_end) {
+        e = cudaMemcpyAsync(b->d_up.p, b->up.p, o_end, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return set_error("lb2_sdp_reset: H2D: %s", cudaGetErrorString(e));
+        b->h2d += (int64_t)o_end;
+    }
+    e = b->d_scratch.reserve((size_t)scratch);
     if (e == cudaSuccess) e = b->d_outs.reserve(n_reads);
     if (e == cudaSuccess) e = b->d_counter.reserve(1);
     if (e == cudaSuccess) e = b->d_off.reserve(n_reads + 1);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // the host vectors above go out of scope
     if (e != cudaSuccess) return set_error("lb2_sdp_reset: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -182,7 +231,7 @@ static int run_stage(lb2_sdp_batch* b, int stage, const int32_t** stream, const 
     CU(cudaSetDevice(ctx_device(b->ctx)));
     const int n = (int)b->n;
     b->off.assign(n + 1, 0);
-    b->stream.clear();
+    b->stream = nullptr; b->outs = nullptr;
     b->pairs = 0;
     if (kernel_ms) *kernel_ms = 0.f;
     if (n > 0) {
@@ -197,31 +246,38 @@ static int run_stage(lb2_sdp_batch* b, int stage, const int32_t** stream, const 
         sdp_scan_kernel<<<1, 1024, 0, st>>>(b->d_outs.p, n, b->d_off.p);
         CU(cudaGetLastError());
         CU(cudaEventRecord(b->ev1, st));
-        b->outs.resize(n);
-        std::vector<long long> h_off(n + 1);
-        CU(cudaMemcpyAsync(b->outs.data(), b->d_outs.p, (size_t)n * sizeof(DOut), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h_off.data(), b->d_off.p, (size_t)(n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        // read-backs land in page-locked memory: [outs][offsets][stream words]; the stream's size is known after the first wait
+        const size_t o_outs = 0, o_off = up64(sizeof(DOut) * (size_t)n), o_dense = o_off + up64(8 * ((size_t)n + 1));
+        CU(b->down.reserve(o_dense + 64));
+        CU(cudaMemcpyAsync(b->down.p + o_outs, b->d_outs.p, (size_t)n * sizeof(DOut), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(b->down.p + o_off, b->d_off.p, (size_t)(n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CU(wait_stream(st, b->ev_wait));
         b->d2h += (int64_t)n * sizeof(DOut) + (int64_t)(n + 1) * 8;
+        const DOut* outs = reinterpret_cast<const DOut*>(b->down.p + o_outs);
+        const long long* h_off = reinterpret_cast<const long long*>(b->down.p + o_off);
         for (int r = 0; r < n; ++r) {
-            if (b->outs[r].err) return set_error("lb2_sdp: read %d: %s", r, err_name(b->outs[r].err));
-            b->pairs += b->outs[r].pairs;
+            if (outs[r].err) return set_error("lb2_sdp: read %d: %s", r, err_name(outs[r].err));
+            b->pairs += outs[r].pairs;
         }
+        for (int r = 0; r <= n; ++r) b->off[r] = h_off[r];
         const long long total = h_off[n];
         CU(b->d_dense.reserve((size_t)total));
-        b->stream.resize((size_t)total);
         if (total > 0) {
+            if (b->down.cap < o_dense + (size_t)total * 4 + 64) {       // grow the landing zone (outs / offsets were consumed above)
+                CU(b->down.reserve(o_dense + (size_t)total * 4 + 64));
+            }
             const int threads = 256, blocks = (int)(((long long)n * 32 + threads - 1) / threads);
             sdp_gather_kernel<<<blocks, threads, 0, st>>>(b->d_reads.p, b->d_outs.p, n, b->para.ske_max, b->d_scratch.p, b->d_off.p, b->d_dense.p);
             CU(cudaGetLastError());
-            CU(cudaMemcpyAsync(b->stream.data(), b->d_dense.p, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
+            CU(cudaMemcpyAsync(b->down.p + o_dense, b->d_dense.p, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(wait_stream(st, b->ev_wait));
             b->d2h += total * 4;
         }
-        for (int r = 0; r <= n; ++r) b->off[r] = h_off[r];
+        b->stream = reinterpret_cast<const int32_t*>(b->down.p + o_dense);
         if (kernel_ms) CU(cudaEventElapsedTime(kernel_ms, b->ev0, b->ev1));
     }
-    if (stream) *stream = b->stream.data();
+    static const int32_t none = 0;
+    if (stream) *stream = b->stream ? b->stream : &none;
     if (off) *off = b->off.data();
     return 0;
 }
@@ -293,10 +349,18 @@ extern "C" int lb2_sdp_run_remain(lb2_sdp_batch* b, const lb2_sdp_read* reads, c
     cudaStream_t st = ctx_stream(b->ctx);
     CU(b->d_regions.reserve(h_regions.size()));
     CU(b->d_pts.reserve(h_pts.size()));
-    if (!h_regions.empty()) CU(cudaMemcpyAsync(b->d_regions.p, h_regions.data(), h_regions.size() * sizeof(DRegion), cudaMemcpyHostToDevice, st));
-    if (!h_pts.empty()) CU(cudaMemcpyAsync(b->d_pts.p, h_pts.data(), h_pts.size() * sizeof(DPoint), cudaMemcpyHostToDevice, st));
-    if (b->n > 0) CU(cudaMemcpyAsync(b->d_reads.p, b->reads.data(), (size_t)b->n * sizeof(DRead), cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));
+    // through the page-locked staging of this stage (untouched until the next remain stage: no wait here)
+    const size_t o_pts = up64(h_regions.size() * sizeof(DRegion));
+    CU(b->up2.reserve(o_pts + up64(h_pts.size() * sizeof(DPoint)) + 64));
+    if (!h_regions.empty()) {
+        memcpy(b->up2.p, h_regions.data(), h_regions.size() * sizeof(DRegion));
+        CU(cudaMemcpyAsync(b->d_regions.p, b->up2.p, h_regions.size() * sizeof(DRegion), cudaMemcpyHostToDevice, st));
+    }
+    if (!h_pts.empty()) {
+        memcpy(b->up2.p + o_pts, h_pts.data(), h_pts.size() * sizeof(DPoint));
+        CU(cudaMemcpyAsync(b->d_pts.p, b->up2.p + o_pts, h_pts.size() * sizeof(DPoint), cudaMemcpyHostToDevice, st));
+    }
+    if (b->n > 0) CU(cudaMemcpyAsync(b->d_reads.p, b->reads, (size_t)b->n * sizeof(DRead), cudaMemcpyHostToDevice, st));
     b->h2d += (int64_t)(h_regions.size() * sizeof(DRegion) + h_pts.size() * sizeof(DPoint) + (size_t)b->n * sizeof(DRead));
     return run_stage(b, 2, stream, off, kernel_ms);
 }
@@ -315,12 +379,19 @@ static int tracked_io(lb2_sdp_batch* b, uint8_t* flags, int set) {
     CU(cudaSetDevice(ctx_device(b->ctx)));
     cudaStream_t st = ctx_stream(b->ctx);
     CU(b->d_flags.reserve((size_t)b->n_hits));
-    if (set) { CU(cudaMemcpyAsync(b->d_flags.p, flags, (size_t)b->n_hits, cudaMemcpyHostToDevice, st)); b->h2d += b->n_hits; }
+    CU(b->flags_pin.reserve((size_t)b->n_hits + 64));
+    if (set) {      // no wait: the staging is not written again before the stage that follows has been waited for
+        memcpy(b->flags_pin.p, flags, (size_t)b->n_hits);
+        CU(cudaMemcpyAsync(b->d_flags.p, b->flags_pin.p, (size_t)b->n_hits, cudaMemcpyHostToDevice, st)); b->h2d += b->n_hits;
+    }
     const int threads = 256, blocks = (int)((b->n * 32 + threads - 1) / threads);
     sdp_tracked_kernel<<<blocks, threads, 0, st>>>(b->d_reads.p, (int)b->n, b->para.ske_max, b->d_scratch.p, b->d_flags.p, set);
     CU(cudaGetLastError());
-    if (!set) { CU(cudaMemcpyAsync(flags, b->d_flags.p, (size_t)b->n_hits, cudaMemcpyDeviceToHost, st)); b->d2h += b->n_hits; }
-    CU(cudaStreamSynchronize(st));
+    if (!set) {
+        CU(cudaMemcpyAsync(b->flags_pin.p, b->d_flags.p, (size_t)b->n_hits, cudaMemcpyDeviceToHost, st)); b->d2h += b->n_hits;
+        CU(wait_stream(st, b->ev_wait));
+        memcpy(flags, b->flags_pin.p, (size_t)b->n_hits);
+    }
     return 0;
 }
 extern "C" int lb2_sdp_get_tracked(lb2_sdp_batch* b, uint8_t* flags) { return tracked_io(b, flags, 0); }

@@ -6,6 +6,8 @@
 // (src/bwt_aln.c:103-148, src/lamsa_aln.c:609) live here too: they operate on caller-owned host
 // structs and never were part of the device path.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -156,8 +158,14 @@ void serve(lb2::SdpRequest* r) {
 
 // All requests of `batch` (same stage, same parameters) as ONE GPU batch.  Each OS thread keeps one
 // grow-only batch object, so steady state allocates nothing.
+// where the time of the chaining batches goes (LB2_FIBER_STATS): seconds of flattening the requests, of loading the
+// batch object (H2D), of the stage (kernels + read-back; the kernels' own event time beside it) and of handing back
+namespace lb2 { std::atomic<long long> g_sdp_ns[5] = {}; }
 void lb2::dropin_submit_sdp(std::vector<lb2::SdpRequest*>& batch) {
     if (batch.empty()) return;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ns = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+    const auto t_begin = now();
     // one grow-only batch object per context (= per scheduler thread, or the process-wide one, which the
     // reference's pthread workers share: those calls are serialised here, like the DP calls in ksw_dropin.cu)
     static std::mutex shared_ctx_mu;
@@ -196,6 +204,7 @@ void lb2::dropin_submit_sdp(std::vector<lb2::SdpRequest*>& batch) {
         if (stage == 2) flags.insert(flags.end(), ws->tracked.begin(), ws->tracked.end());
     }
     const lb2_sdp_para* P = &batch[0]->ws->para;
+    const auto t_flat = now();
     if (!tl_batch) {
         if (lb2_sdp_create(my_ctx, P, n, reads.data(), sid.data(), mn.data(), hits.data(), &tl_batch)) die("chaining batch");
         std::lock_guard<std::mutex> lk(batch_mu);
@@ -203,14 +212,17 @@ void lb2::dropin_submit_sdp(std::vector<lb2::SdpRequest*>& batch) {
     }
     else if (lb2_sdp_reset(tl_batch, P, n, reads.data(), sid.data(), mn.data(), hits.data())) die("chaining batch");
     const int32_t* w; const int64_t* off;
+    const auto t_load = now();
+    float kms = 0.f;
     if (stage == 1) {
-        if (lb2_sdp_run_bcc(tl_batch, &w, &off, nullptr)) die("frag_line_BCC");
+        if (lb2_sdp_run_bcc(tl_batch, &w, &off, &kms)) die("frag_line_BCC");
         flags.resize(hits.size());
         if (lb2_sdp_get_tracked(tl_batch, flags.data())) die("frag_line_BCC");
     } else {
         if (lb2_sdp_set_tracked(tl_batch, flags.data())) die("frag_line_remain");
-        if (lb2_sdp_run_remain(tl_batch, reads.data(), regs.data(), &w, &off, nullptr)) die("frag_line_remain");
+        if (lb2_sdp_run_remain(tl_batch, reads.data(), regs.data(), &w, &off, &kms)) die("frag_line_remain");
     }
+    const auto t_run = now();
     for (int64_t i = 0; i < n; ++i) {
         lb2::SdpRequest* q = batch[(size_t)i];
         q->stream.assign(w + off[i], w + off[i + 1]);
@@ -219,6 +231,8 @@ void lb2::dropin_submit_sdp(std::vector<lb2::SdpRequest*>& batch) {
             q->ws->tracked.assign(flags.begin() + h0, flags.begin() + h0 + hn);
         }
     }
+    lb2::g_sdp_ns[0] += ns(t_begin, t_flat); lb2::g_sdp_ns[1] += ns(t_flat, t_load); lb2::g_sdp_ns[2] += ns(t_load, t_run);
+    lb2::g_sdp_ns[3] += (long long)(kms * 1e6); lb2::g_sdp_ns[4] += ns(t_run, now());
 }
 
 extern "C" int frag_line_BCC(lb2_ref_map_msg* m_msg, lb2_ref_frag_msg** f_msg, lb2_ref_per_para* APP, lamsa_aln_para* AP,
