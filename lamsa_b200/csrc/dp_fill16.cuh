@@ -332,7 +332,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
             }
             // lanes right of `end` hold nothing of this row (and would alias live slots of the window)
             if (r0 <= re) { PVec<NP>::st(hb + s0, H); PVec<NP>::st(eb + s0, E); }
-            if (want && r0 < re) {
+            if (want) {
                 if (NP == 2) *reinterpret_cast<uint16_t*>(zp) = (uint16_t)dirw;
                 else *reinterpret_cast<uint32_t*>(zp) = dirw;
             }

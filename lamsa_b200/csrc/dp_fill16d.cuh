@@ -287,7 +287,11 @@ __device__ void fill_bundle16_dyn(const DTask* __restrict__ tasks, const int32_t
                 H[p] = EXT ? blend(sh, H[p], cm[p]) : sh;
             }
             if (ta && r0 <= re) { PVec<NP>::st(hb + s0, H); PVec<NP>::st(eb + s0, E); }
-            if (ta && want && r0 < re) {
+            // every lane of a tile pass stores, also those right of the band: a group's stores then fill whole 32-byte
+            // sectors and nothing has to be read back to merge a partly written one when it leaves the L2 (ncu: 1.2 GB of
+            // DRAM reads per 200 k-task launch of the dominant kernel came from exactly that); the bytes lie inside the
+            // row's allocation and the traceback never looks outside [beg, end)
+            if (ta && want) {
                 if (NP == 2) *reinterpret_cast<uint16_t*>(zp) = (uint16_t)dirw;
                 else *reinterpret_cast<uint32_t*>(zp) = dirw;
             }

@@ -240,7 +240,7 @@ __device__ void fill_bundle16(const DTask* __restrict__ tasks, const int32_t* __
                 H[p] = EXT ? blend(sh, H[p], cm[p]) : sh;
             }
             if (ta && r0 <= re) { PVec<NP>::st(hb + s0, H); PVec<NP>::st(eb + s0, E); }
-            if (ta && want && r0 < re) {
+            if (ta && want) {
                 if (NP == 2) *reinterpret_cast<uint16_t*>(zp) = (uint16_t)dirw;
                 else *reinterpret_cast<uint32_t*>(zp) = dirw;
             }
