@@ -69,7 +69,7 @@ __device__ __forceinline__ TargetSrc make_target(const struct DTask& T, const ui
 // extension, bit3 F was an extension.  The reference byte (src/ksw.c:556) is
 // nib&3 | (nib&4) | (nib&8)<<2.
 __host__ __device__ inline uint64_t ext_meta_bytes(int tlen) {
-    return ((uint64_t)tlen * 8 + 15) & ~uint64_t(15);
+    return ((uint64_t)tlen * 8 + 31) & ~uint64_t(31);      // 32: the direction rows behind it start on a sector boundary
 }
 
 // bytes of direction storage per lane per tile (G nibbles; one byte when G==1)

@@ -201,7 +201,7 @@ inline int classify_task(const lb2_task& t, int64_t l_pac, PackedTask& o, char* 
         const int G = 1 << cs;
         uint64_t z = (uint64_t)t.tlen * d.row_chunks * 32 * dir_lane_bytes(G);
         if (t.kind == LB2_KIND_EXTEND) z += ext_meta_bytes(t.tlen);
-        o.zsz = (z + 15) & ~uint64_t(15);
+        o.zsz = (z + 31) & ~uint64_t(31);                 // tasks start on a 32-byte sector boundary
         o.ctmpw = t.qlen + t.tlen + 2;
     } else { o.zsz = 0; o.ctmpw = 0; }
     const int64_t cost = (int64_t)t.tlen * ncol + 1;                 // ~3 bins per octave, heaviest first
