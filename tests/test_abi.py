@@ -164,3 +164,25 @@ def test_no_gpu_fails_loudly(lib):
     assert b"no CPU path" in lib.lb2_last_error() or b"CUDA" in lib.lb2_last_error()
     with pytest.raises(RuntimeError):
         lamsa_b200.Context(0)
+
+
+def test_pool_pack_copies_sequences_in_task_order(lib):
+    """lb2_pool_pack (host only): the sequences of scattered task records end up in ONE pool, task by task, and the
+    records point into it (the layout under which a chunk of lb2_dp_run_pool uploads one tight range)."""
+    import numpy as np
+    from lamsa_b200 import workload
+    tasks, keep = workload.gen_microbench(3000, seed=9, qmin=0, qmax=120)
+    ptasks, pool = workload.pool_tasks(tasks, keep)
+    base = pool.ctypes.data
+    q_off = (ptasks["query"] - np.uint64(base)).astype(np.int64)
+    t_off = (ptasks["target"] - np.uint64(base)).astype(np.int64)
+    assert (q_off >= 0).all() and (t_off + ptasks["tlen"] <= pool.nbytes).all()
+    assert (np.diff(q_off) > 0).all() and (t_off == q_off + ptasks["qlen"]).all()
+    import ctypes as C
+    for i in (0, 1, 17, 2999):
+        for f, n in (("query", "qlen"), ("target", "tlen")):
+            a = np.ctypeslib.as_array(C.cast(int(tasks[f][i]), C.POINTER(C.c_uint8)), shape=(max(int(tasks[n][i]), 1),))[: int(tasks[n][i])]
+            b = np.ctypeslib.as_array(C.cast(int(ptasks[f][i]), C.POINTER(C.c_uint8)), shape=(max(int(tasks[n][i]), 1),))[: int(tasks[n][i])]
+            assert (a == b).all()
+    for f in ("kind", "qlen", "tlen", "w", "h0", "mat"):
+        assert (ptasks[f] == tasks[f]).all()
