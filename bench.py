@@ -372,9 +372,13 @@ def main():
 
     traffic, traffic_note = None, "no ncu capture committed"
     try:        # dram bytes of the dominant kernel from the committed ncu capture, scaled to this task count
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        tj = json.load(open(tp if os.path.exists(tp) else os.path.join(ROOT, "profiles", "r01_traffic.json")))
         traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * a.tasks / tj["tasks"]
         traffic_note = f"{tj['dominant_kernel']}: dram read+write per launch from {tj['source']}, scaled x{a.tasks / tj['tasks']:g}"
+        if "algorithmic_bytes" in tj:
+            traffic_note += (f"; algorithmic bytes of that launch {tj['algorithmic_bytes']:.3e} (ratio {(tj['dram_bytes_read'] + tj['dram_bytes_write']) / tj['algorithmic_bytes']:.2f}), "
+                             f"{tj.get('warp_instructions_per_cell')} warp instructions per cell")
     except Exception:
         pass
     if rank == 0:

@@ -52,3 +52,23 @@ def test_gpu_hash_split_map_matches_reference_golden(ctx):
         assert len(cig) == len(want) and (cig == want).all(), f"case {k}: CIGAR differs"
         flags |= res
     assert flags & 2
+
+
+def test_gpu_hash_edge_cases(ctx):
+    """windows / reads shorter than a k-mer, empty windows, a read of exactly one k-mer, identical sequences with a
+    k-mer that repeats beyond the 50-hit cap everywhere (no seeds survive)"""
+    rng = np.random.default_rng(5)
+    base = dict(ref_offset=0, hash_len=10, hash_step=10, split_len=100, head=1, tail=1)
+    ref = rng.integers(0, 4, size=300, dtype=np.uint8)
+    cases = [dict(base, ref=ref, read=ref[:5].copy()),                         # read shorter than a k-mer: no seeds
+             dict(base, ref=ref[:4].copy(), read=ref[:60].copy()),               # window shorter than a k-mer
+             dict(base, ref=np.zeros(0, np.uint8), read=ref[:60].copy()),        # empty window
+             dict(base, ref=ref, read=ref[40:50].copy()),                        # one k-mer
+             dict(base, ref=np.zeros(400, np.uint8), read=np.zeros(200, np.uint8)),      # poly-A: every k-mer beyond the cap
+             dict(base, ref=ref, read=ref.copy(), head=0, tail=0),
+             dict(base, ref=ref, read=np.full(100, 4, np.uint8))]                # all-N read (hashes as G)
+    lines, hits = _hash.gpu_lines(ctx, cases)
+    for k, c in enumerate(cases):
+        want = _hash.oracle_line(c)
+        assert lines[k].shape == want.shape and (lines[k] == want).all(), f"edge case {k}"
+    assert len(lines[0]) == 0 and len(lines[1]) == 0 and len(lines[2]) == 0 and hits[4] == 0 and len(lines[5]) > 20

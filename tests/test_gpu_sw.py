@@ -63,3 +63,22 @@ def test_gpu_sw_batch_and_profile_reuse(ctx):
             want = _sw.oracle_align2(dict(c0, t=c["t"], o_del=5, e_del=2, o_ins=5, e_ins=2, xtra=_sw.XBYTE if size == 1 else 0))
             assert r == want
         libc.free(prof)
+
+
+def test_gpu_sw_edge_cases(ctx):
+    """one-base sequences, an empty target, a query longer than the target, protein-sized alphabets"""
+    rng = np.random.default_rng(6)
+    mat5 = np.full((5, 5), -3, np.int8); np.fill_diagonal(mat5, 1)
+    base = dict(m=5, mat=mat5.reshape(-1), o_del=5, e_del=2, o_ins=5, e_ins=2)
+    cases = []
+    for xtra in (0, _sw.XBYTE, _sw.XSTART, _sw.XBYTE | _sw.XSTART | _sw.XSUBO | 3):
+        cases += [dict(base, q=np.array([1], np.uint8), t=np.array([1], np.uint8), xtra=xtra),
+                  dict(base, q=np.array([1], np.uint8), t=np.array([2], np.uint8), xtra=xtra),
+                  dict(base, q=rng.integers(0, 4, size=40, dtype=np.uint8), t=np.zeros(0, np.uint8), xtra=xtra),
+                  dict(base, q=rng.integers(0, 4, size=300, dtype=np.uint8), t=rng.integers(0, 4, size=7, dtype=np.uint8), xtra=xtra)]
+    m20 = rng.integers(-4, 6, size=(20, 20)).astype(np.int8); m20 = np.minimum(m20, m20.T); np.fill_diagonal(m20, 5)
+    for xtra in (0, _sw.XBYTE | _sw.XSTART):
+        t = rng.integers(0, 20, size=400, dtype=np.uint8)
+        cases.append(dict(m=20, mat=m20.reshape(-1), o_del=10, e_del=1, o_ins=10, e_ins=1, q=t[100:180].copy(), t=t, xtra=xtra))
+    for k, c in enumerate(cases):
+        assert _sw.gpu_align2(c) == _sw.oracle_align2(c), f"edge case {k}"
