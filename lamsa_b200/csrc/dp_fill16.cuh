@@ -233,9 +233,6 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
         const int ntile = end >= base ? ((end - base) >> (5 + GS)) + 1 : 0;
         uint32_t carryF = dup2(EXT ? FINIT + rb * e_ins : kNeg16);            // seeded with F(i,beg) in the u-domain
         uint32_t carryH = 0;                                   // left neighbour's last pair, previous tile
-        uint32_t RO1[NP], NRO[NP];
-#pragma unroll
-        for (int p = 0; p < NP; ++p) { RO1[p] = RO1_0[p]; NRO[p] = NRO_0[p]; }
         uint32_t mrowmax[NP];                                  // extension: running row maxima per pair
         int mt_lo[NP], mt_hi[NP];                              // tile of the last (tie-)update
 #pragma unroll
@@ -269,7 +266,7 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
                     M[p] = __vadd2(H[p], s);                     // hat domain: s already holds s + e_ins
                     tI[p] = __vadd2(M[p], N_O_INS);              // u^ = M^ - o_ins
                 }
-                const uint32_t u = EXT ? __vadd2(tI[p], RO1[p]) : tI[p];
+                const uint32_t u = EXT ? __vadd2(tI[p], RO1_0[p]) : tI[p];
                 // exclusive prefix inside the lane: (run, max(run, u.lo))
                 pre[p] = __vmaxs2(run, prmt(u, NEGP, 0x1054));
                 run = __vimax3_s16x2(run, u, prmt(u, 0u, 0x1032));
@@ -282,12 +279,13 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
             if (lane == 0) pin = NEGP;
             pin = __vmaxs2(pin, carryF);
             carryF = __vmaxs2(carryF, __shfl_sync(kFull, incl, 31));
+            if (EXT) carryF = __vadd2(carryF, N_TILE_STEP);          // scan offsets are tile-relative: move the carry into the next tile's domain
 
             uint32_t dirw = 0;
             uint32_t Hn[NP];
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-                const uint32_t F = EXT ? __vadd2(__vmaxs2(pin, pre[p]), NRO[p]) : __vmaxs2(pin, pre[p]);
+                const uint32_t F = EXT ? __vadd2(__vmaxs2(pin, pre[p]), NRO_0[p]) : __vmaxs2(pin, pre[p]);
                 bool a_hi, a_lo, b_hi, b_lo, c_hi, c_lo, d_hi, d_lo;
                 uint32_t h;
                 if (EXT) {                           // ties: E over M, F over both (src/ksw.c:738-741)
@@ -315,10 +313,6 @@ __device__ void fill_task16(const DTask& T, const uint8_t* __restrict__ pool, co
                     mrowmax[p] = __vibmax_s16x2(hm, mrowmax[p], &m_hi, &m_lo);
                     if (m_lo) mt_lo[p] = tile;
                     if (m_hi) mt_hi[p] = tile;
-                }
-                if (EXT) {
-                    RO1[p] = __vadd2(RO1[p], TILE_STEP);
-                    NRO[p] = __vadd2(NRO[p], N_TILE_STEP);
                 }
             }
             // shifted H row: slot j <- H(i, j-1); my first slot takes the left neighbour's last column

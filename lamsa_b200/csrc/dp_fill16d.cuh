@@ -190,9 +190,6 @@ __device__ void fill_bundle16_dyn(const DTask* __restrict__ tasks, const int32_t
         const int ntile_max = __reduce_max_sync(kFull, ntile);
         uint32_t carryF = dup2(EXT ? FINIT + rb * e_ins : kNeg16);
         uint32_t carryH = 0;
-        uint32_t RO1[NP], NRO[NP];
-#pragma unroll
-        for (int p = 0; p < NP; ++p) { RO1[p] = RO1_0[p]; NRO[p] = NRO_0[p]; }
         uint32_t mrowmax[NP];
         int mt_lo[NP], mt_hi[NP];
 #pragma unroll
@@ -225,7 +222,7 @@ __device__ void fill_bundle16_dyn(const DTask* __restrict__ tasks, const int32_t
                     M[p] = __vadd2(H[p], s);                     // hat domain: s already holds s + e_ins
                     tI[p] = __vadd2(M[p], N_O_INS);              // u^ = M^ - o_ins
                 }
-                const uint32_t u = EXT ? __vadd2(tI[p], RO1[p]) : tI[p];
+                const uint32_t u = EXT ? __vadd2(tI[p], RO1_0[p]) : tI[p];
                 pre[p] = __vmaxs2(run, prmt(u, NEGP, 0x1054));
                 run = __vimax3_s16x2(run, u, prmt(u, 0u, 0x1032));
             }
@@ -235,13 +232,16 @@ __device__ void fill_bundle16_dyn(const DTask* __restrict__ tasks, const int32_t
             uint32_t pin = __shfl_up_sync(kFull, incl, 1, L);
             if (gl == 0) pin = NEGP;
             pin = __vmaxs2(pin, carryF);
+            // the scan offsets are TILE-relative (column index inside the tile): the carry moves into the next tile's domain,
+            // one subtraction per tile instead of two offset updates per register
             carryF = __vmaxs2(carryF, __shfl_sync(kFull, incl, L - 1, L));
+            if (EXT) carryF = __vadd2(carryF, N_TILE_STEP);
 
             uint32_t dirw = 0;
             uint32_t Hn[NP];
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-                const uint32_t F = EXT ? __vadd2(__vmaxs2(pin, pre[p]), NRO[p]) : __vmaxs2(pin, pre[p]);
+                const uint32_t F = EXT ? __vadd2(__vmaxs2(pin, pre[p]), NRO_0[p]) : __vmaxs2(pin, pre[p]);
                 bool a_hi, a_lo, b_hi, b_lo, c_hi, c_lo, d_hi, d_lo;
                 uint32_t h;
                 if (EXT) {
@@ -266,16 +266,10 @@ __device__ void fill_bundle16_dyn(const DTask* __restrict__ tasks, const int32_t
                 if (EXT) {
                     bool m_hi, m_lo;
                     const uint32_t hm = h | ~am[p];
-                    const uint32_t nm = __vibmax_s16x2(hm, mrowmax[p], &m_hi, &m_lo);
-                    if (ta) {
-                        mrowmax[p] = nm;
-                        if (m_lo) mt_lo[p] = tile;
-                        if (m_hi) mt_hi[p] = tile;
-                    }
-                }
-                if (EXT) {
-                    RO1[p] = __vadd2(RO1[p], TILE_STEP);
-                    NRO[p] = __vadd2(NRO[p], N_TILE_STEP);
+                    // no `ta` guard: beyond the group's last tile the mask am is empty, hm reads -1 and never wins
+                    mrowmax[p] = __vibmax_s16x2(hm, mrowmax[p], &m_hi, &m_lo);
+                    if (m_lo) mt_lo[p] = tile;
+                    if (m_hi) mt_hi[p] = tile;
                 }
             }
             uint32_t left = __shfl_up_sync(kFull, Hn[NP - 1], 1, L);

@@ -117,7 +117,7 @@ __device__ void fill_task_lean(const DTask& T, const uint8_t* __restrict__ pool,
         en = en > t ? en : t;
         d |= (f - e_ins) > tI ? 8u : 0u;
         if (want) {
-            if (act) zrow[r] = (uint8_t)d;
+            zrow[r & 31] = (uint8_t)d;              // all 32 lanes: one whole sector per row (ranks are distinct mod 32; cells outside the band are never read)
             if (lane == 0) rowmeta[i] = make_int2(beg, end);
         }
         cells += end > beg ? end - beg : 0;
