@@ -17,7 +17,6 @@
 #include "../../include/lamsa_b200.h"
 #include "dp_fill.cuh"
 #include "dp_fill16.cuh"
-#include "dp_fill16s.cuh"
 #include "dp_fill16d.cuh"
 #include "dp_fill_lean.cuh"
 #include "dp_trace.cuh"
@@ -117,33 +116,21 @@ typedef void (*fill_fn)(const DTask*, const int32_t*, int, const uint8_t*, const
                         const uint2*, unsigned int*, int, uint8_t*);
 static fill_fn fill_table(int kind, int var) {
     if (var == kVarBlock) return fill_lean_kernel;
-    // group kernels with dynamic refill (dp_fill16d.cuh) unless LB2_DYN=0
-    static const bool dyn = [] { const char* e = getenv("LB2_DYN"); return !(e && *e == '0'); }();
-    if (dyn && var >= 6) {
-        if (kind == kKindGlobal) switch (var) {
-            case 6: return fill16d_kernel<2, kKindGlobal, 16>;  case 7: return fill16d_kernel<2, kKindGlobal, 8>;
-            case 8: return fill16d_kernel<4, kKindGlobal, 8>;   default: return fill16d_kernel<4, kKindGlobal, 16>;
-        }
-        switch (var) {
-            case 6: return fill16d_kernel<2, kKindExtend, 16>;  case 7: return fill16d_kernel<2, kKindExtend, 8>;
-            case 8: return fill16d_kernel<4, kKindExtend, 8>;   default: return fill16d_kernel<4, kKindExtend, 16>;
-        }
-    }
     if (kind == kKindGlobal) {
         switch (var) {
             case 0: return fill_kernel<1, kKindGlobal, false>;   case 1: return fill_kernel<2, kKindGlobal, false>;
             case 2: return fill_kernel<4, kKindGlobal, false>;   case 3: return fill16_kernel<2, kKindGlobal>;
             case 4: return fill16_kernel<4, kKindGlobal>;        case 5: return fill_kernel<4, kKindGlobal, true>;
-            case 6: return fill16s_kernel<2, kKindGlobal, 16>;   case 7: return fill16s_kernel<2, kKindGlobal, 8>;
-            case 8: return fill16s_kernel<4, kKindGlobal, 8>;    default: return fill16s_kernel<4, kKindGlobal, 16>;
+            case 6: return fill16d_kernel<2, kKindGlobal, 16>;   case 7: return fill16d_kernel<2, kKindGlobal, 8>;
+            case 8: return fill16d_kernel<4, kKindGlobal, 8>;    default: return fill16d_kernel<4, kKindGlobal, 16>;
         }
     }
     switch (var) {
         case 0: return fill_kernel<1, kKindExtend, false>;   case 1: return fill_kernel<2, kKindExtend, false>;
         case 2: return fill_kernel<4, kKindExtend, false>;   case 3: return fill16_kernel<2, kKindExtend>;
         case 4: return fill16_kernel<4, kKindExtend>;        case 5: return fill_kernel<4, kKindExtend, true>;
-        case 6: return fill16s_kernel<2, kKindExtend, 16>;   case 7: return fill16s_kernel<2, kKindExtend, 8>;
-        case 8: return fill16s_kernel<4, kKindExtend, 8>;    default: return fill16s_kernel<4, kKindExtend, 16>;
+        case 6: return fill16d_kernel<2, kKindExtend, 16>;   case 7: return fill16d_kernel<2, kKindExtend, 8>;
+        case 8: return fill16d_kernel<4, kKindExtend, 8>;    default: return fill16d_kernel<4, kKindExtend, 16>;
     }
 }
 

@@ -1,13 +1,13 @@
-// dp_fill16d.cuh -- the sub-warp bundles of dp_fill16s.cuh with DYNAMIC REFILL: every L-lane group of a
-// warp walks its own task with its own row index and, when that task is over (target end reached, m == 0
-// or z-drop exit), commits it and takes the next task from the launch's atomic counter while the other
-// groups keep going.  In dp_fill16s.cuh a bundle of 32/L tasks is walked with a common row index and
-// lasts as long as its longest member; extensions end early at unpredictable rows (z-drop: the cells the
-// reference evaluates are 64 % of the static band area on the C2 workload), so there a finished group
-// idles for most of the bundle.  The per-row arithmetic is the text of fill_bundle16, unchanged; only the
-// task prologue / epilogue moved inside the loop.
+// dp_fill16d.cuh -- the packed fill of dp_fill16.cuh in SUB-WARP LANE GROUPS with dynamic refill: a warp runs 32/L tasks
+// at once (L = 8 or 16 lanes each, tiles of L*2NP columns, collectives group-scoped), so that the per-row scalar work of
+// the extension is issued once per bundle and narrow / adaptive bands do not idle most of a 32-lane tile.  Every group
+// walks its own task with its own row index and, when that task is over (target end reached, m == 0 or z-drop exit),
+// commits it and takes the next task from the launch's atomic counter while the other groups keep going: extensions end
+// early at unpredictable rows (z-drop: the cells the reference evaluates are 64 % of the static band area on the C2
+// workload), so with a common row index a finished group would idle for most of its bundle (the static-bundle build of
+// round 1 was 7 % slower and is gone).
 #pragma once
-#include "dp_fill16s.cuh"
+#include "dp_fill16.cuh"
 
 namespace lb2 {
 
